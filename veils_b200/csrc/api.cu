@@ -1,0 +1,487 @@
+// api.cu -- the C ABI of include/veils_cuda.h: plan objects, geometry queries, dispatch of the
+// compute calls to the kernel families, device-buffer / stream helpers.
+#include "../../include/veils_cuda.h"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace veils;
+
+namespace veils {
+// device copies of the plan's tables, element type = plan precision
+struct DeviceTables {
+    void *win = nullptr;
+    void *dual = nullptr;
+    double2 *tw_full = nullptr;
+    void *tw_pow2 = nullptr;
+};
+}  // namespace veils
+
+struct veils_plan {
+    Plan pl;
+};
+
+static thread_local std::string t_err;
+
+static int32_t fail(int32_t code, const std::string &msg) {
+    t_err = msg;
+    return code;
+}
+static int32_t cuda_fail(cudaError_t e, const char *what) {
+    return fail(VEILS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                          \
+    do {                                                  \
+        cudaError_t e_ = (call);                          \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+// exp(-2 pi i m / M): long-double evaluation (error ~1e-19), exact values on the axes
+static void twiddle(int64_t m, int64_t M, double *re, double *im) {
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const int64_t mm = ((m % M) + M) % M;
+    if ((4 * mm) % M == 0) {                       // multiples of a quarter turn
+        static const double c4[4] = {1, 0, -1, 0}, s4[4] = {0, 1, 0, -1};
+        const int q = (int)(4 * mm / M);
+        *re = c4[q];
+        *im = -s4[q];
+        return;
+    }
+    const long double a = two_pi * (long double)mm / (long double)M;
+    *re = (double)cosl(a);
+    *im = (double)(-sinl(a));
+}
+
+template <typename T>
+static cudaError_t upload_as(const std::vector<double> &src, void **dst) {
+    std::vector<T> tmp(src.begin(), src.end());
+    cudaError_t e = cudaMalloc(dst, tmp.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+// Create the device tables on first use.  need_dual: also resolve + upload the dual window.
+static int32_t ensure_device(Plan &pl, bool need_dual) {
+    if (need_dual) {
+        std::string e = plan_dual(pl);
+        if (!e.empty()) return fail(VEILS_ERR_NOT_INVERTIBLE, e);
+    }
+    std::lock_guard<std::mutex> g(pl.mu);
+    CU(cudaSetDevice(pl.device));
+    if (!pl.dev) {
+        DeviceTables *d = new (std::nothrow) DeviceTables();
+        if (!d) return fail(VEILS_ERR_CUDA, "out of host memory");
+        cudaError_t e = pl.precision == F32 ? upload_as<float>(pl.win, &d->win)
+                                            : upload_as<double>(pl.win, &d->win);
+        if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload window"); }
+        if (pl.pow2_path) {
+            const int64_t cnt = pow2_twiddle_count(pl.M);
+            std::vector<double> tw((size_t)cnt);
+            pow2_twiddle_fill(pl.M, tw.data());
+            e = pl.precision == F32 ? upload_as<float>(tw, &d->tw_pow2)
+                                    : upload_as<double>(tw, &d->tw_pow2);
+            if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload twiddles"); }
+        } else {
+            std::vector<double> tw((size_t)pl.M * 2);
+            for (int64_t m = 0; m < pl.M; ++m) twiddle(m, pl.M, &tw[2 * m], &tw[2 * m + 1]);
+            e = cudaMalloc((void **)&d->tw_full, tw.size() * sizeof(double));
+            if (e == cudaSuccess)
+                e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload twiddles"); }
+        }
+        pl.dev = d;
+    }
+    if (need_dual && !pl.dev->dual) {
+        cudaError_t e = pl.precision == F32 ? upload_as<float>(pl.dual, &pl.dev->dual)
+                                            : upload_as<double>(pl.dual, &pl.dev->dual);
+        if (e != cudaSuccess) return cuda_fail(e, "upload dual window");
+    }
+    return VEILS_OK;
+}
+
+template <typename T>
+static Tables<T> tables_of(const Plan &pl) {
+    Tables<T> tb;
+    tb.win = (const T *)pl.dev->win;
+    tb.dual = (const T *)pl.dev->dual;
+    tb.tw_full = pl.dev->tw_full;
+    tb.tw_pow2 = (const T *)pl.dev->tw_pow2;
+    return tb;
+}
+
+extern "C" {
+
+int32_t veils_abi_version(void) { return VEILS_ABI_VERSION; }
+const char *veils_last_error(void) { return t_err.c_str(); }
+
+int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
+    if (!d || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    veils_plan *p = new (std::nothrow) veils_plan();
+    if (!p) return fail(VEILS_ERR_INVALID, "out of host memory");
+    std::string e = plan_init(p->pl, d->win, d->m_num, d->hop, d->fs, d->fft_mode, d->mfft,
+                              d->dual_win, d->scale_to, d->phase_shift, d->precision, d->device);
+    if (!e.empty()) {
+        delete p;
+        return fail(VEILS_ERR_INVALID, e);
+    }
+    p->pl.pow2_path = pow2_supported(p->pl.M, p->pl.N, p->pl.H, p->pl.precision);
+    *out = p;
+    return VEILS_OK;
+}
+
+void veils_plan_destroy(veils_plan *p) {
+    if (!p) return;
+    if (p->pl.dev) {
+        cudaSetDevice(p->pl.device);
+        cudaFree(p->pl.dev->win);
+        cudaFree(p->pl.dev->dual);
+        cudaFree(p->pl.dev->tw_full);
+        cudaFree(p->pl.dev->tw_pow2);
+        delete p->pl.dev;
+    }
+    delete p;
+}
+
+int64_t veils_m_num(const veils_plan *p) { return p->pl.N; }
+int64_t veils_m_num_mid(const veils_plan *p) { return p->pl.mid; }
+int64_t veils_hop(const veils_plan *p) { return p->pl.H; }
+int64_t veils_mfft(const veils_plan *p) { return p->pl.M; }
+int64_t veils_f_pts(const veils_plan *p) { return p->pl.F; }
+int64_t veils_phase_shift(const veils_plan *p) { return p->pl.phase_shift; }
+double veils_fs(const veils_plan *p) { return p->pl.fs; }
+double veils_delta_t(const veils_plan *p) { return (double)p->pl.H * (1.0 / p->pl.fs); }
+double veils_delta_f(const veils_plan *p) { return 1.0 / ((double)p->pl.M * (1.0 / p->pl.fs)); }
+int32_t veils_fft_mode(const veils_plan *p) { return p->pl.mode; }
+int32_t veils_onesided_fft(const veils_plan *p) { return p->pl.mode >= ONESIDED; }
+int32_t veils_scaling(const veils_plan *p) { return p->pl.scaling; }
+int32_t veils_precision(const veils_plan *p) { return p->pl.precision; }
+int32_t veils_device(const veils_plan *p) { return p->pl.device; }
+
+int32_t veils_win(const veils_plan *p, double *out) {
+    if (!p || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    std::memcpy(out, p->pl.win.data(), p->pl.win.size() * sizeof(double));
+    return VEILS_OK;
+}
+
+int32_t veils_dual_win(veils_plan *p, double *out) {
+    if (!p || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    std::string e = plan_dual(p->pl);
+    if (!e.empty()) return fail(VEILS_ERR_NOT_INVERTIBLE, e);
+    std::memcpy(out, p->pl.dual.data(), p->pl.dual.size() * sizeof(double));
+    return VEILS_OK;
+}
+
+int32_t veils_invertible(veils_plan *p) { return p && plan_dual(p->pl).empty() ? 1 : 0; }
+
+int64_t veils_p_min(const veils_plan *p) { return p->pl.p_min; }
+int64_t veils_k_min(const veils_plan *p) { return p->pl.k_min; }
+
+int32_t veils_p_max(const veils_plan *p, int64_t n, int64_t *out) {
+    std::string e = plan_post_padding(p->pl, n, nullptr, out);
+    return e.empty() ? VEILS_OK : fail(VEILS_ERR_INVALID, e);
+}
+int32_t veils_k_max(const veils_plan *p, int64_t n, int64_t *out) {
+    std::string e = plan_post_padding(p->pl, n, out, nullptr);
+    return e.empty() ? VEILS_OK : fail(VEILS_ERR_INVALID, e);
+}
+int32_t veils_p_num(const veils_plan *p, int64_t n, int64_t *out) {
+    int64_t pm = 0;
+    std::string e = plan_post_padding(p->pl, n, nullptr, &pm);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    *out = pm - p->pl.p_min;
+    return VEILS_OK;
+}
+int32_t veils_p_range(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t *p1,
+                      int64_t *o0, int64_t *o1) {
+    std::string e = plan_p_range(p->pl, n, p0, p1, o0, o1);
+    return e.empty() ? VEILS_OK : fail(VEILS_ERR_INVALID, e);
+}
+int32_t veils_istft_range(veils_plan *p, int64_t P, const int64_t *k0, const int64_t *k1,
+                          int64_t *o0, int64_t *o1) {
+    IstftRange r;
+    std::string e = plan_istft_range(p->pl, P, k0, k1, &r);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    *o0 = r.k0;
+    *o1 = r.k1;
+    return VEILS_OK;
+}
+
+int32_t veils_t(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t *p1,
+                int64_t k_offset, double *out) {
+    int64_t a, b;
+    std::string e = plan_p_range(p->pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    const double T = 1.0 / p->pl.fs;
+    for (int64_t q = a; q < b; ++q) out[q - a] = (double)(q * p->pl.H + k_offset) * T;
+    return VEILS_OK;
+}
+
+int32_t veils_f(const veils_plan *p, double *out) {
+    const Plan &pl = p->pl;
+    const double T = 1.0 / pl.fs;
+    const int64_t M = pl.M;
+    if (pl.mode >= ONESIDED) {
+        for (int64_t i = 0; i < pl.F; ++i) out[i] = (double)i / ((double)M * T);
+        return VEILS_OK;
+    }
+    // fftfreq order (src/lib.rs:936-945); numpy puts i >= ceil(M/2) on the negative side
+    std::vector<double> fr((size_t)M);
+    for (int64_t i = 0; i < M; ++i) {
+        if (pl.mode == CENTERED) {
+            const int64_t s = (i < (M + 1) / 2) ? i : i - M;          // numpy.fft.fftfreq
+            fr[i] = (double)s / ((double)M * T);
+        } else {
+            double f = (double)i / ((double)M * T);
+            fr[i] = (i > M / 2) ? f - 1.0 / T : f;
+        }
+    }
+    if (pl.mode == CENTERED) {                                         // fftshift (scipy)
+        const int64_t sh = (M + 1) / 2;
+        for (int64_t i = 0; i < M; ++i) out[i] = fr[(i + sh) % M];
+    } else {
+        std::memcpy(out, fr.data(), (size_t)M * sizeof(double));
+    }
+    return VEILS_OK;
+}
+
+// ---- compute -----------------------------------------------------------------------------
+static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                            const int64_t *p0, const int64_t *p1, int64_t k_offset, void *out,
+                            int64_t ldp, void *stream, int spectrogram) {
+    if (!p || !x || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    Plan &pl = p->pl;
+    if (batch < 0) return fail(VEILS_ERR_INVALID, "batch must be >= 0");
+    const int64_t m2p = pl.N - pl.mid;
+    if (n < m2p)                                              // src/lib.rs:700-707
+        return fail(VEILS_ERR_INVALID, "Input length " + std::to_string((long long)n) +
+                                           " must be >= ceil(m_num/2) = " + std::to_string((long long)m2p));
+    int64_t a, b;
+    std::string e = plan_p_range(pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    if (x_pitch < n) return fail(VEILS_ERR_INVALID, "x_pitch must be >= n");
+    if (ldp < b - a) return fail(VEILS_ERR_INVALID, "ldp must be >= p1 - p0");
+    if (batch == 0) return VEILS_OK;
+    int32_t rc = ensure_device(pl, false);
+    if (rc != VEILS_OK) return rc;
+    FwdParams prm;
+    prm.n = n; prm.x_pitch = x_pitch; prm.batch = batch;
+    prm.N = pl.N; prm.H = pl.H; prm.M = pl.M; prm.F = pl.F; prm.mid = pl.mid; prm.ps = pl.ps;
+    prm.p0 = a; prm.P = b - a; prm.k_offset = k_offset; prm.ldp = ldp;
+    prm.mode = pl.mode; prm.fac2x = pl.fac2x; prm.spectrogram = spectrogram;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    if (pl.precision == F32) {
+        Tables<float> tb = tables_of<float>(pl);
+        ce = pl.pow2_path ? pow2_forward<float>((const float *)x, out, prm, tb, st)
+                          : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
+    } else {
+        Tables<double> tb = tables_of<double>(pl);
+        ce = pl.pow2_path ? pow2_forward<double>((const double *)x, out, prm, tb, st)
+                          : dft_generic_forward<double>((const double *)x, out, prm, tb, st);
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "stft launch");
+    return VEILS_OK;
+}
+
+int32_t veils_stft_dev(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                       const int64_t *p0, const int64_t *p1, int64_t k_offset, void *S, int64_t ldp,
+                       void *stream) {
+    return forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, S, ldp, stream, 0);
+}
+
+int32_t veils_spectrogram_dev(veils_plan *p, const void *x, int64_t n, int64_t batch,
+                              int64_t x_pitch, const int64_t *p0, const int64_t *p1,
+                              int64_t k_offset, void *Sxx, int64_t ldp, void *stream) {
+    return forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, Sxx, ldp, stream, 1);
+}
+
+int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,
+                        const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
+                        void *stream) {
+    if (!p || !S || !x_out) return fail(VEILS_ERR_INVALID, "null argument");
+    Plan &pl = p->pl;
+    if (batch < 0) return fail(VEILS_ERR_INVALID, "batch must be >= 0");
+    IstftRange r;
+    std::string e = plan_istft_range(pl, P, k0, k1, &r);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    if (ldp < P) return fail(VEILS_ERR_INVALID, "ldp must be >= P");
+    if (out_pitch < r.k1 - r.k0) return fail(VEILS_ERR_INVALID, "out_pitch must be >= k1 - k0");
+    if (batch == 0) return VEILS_OK;
+    int32_t rc = ensure_device(pl, true);                    // dual_win()? (src/lib.rs:849)
+    if (rc != VEILS_OK) return rc;
+    InvParams prm;
+    prm.P = P; prm.ldp = ldp; prm.batch = batch;
+    prm.N = pl.N; prm.H = pl.H; prm.M = pl.M; prm.F = pl.F; prm.mid = pl.mid; prm.ps = pl.ps;
+    prm.p_min = pl.p_min; prm.k0 = r.k0; prm.k1 = r.k1; prm.q0 = r.q0; prm.q1 = r.q1;
+    prm.out_pitch = out_pitch; prm.mode = pl.mode; prm.fac2x = pl.fac2x;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce;
+    if (pl.precision == F32) {
+        Tables<float> tb = tables_of<float>(pl);
+        ce = pl.pow2_path ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
+                          : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
+    } else {
+        Tables<double> tb = tables_of<double>(pl);
+        ce = pl.pow2_path ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
+                          : dft_generic_inverse<double>(S, (double *)x_out, prm, tb, st);
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "istft launch");
+    return VEILS_OK;
+}
+
+// ---- host-pointer flavour ------------------------------------------------------------------
+static size_t esz(const Plan &pl) { return pl.precision == F32 ? 4 : 8; }
+
+static int32_t forward_host(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                            const int64_t *p0, const int64_t *p1, int64_t k_offset, void *out,
+                            int spectrogram) {
+    if (!p || !x || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    Plan &pl = p->pl;
+    if (x_pitch < n) return fail(VEILS_ERR_INVALID, "x_pitch must be >= n");
+    if (pl.mode >= ONESIDED) {                                // src/lib.rs:696-698
+        bool nan = false;
+        for (int64_t b = 0; b < batch && !nan; ++b) {
+            if (pl.precision == F32) {
+                const float *r = (const float *)x + b * x_pitch;
+                for (int64_t i = 0; i < n; ++i) if (std::isnan(r[i])) { nan = true; break; }
+            } else {
+                const double *r = (const double *)x + b * x_pitch;
+                for (int64_t i = 0; i < n; ++i) if (std::isnan(r[i])) { nan = true; break; }
+            }
+        }
+        if (nan) return fail(VEILS_ERR_INVALID, "Complex-valued input not allowed for one-sided FFT modes");
+    }
+    const int64_t m2p = pl.N - pl.mid;
+    if (n < m2p)
+        return fail(VEILS_ERR_INVALID, "Input length " + std::to_string((long long)n) +
+                                           " must be >= ceil(m_num/2) = " + std::to_string((long long)m2p));
+    int64_t a, b;
+    std::string e = plan_p_range(pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    if (batch <= 0) return VEILS_OK;
+    const int64_t P = b - a;
+    const size_t es = esz(pl);
+    const size_t in_bytes = (size_t)batch * (size_t)n * es;
+    const size_t out_bytes = (size_t)batch * (size_t)pl.F * (size_t)P * es * (spectrogram ? 1 : 2);
+    CU(cudaSetDevice(pl.device));
+    void *dx = nullptr, *ds = nullptr;
+    CU(cudaMalloc(&dx, in_bytes));
+    cudaError_t ce = cudaMalloc(&ds, out_bytes);
+    if (ce != cudaSuccess) { cudaFree(dx); return cuda_fail(ce, "cudaMalloc"); }
+    ce = cudaMemcpy2D(dx, (size_t)n * es, x, (size_t)x_pitch * es, (size_t)n * es, (size_t)batch,
+                      cudaMemcpyHostToDevice);
+    int32_t rc = VEILS_OK;
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "H2D copy");
+    if (rc == VEILS_OK)
+        rc = forward_impl(p, dx, n, batch, n, &a, &b, k_offset, ds, P, nullptr, spectrogram);
+    if (rc == VEILS_OK) {
+        ce = cudaMemcpy(out, ds, out_bytes, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "D2H copy");
+    }
+    cudaFree(dx);
+    cudaFree(ds);
+    return rc;
+}
+
+int32_t veils_stft_host(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                        const int64_t *p0, const int64_t *p1, int64_t k_offset, void *S) {
+    return forward_host(p, x, n, batch, x_pitch, p0, p1, k_offset, S, 0);
+}
+int32_t veils_spectrogram_host(veils_plan *p, const void *x, int64_t n, int64_t batch,
+                               int64_t x_pitch, const int64_t *p0, const int64_t *p1,
+                               int64_t k_offset, void *Sxx) {
+    return forward_host(p, x, n, batch, x_pitch, p0, p1, k_offset, Sxx, 1);
+}
+
+int32_t veils_istft_host(veils_plan *p, const void *S, int64_t P, int64_t batch, const int64_t *k0,
+                         const int64_t *k1, void *x_out) {
+    if (!p || !S || !x_out) return fail(VEILS_ERR_INVALID, "null argument");
+    Plan &pl = p->pl;
+    IstftRange r;
+    std::string e = plan_istft_range(pl, P, k0, k1, &r);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    if (batch <= 0) return VEILS_OK;
+    const size_t es = esz(pl);
+    const int64_t len = r.k1 - r.k0;
+    const size_t s_bytes = (size_t)batch * (size_t)pl.F * (size_t)P * es * 2;
+    const size_t o_bytes = (size_t)batch * (size_t)len * es;
+    CU(cudaSetDevice(pl.device));
+    void *ds = nullptr, *dx = nullptr;
+    CU(cudaMalloc(&ds, s_bytes));
+    cudaError_t ce = cudaMalloc(&dx, o_bytes);
+    if (ce != cudaSuccess) { cudaFree(ds); return cuda_fail(ce, "cudaMalloc"); }
+    int32_t rc = VEILS_OK;
+    ce = cudaMemcpy(ds, S, s_bytes, cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "H2D copy");
+    if (rc == VEILS_OK) rc = veils_istft_dev(p, ds, P, batch, P, &r.k0, &r.k1, dx, len, nullptr);
+    if (rc == VEILS_OK) {
+        ce = cudaMemcpy(x_out, dx, o_bytes, cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) rc = cuda_fail(ce, "D2H copy");
+    }
+    cudaFree(ds);
+    cudaFree(dx);
+    return rc;
+}
+
+// ---- device buffers / streams ---------------------------------------------------------------
+int32_t veils_device_count(int32_t *out) {
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    *out = n;
+    return VEILS_OK;
+}
+int32_t veils_dev_alloc(int32_t device, uint64_t bytes, void **out) {
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(out, bytes));
+    return VEILS_OK;
+}
+int32_t veils_dev_free(int32_t device, void *ptr) {
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr));
+    return VEILS_OK;
+}
+int32_t veils_dev_upload(void *dst, const void *src, uint64_t bytes, void *stream) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return VEILS_OK;
+}
+int32_t veils_dev_download(void *dst, const void *src, uint64_t bytes, void *stream) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return VEILS_OK;
+}
+int32_t veils_host_alloc_pinned(uint64_t bytes, void **out) {
+    CU(cudaMallocHost(out, bytes));
+    return VEILS_OK;
+}
+int32_t veils_host_free_pinned(void *ptr) {
+    CU(cudaFreeHost(ptr));
+    return VEILS_OK;
+}
+int32_t veils_stream_create(int32_t device, void **out) {
+    CU(cudaSetDevice(device));
+    cudaStream_t s;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void *)s;
+    return VEILS_OK;
+}
+int32_t veils_stream_destroy(void *stream) {
+    CU(cudaStreamDestroy((cudaStream_t)stream));
+    return VEILS_OK;
+}
+int32_t veils_stream_sync(void *stream) {
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    return VEILS_OK;
+}
+
+uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
+const char *veils_plan_kernel_name(const veils_plan *p, int32_t) {
+    return p->pl.pow2_path ? "pow2_tile" : "dft_generic";
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// kernels.cuh -- launch interface between the C ABI (api.cu) and the kernel families.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdint>
+
+namespace veils {
+
+// Forward problem: frames p0 .. p0+P of `batch` signals (reference src/lib.rs:612-749).
+struct FwdParams {
+    int64_t n, x_pitch, batch;          // input signals x[b][0..n)
+    int64_t N, H, M, F, mid, ps;        // m_num, hop, mfft, f_pts, m_num_mid, roll
+    int64_t p0, P, k_offset;            // slice range and sample offset
+    int64_t ldp;                        // row pitch of S (elements), >= P
+    int mode;                           // Mode
+    double fac2x;                       // onesided2X factor
+    int spectrogram;                    // 1: write re^2 + im^2 (real) instead of complex
+};
+
+// Inverse problem (reference src/lib.rs:792-914).
+struct InvParams {
+    int64_t P, ldp, batch;              // S[b][F][ldp] with P valid slices
+    int64_t N, H, M, F, mid, ps;
+    int64_t p_min;                      // S column c holds slice q = c + p_min
+    int64_t k0, k1, q0, q1;             // output samples [k0, k1), slices [q0, q1)
+    int64_t out_pitch;
+    int mode;
+    double fac2x;
+};
+
+// Device tables of one plan (element type T = float / double).
+template <typename T>
+struct Tables {
+    const T *win = nullptr;             // [N] window (scaled)
+    const T *dual = nullptr;            // [N] dual window (nullptr until istft is used)
+    const double2 *tw_full = nullptr;   // [M] exp(-2 pi i m / M) in f64 (generic path)
+    const T *tw_pow2 = nullptr;         // fast-path twiddles (layout: see pow2_tile.cu)
+};
+
+extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library
+
+// ---- generic O(M^2) DFT family: any mfft, any mode (dft_generic.cu) ----------------------
+template <typename T>
+cudaError_t dft_generic_forward(const T *x, void *out, const FwdParams &prm, const Tables<T> &tb,
+                                cudaStream_t st);
+template <typename T>
+cudaError_t dft_generic_inverse(const void *S, T *x_out, const InvParams &prm, const Tables<T> &tb,
+                                cudaStream_t st);
+
+// ---- power-of-two tile family (pow2_tile.cu) ----------------------------------------------
+bool pow2_supported(int64_t M, int64_t N, int64_t H, int precision);
+template <typename T>
+cudaError_t pow2_forward(const T *x, void *out, const FwdParams &prm, const Tables<T> &tb,
+                         cudaStream_t st);
+template <typename T>
+cudaError_t pow2_inverse(const void *S, T *x_out, const InvParams &prm, const Tables<T> &tb,
+                         cudaStream_t st);
+// size (in T elements) and contents of the fast-path twiddle table for mfft = M
+int64_t pow2_twiddle_count(int64_t M);
+void pow2_twiddle_fill(int64_t M, double *re_im_pairs);
+
+}  // namespace veils

@@ -1,0 +1,251 @@
+"""Host-side mirror of the reference's `StandaloneSTFT` (Rust src/lib.rs:116-955; Python twin
+python/standalone_stft.py:53-444) on top of the C ABI of libveils_cuda.so.
+
+Same constructor arguments, methods, defaults and error texts as the reference, plus the two
+scipy.signal.ShortTimeFFT features BASELINE.json's north_star asks for (`scale_to`,
+`spectrogram`).  All arithmetic runs in the CUDA kernels; this file only marshals arguments.
+numpy inputs go through the host-pointer entry points, torch CUDA tensors through the
+device-pointer entry points (no copies, current torch stream)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, opt_i64
+
+_MODES = ("twosided", "centered", "onesided", "onesided2X")
+_SCALES = (None, "magnitude", "psd")
+
+
+class VeilsError(ValueError):
+    """An `Err(String)` of the reference API (status code in `.code`)."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def _check(rc):
+    if rc != _lib.OK:
+        msg = _lib.last_error()
+        if rc == _lib.ERR_CUDA:
+            raise RuntimeError(f"veils_b200 CUDA failure: {msg}")
+        raise VeilsError(rc, msg)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class StandaloneSTFT:
+    """Drop-in for veils::StandaloneSTFT backed by the sm_100a kernels."""
+
+    def __init__(self, win, hop, fs, *, fft_mode="onesided", mfft=None, dual_win=None,
+                 scale_to=None, phase_shift=0, precision="f64", device=0):
+        L = lib()
+        win = np.ascontiguousarray(np.asarray(win, dtype=np.float64).ravel())
+        dual = None if dual_win is None else np.ascontiguousarray(
+            np.asarray(dual_win, dtype=np.float64).ravel())
+        if dual is not None and dual.shape != win.shape:
+            raise VeilsError(_lib.ERR_INVALID, "dual_win.len() must equal win.len()!")
+        if not isinstance(hop, (int, np.integer)):
+            raise VeilsError(_lib.ERR_INVALID, f"Parameter hop={hop} is not >= 1!")
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        d = _lib.PlanDesc()
+        d.win = _dptr(win) if win.size else None
+        d.m_num = win.size
+        d.hop = int(hop)
+        d.fs = float(fs)
+        d.fft_mode = None if fft_mode is None else str(fft_mode).encode()
+        d.mfft = 0 if mfft is None else int(mfft)
+        d.dual_win = None if dual is None else _dptr(dual)
+        d.scale_to = None if scale_to is None else str(scale_to).encode()
+        d.phase_shift = 0 if phase_shift is None else int(phase_shift)
+        d.precision = _lib.F32 if precision == "f32" else _lib.F64
+        d.device = int(device)
+        if mfft is not None and int(mfft) <= 0:
+            raise VeilsError(_lib.ERR_INVALID, f"Parameter mfft={mfft} is not >= 1!")
+        h = C.c_void_p()
+        self._h = None
+        _check(L.veils_plan_create(C.byref(d), C.byref(h)))
+        self._h = h
+        self._L = L
+        self.precision = precision
+        self._rdt = np.float32 if precision == "f32" else np.float64
+        self._cdt = np.complex64 if precision == "f32" else np.complex128
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.veils_plan_destroy(h)
+
+    # ---- accessors (src/lib.rs:227-281) --------------------------------------------------
+    @property
+    def win(self):
+        out = np.empty(self.m_num)
+        _check(self._L.veils_win(self._h, _dptr(out)))
+        return out
+
+    @property
+    def dual_win(self):
+        out = np.empty(self.m_num)
+        _check(self._L.veils_dual_win(self._h, _dptr(out)))
+        return out
+
+    @property
+    def invertible(self):
+        return bool(self._L.veils_invertible(self._h))
+
+    hop = property(lambda s: s._L.veils_hop(s._h))
+    fs = property(lambda s: s._L.veils_fs(s._h))
+    mfft = property(lambda s: s._L.veils_mfft(s._h))
+    m_num = property(lambda s: s._L.veils_m_num(s._h))
+    m_num_mid = property(lambda s: s._L.veils_m_num_mid(s._h))
+    f_pts = property(lambda s: s._L.veils_f_pts(s._h))
+    phase_shift = property(lambda s: s._L.veils_phase_shift(s._h))
+    delta_t = property(lambda s: s._L.veils_delta_t(s._h))
+    delta_f = property(lambda s: s._L.veils_delta_f(s._h))
+    T = property(lambda s: 1.0 / s.fs)
+    sampling_period = T
+    fft_mode = property(lambda s: _MODES[s._L.veils_fft_mode(s._h)])
+    onesided_fft = property(lambda s: bool(s._L.veils_onesided_fft(s._h)))
+    scaling = property(lambda s: _SCALES[s._L.veils_scaling(s._h)])
+    p_min = property(lambda s: s._L.veils_p_min(s._h))
+    k_min = property(lambda s: s._L.veils_k_min(s._h))
+    device = property(lambda s: s._L.veils_device(s._h))
+
+    def kernel_name(self, inverse=False):
+        return self._L.veils_plan_kernel_name(self._h, int(inverse)).decode()
+
+    def _i64(self, fn, *args):
+        out = C.c_int64()
+        _check(fn(self._h, *args, C.byref(out)))
+        return out.value
+
+    def p_max(self, n):
+        return self._i64(self._L.veils_p_max, int(n))
+
+    def k_max(self, n):
+        return self._i64(self._L.veils_k_max, int(n))
+
+    def p_num(self, n):
+        return self._i64(self._L.veils_p_num, int(n))
+
+    def p_range(self, n, p0=None, p1=None):
+        a, b = C.c_int64(), C.c_int64()
+        _check(self._L.veils_p_range(self._h, int(n), opt_i64(p0), opt_i64(p1), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def istft_range(self, P, k0=None, k1=None):
+        a, b = C.c_int64(), C.c_int64()
+        _check(self._L.veils_istft_range(self._h, int(P), opt_i64(k0), opt_i64(k1), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def t(self, n, p0=None, p1=None, k_offset=0):
+        a, b = self.p_range(n, p0, p1)
+        out = np.empty(b - a)
+        _check(self._L.veils_t(self._h, int(n), opt_i64(p0), opt_i64(p1), int(k_offset), _dptr(out)))
+        return out
+
+    def f(self):
+        out = np.empty(self.f_pts)
+        _check(self._L.veils_f(self._h, _dptr(out)))
+        return out
+
+    # ---- compute ---------------------------------------------------------------------------
+    @staticmethod
+    def _is_tensor(x):
+        return type(x).__module__.startswith("torch")
+
+    def _fwd(self, x, p0, p1, k_offset, spectrogram):
+        if self._is_tensor(x):
+            return self._fwd_tensor(x, p0, p1, k_offset, spectrogram)
+        x = np.asarray(x)
+        if np.iscomplexobj(x):
+            raise VeilsError(_lib.ERR_INVALID, "Complex-valued input not allowed (real input only)")
+        squeeze = x.ndim == 1
+        x2 = np.ascontiguousarray(np.atleast_2d(x), dtype=self._rdt)
+        batch, n = x2.shape
+        # validation of n / p-range happens in the library, but the output must be sized first
+        if n < self.m_num - self.m_num_mid:
+            raise VeilsError(_lib.ERR_INVALID,
+                             f"Input length {n} must be >= ceil(m_num/2) = {self.m_num - self.m_num_mid}")
+        a, b = self.p_range(n, p0, p1)
+        out = np.empty((batch, self.f_pts, b - a), dtype=self._rdt if spectrogram else self._cdt)
+        fn = self._L.veils_spectrogram_host if spectrogram else self._L.veils_stft_host
+        _check(fn(self._h, x2.ctypes.data, n, batch, n, opt_i64(a), opt_i64(b), int(k_offset),
+                  out.ctypes.data))
+        return out[0] if squeeze else out
+
+    def _fwd_tensor(self, x, p0, p1, k_offset, spectrogram):
+        import torch
+        tdt = torch.float32 if self.precision == "f32" else torch.float64
+        if not x.is_cuda or x.dtype != tdt:
+            raise ValueError(f"expected a CUDA tensor of dtype {tdt}")
+        squeeze = x.dim() == 1
+        x2 = x.reshape(1, -1) if squeeze else x
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        batch, n = x2.shape
+        if n < self.m_num - self.m_num_mid:
+            raise VeilsError(_lib.ERR_INVALID,
+                             f"Input length {n} must be >= ceil(m_num/2) = {self.m_num - self.m_num_mid}")
+        a, b = self.p_range(n, p0, p1)
+        P = b - a
+        if spectrogram:
+            out = torch.empty((batch, self.f_pts, P), dtype=tdt, device=x.device)
+        else:
+            out = torch.empty((batch, self.f_pts, P), device=x.device,
+                              dtype=torch.complex64 if self.precision == "f32" else torch.complex128)
+        fn = self._L.veils_spectrogram_dev if spectrogram else self._L.veils_stft_dev
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        _check(fn(self._h, x2.data_ptr(), n, batch, x2.stride(0) if batch > 1 else n, opt_i64(a),
+                  opt_i64(b), int(k_offset), out.data_ptr(), P, st))
+        return out[0] if squeeze else out
+
+    def stft(self, x, p0=None, p1=None, *, k_offset=0):
+        """src/lib.rs:689-749 -> S[f_pts][P] (or [batch][f_pts][P] for 2-d input)."""
+        return self._fwd(x, p0, p1, k_offset, False)
+
+    def spectrogram(self, x, p0=None, p1=None, *, k_offset=0):
+        """scipy ShortTimeFFT.spectrogram: |stft(x)|^2, real."""
+        return self._fwd(x, p0, p1, k_offset, True)
+
+    def istft(self, S, k0=None, k1=None):
+        """src/lib.rs:792-914 -> real signal of length k1-k0 (default k0=0, k1=k_max of S)."""
+        if self._is_tensor(S):
+            return self._istft_tensor(S, k0, k1)
+        S = np.asarray(S)
+        if S.ndim not in (2, 3) or S.size == 0:
+            raise VeilsError(_lib.ERR_INVALID, "STFT data cannot be empty")
+        squeeze = S.ndim == 2
+        S3 = np.ascontiguousarray(S[None] if squeeze else S, dtype=self._cdt)
+        batch, F, P = S3.shape
+        if F != self.f_pts:
+            raise VeilsError(_lib.ERR_INVALID,
+                             f"STFT frequency dimension {F} must equal {self.f_pts}")
+        a, b = self.istft_range(P, k0, k1)
+        out = np.empty((batch, b - a), dtype=self._rdt)
+        _check(self._L.veils_istft_host(self._h, S3.ctypes.data, P, batch, opt_i64(a), opt_i64(b),
+                                        out.ctypes.data))
+        return out[0] if squeeze else out
+
+    def _istft_tensor(self, S, k0, k1):
+        import torch
+        cdt = torch.complex64 if self.precision == "f32" else torch.complex128
+        if not S.is_cuda or S.dtype != cdt:
+            raise ValueError(f"expected a CUDA tensor of dtype {cdt}")
+        squeeze = S.dim() == 2
+        S3 = (S[None] if squeeze else S).contiguous()
+        batch, F, P = S3.shape
+        if F != self.f_pts:
+            raise VeilsError(_lib.ERR_INVALID,
+                             f"STFT frequency dimension {F} must equal {self.f_pts}")
+        a, b = self.istft_range(P, k0, k1)
+        out = torch.empty((batch, b - a), device=S.device,
+                          dtype=torch.float32 if self.precision == "f32" else torch.float64)
+        st = torch.cuda.current_stream(S.device).cuda_stream
+        _check(self._L.veils_istft_dev(self._h, S3.data_ptr(), P, batch, P, opt_i64(a), opt_i64(b),
+                                       out.data_ptr(), b - a, st))
+        return out[0] if squeeze else out
