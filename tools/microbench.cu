@@ -183,6 +183,7 @@ static void run_load(const char *name, float *S, float *sink, int B, int F, int 
 }
 
 int main() {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
     printf("device %s SMs %d clock %d kHz L2 %d MB smem/SM %zu\n", pr.name, pr.multiProcessorCount, pr.clockRate, pr.l2CacheSize >> 20, pr.sharedMemPerMultiprocessor);
     float *out; CK(cudaMalloc(&out, 1024));
@@ -229,7 +230,6 @@ int main() {
             run_store<16, 2>("tile_store", S, B, F, P, ldp);
             run_store<32, 2>("tile_store", S, B, F, P, ldp);
             run_store<64, 4>("tile_store", S, B, F, P, ldp);
-            run_store<128, 4>("tile_store", S, B, F, P, ldp);
         }
         for (int ldp : {1253, 1256}) {
             run_load<8>("tile_load", S, out, B, F, P, ldp);

@@ -3,6 +3,7 @@
 #include "../../include/veils_cuda.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -16,9 +17,11 @@ using namespace veils;
 namespace veils {
 // device copies of the plan's tables, element type = plan precision
 struct DeviceTables {
-    void *win = nullptr;
+    void *win = nullptr;          // generic path
     void *dual = nullptr;
     double2 *tw_full = nullptr;
+    void *win_half = nullptr;     // pow2 path (exact power-of-two rescalings, see pow2_tile_impl.cuh)
+    void *dual_scaled = nullptr;
     void *tw_pow2 = nullptr;
 };
 }  // namespace veils
@@ -59,11 +62,16 @@ static void twiddle(int64_t m, int64_t M, double *re, double *im) {
 }
 
 template <typename T>
-static cudaError_t upload_as(const std::vector<double> &src, void **dst) {
-    std::vector<T> tmp(src.begin(), src.end());
+static cudaError_t upload_as(const std::vector<double> &src, void **dst, double scale = 1.0) {
+    std::vector<T> tmp(src.size());
+    for (size_t i = 0; i < src.size(); ++i) tmp[i] = (T)(src[i] * scale);
     cudaError_t e = cudaMalloc(dst, tmp.size() * sizeof(T));
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+static cudaError_t upload_prec(const Plan &pl, const std::vector<double> &src, void **dst,
+                               double scale = 1.0) {
+    return pl.precision == F32 ? upload_as<float>(src, dst, scale) : upload_as<double>(src, dst, scale);
 }
 
 // Create the device tables on first use.  need_dual: also resolve + upload the dual window.
@@ -77,29 +85,32 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
     if (!pl.dev) {
         DeviceTables *d = new (std::nothrow) DeviceTables();
         if (!d) return fail(VEILS_ERR_CUDA, "out of host memory");
-        cudaError_t e = pl.precision == F32 ? upload_as<float>(pl.win, &d->win)
-                                            : upload_as<double>(pl.win, &d->win);
-        if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload window"); }
-        if (pl.pow2_path) {
-            const int64_t cnt = pow2_twiddle_count(pl.M);
-            std::vector<double> tw((size_t)cnt);
+        cudaError_t e = upload_prec(pl, pl.win, &d->win);
+        if (e == cudaSuccess) e = upload_prec(pl, pl.win, &d->win_half, 0.5);
+        if (e == cudaSuccess && (pl.pow2_fwd || pl.pow2_inv)) {
+            std::vector<double> tw((size_t)pow2_twiddle_count(pl.M));
             pow2_twiddle_fill(pl.M, tw.data());
-            e = pl.precision == F32 ? upload_as<float>(tw, &d->tw_pow2)
-                                    : upload_as<double>(tw, &d->tw_pow2);
-            if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload twiddles"); }
-        } else {
+            e = upload_prec(pl, tw, &d->tw_pow2);
+        }
+        if (e == cudaSuccess && !(pl.pow2_fwd && pl.pow2_inv)) {
             std::vector<double> tw((size_t)pl.M * 2);
             for (int64_t m = 0; m < pl.M; ++m) twiddle(m, pl.M, &tw[2 * m], &tw[2 * m + 1]);
             e = cudaMalloc((void **)&d->tw_full, tw.size() * sizeof(double));
             if (e == cudaSuccess)
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { delete d; return cuda_fail(e, "upload twiddles"); }
+        }
+        if (e != cudaSuccess) {
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full);
+            delete d;
+            return cuda_fail(e, "upload plan tables");
         }
         pl.dev = d;
     }
     if (need_dual && !pl.dev->dual) {
-        cudaError_t e = pl.precision == F32 ? upload_as<float>(pl.dual, &pl.dev->dual)
-                                            : upload_as<double>(pl.dual, &pl.dev->dual);
+        // pow2 inverse folds 1/M (and the 1/2 of the Hermitian part for two-sided layouts) here
+        const double sc = 1.0 / ((double)pl.M * (pl.mode >= ONESIDED ? 1.0 : 2.0));
+        cudaError_t e = upload_prec(pl, pl.dual, &pl.dev->dual_scaled, sc);
+        if (e == cudaSuccess) e = upload_prec(pl, pl.dual, &pl.dev->dual);
         if (e != cudaSuccess) return cuda_fail(e, "upload dual window");
     }
     return VEILS_OK;
@@ -111,6 +122,8 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.win = (const T *)pl.dev->win;
     tb.dual = (const T *)pl.dev->dual;
     tb.tw_full = pl.dev->tw_full;
+    tb.win_half = (const T *)pl.dev->win_half;
+    tb.dual_scaled = (const T *)pl.dev->dual_scaled;
     tb.tw_pow2 = (const T *)pl.dev->tw_pow2;
     return tb;
 }
@@ -131,7 +144,12 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         delete p;
         return fail(VEILS_ERR_INVALID, e);
     }
-    p->pl.pow2_path = pow2_supported(p->pl.M, p->pl.N, p->pl.H, p->pl.precision);
+    {
+        Plan &pl = p->pl;
+        const bool force_generic = d->precision >= 0 && getenv("VEILS_FORCE_GENERIC") != nullptr;
+        pl.pow2_fwd = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, false);
+        pl.pow2_inv = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, true);
+    }
     *out = p;
     return VEILS_OK;
 }
@@ -143,6 +161,8 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->win);
         cudaFree(p->pl.dev->dual);
         cudaFree(p->pl.dev->tw_full);
+        cudaFree(p->pl.dev->win_half);
+        cudaFree(p->pl.dev->dual_scaled);
         cudaFree(p->pl.dev->tw_pow2);
         delete p->pl.dev;
     }
@@ -279,11 +299,11 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pow2_path ? pow2_forward<float>((const float *)x, out, prm, tb, st)
+        ce = pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
                           : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
-        ce = pl.pow2_path ? pow2_forward<double>((const double *)x, out, prm, tb, st)
+        ce = pl.pow2_fwd ? pow2_forward<double>((const double *)x, out, prm, tb, st)
                           : dft_generic_forward<double>((const double *)x, out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "stft launch");
@@ -325,11 +345,11 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pow2_path ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
+        ce = pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
                           : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
-        ce = pl.pow2_path ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
+        ce = pl.pow2_inv ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
                           : dft_generic_inverse<double>(S, (double *)x_out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "istft launch");
@@ -480,8 +500,8 @@ int32_t veils_stream_sync(void *stream) {
 }
 
 uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
-const char *veils_plan_kernel_name(const veils_plan *p, int32_t) {
-    return p->pl.pow2_path ? "pow2_tile" : "dft_generic";
+const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse) {
+    return (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) ? "pow2_tile" : "dft_generic";
 }
 
 }  // extern "C"

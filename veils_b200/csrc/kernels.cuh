@@ -34,7 +34,9 @@ struct Tables {
     const T *win = nullptr;             // [N] window (scaled)
     const T *dual = nullptr;            // [N] dual window (nullptr until istft is used)
     const double2 *tw_full = nullptr;   // [M] exp(-2 pi i m / M) in f64 (generic path)
-    const T *tw_pow2 = nullptr;         // fast-path twiddles (layout: see pow2_tile.cu)
+    const T *win_half = nullptr;        // [N] window / 2           (pow2 forward)
+    const T *dual_scaled = nullptr;     // [N] dual / M or / (2M)   (pow2 inverse)
+    const T *tw_pow2 = nullptr;         // pow2 twiddles (layout: pow2_cfg.hpp)
 };
 
 extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library
@@ -48,7 +50,7 @@ cudaError_t dft_generic_inverse(const void *S, T *x_out, const InvParams &prm, c
                                 cudaStream_t st);
 
 // ---- power-of-two tile family (pow2_tile.cu) ----------------------------------------------
-bool pow2_supported(int64_t M, int64_t N, int64_t H, int precision);
+bool pow2_supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse);
 template <typename T>
 cudaError_t pow2_forward(const T *x, void *out, const FwdParams &prm, const Tables<T> &tb,
                          cudaStream_t st);

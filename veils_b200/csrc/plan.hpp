@@ -47,7 +47,8 @@ struct Plan {
 
     // device side, created lazily by the first compute call
     DeviceTables *dev = nullptr;
-    bool pow2_path = false;   // dispatch decision (see api.cu)
+    bool pow2_fwd = false;    // dispatch decisions (see api.cu)
+    bool pow2_inv = false;
 };
 
 // Each returns "" on success or the reference's error text.

@@ -1,0 +1,158 @@
+// pow2_cfg.hpp -- host-side configuration of the power-of-two family, shared by the CUDA
+// launchers (pow2_tile.cu) and the host emulation used by the CPU tests (tests/emu/pow2_emu.cu),
+// so both run the very same (TF, NSUB) instantiation, twiddle table and tile layout.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "pow2_tile_impl.cuh"
+
+namespace veils {
+namespace p2 {
+
+struct Cfg {
+    int logmc;   // log2(mfft / 2)
+    int tf;      // slices per tile
+    int nsub;    // butterfly groups worked on concurrently (threads = tf * nsub)
+};
+
+inline int ilog2_exact(int64_t v) {
+    if (v <= 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((int64_t(1) << l) < v) ++l;
+    return l;
+}
+
+// (TF, NSUB) per precision and size.  The work buffer Mc * TF complex is kept <= 128 KiB.
+inline bool cfg_for(int64_t M, int precision, Cfg *c) {
+    const int lm = ilog2_exact(M);
+    if (lm < 5 || lm > 13) return false;              // mfft in [32, 8192]
+    c->logmc = lm - 1;
+    static const int tf32[13] = {0, 0, 0, 0, 32, 32, 32, 32, 32, 32, 16, 8, 4};
+    static const int tf64[13] = {0, 0, 0, 0, 32, 32, 32, 32, 16, 16, 8, 4, 2};
+    c->tf = precision == 0 ? tf32[c->logmc] : tf64[c->logmc];
+    int np, r1, r2, r3;
+    fac_of(c->logmc, &np, &r1, &r2, &r3);
+    const int l1 = (1 << c->logmc) / r1;
+    int nsub = 256 / c->tf;
+    if (nsub > l1 / 2) nsub = l1 / 2;
+    if (nsub < 1) nsub = 1;
+    c->nsub = nsub;
+    return true;
+}
+
+inline int64_t twiddle_count(int64_t M) {             // number of reals
+    Cfg c;
+    if (!cfg_for(M, 0, &c)) return 0;
+    int np, r1, r2, r3;
+    fac_of(c.logmc, &np, &r1, &r2, &r3);
+    const int64_t mc = M / 2, l1 = mc / r1;
+    return 2 * (mc + l1 + mc + 1);
+}
+
+inline void tw_exact(int64_t m, int64_t M, double *re, double *im) {   // exp(-2 pi i m / M)
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    const int64_t mm = ((m % M) + M) % M;
+    if ((4 * mm) % M == 0) {
+        static const double c4[4] = {1, 0, -1, 0}, s4[4] = {0, 1, 0, -1};
+        const int q = (int)(4 * mm / M);
+        *re = c4[q];
+        *im = -s4[q];
+        return;
+    }
+    const long double a = two_pi * (long double)mm / (long double)M;
+    *re = (double)cosl(a);
+    *im = (double)(-sinl(a));
+}
+
+// layout: [tw1: W_Mc^(j c) at j*R1+c][tw2: W_L1^(j2 c2) at j2*R2+c2][twp: W_M^k, k = 0..Mc]
+inline void twiddle_fill(int64_t M, double *t) {
+    Cfg c;
+    if (!cfg_for(M, 0, &c)) return;
+    int np, r1, r2, r3;
+    fac_of(c.logmc, &np, &r1, &r2, &r3);
+    const int64_t mc = M / 2, l1 = mc / r1;
+    double *p = t;
+    for (int64_t j = 0; j < l1; ++j)
+        for (int64_t cc = 0; cc < r1; ++cc, p += 2) tw_exact(j * cc, mc, p, p + 1);
+    if (np == 3) {
+        const int64_t l2 = l1 / r2;
+        for (int64_t j2 = 0; j2 < l2; ++j2)
+            for (int64_t cc = 0; cc < r2; ++cc, p += 2) tw_exact(j2 * cc, l1, p, p + 1);
+    } else {
+        for (int64_t i = 0; i < l1; ++i, p += 2) { p[0] = 1; p[1] = 0; }
+    }
+    for (int64_t k = 0; k <= mc; ++k, p += 2) tw_exact(k, M, p, p + 1);
+}
+
+// staged-tile layout for hop H: the slice stride H + padw (in elements) must be
+//   = 2 (mod 4) for paired (2-element) loads, odd for single-element loads.
+inline TileLayout tile_layout(int64_t H, bool vec) {
+    TileLayout l;
+    l.H = (int)H;
+    l.logH = ilog2_exact(H);
+    if (vec) l.padw = (int)((2 - (H % 4) + 4) % 4);   // H even -> padw in {2, 0}
+    else l.padw = (H % 2 == 0) ? 1 : 0;
+    return l;
+}
+inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H % 2 == 0 && N % 2 == 0; }
+
+inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) {
+    const int64_t span = (int64_t)(tf - 1) * H + N;
+    return span + (span / H + 1) * l.padw + 2;
+}
+inline size_t fwd_smem_bytes(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, const Cfg &c) {
+    const size_t es = precision == 0 ? 4 : 8;
+    const TileLayout l = tile_layout(H, fwd_vec(ps, H, N));
+    return (size_t)(M / 2) * c.tf * 2 * es + (size_t)fwd_xin_elems(N, H, c.tf, l) * es;
+}
+inline int inv_halo(int64_t N, int64_t H) { return (int)((N + H - 1) / H) - 1; }
+inline int inv_ostride(int64_t N) { return (int)(N | 1); }   // odd stride: lane writes conflict free
+inline size_t inv_smem_bytes(int64_t M, int64_t N, int precision, const Cfg &c) {
+    const size_t es = precision == 0 ? 4 : 8;
+    const size_t work = (size_t)(M / 2) * c.tf * 2 * es;
+    const size_t ola = (size_t)c.tf * inv_ostride(N) * es;
+    return work > ola ? work : ola;
+}
+
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+
+inline bool supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse) {
+    Cfg c;
+    if (!cfg_for(M, precision, &c)) return false;
+    if (N > M || H < 1) return false;
+    if (!inverse) return fwd_smem_bytes(M, N, H, ps, precision, c) <= SMEM_LIMIT;
+    if (H > N) return false;
+    if (inv_halo(N, H) >= c.tf) return false;         // at least one owned slice per tile
+    return inv_smem_bytes(M, N, precision, c) <= SMEM_LIMIT;
+}
+
+// Calls fn.template run<T, LOGMC, TF, NSUB>() for the configuration of (M, precision).
+#define VEILS_P2_CASE(T, LM, TFV)                                             \
+    case LM: {                                                                \
+        constexpr int l1_ = (1 << LM) / Fac<LM>::R1;                          \
+        constexpr int ns0_ = 256 / TFV;                                       \
+        constexpr int ns1_ = ns0_ > l1_ / 2 ? l1_ / 2 : ns0_;                 \
+        constexpr int ns_ = ns1_ < 1 ? 1 : ns1_;                              \
+        return fn.template run<T, LM, TFV, ns_>();                            \
+    }
+template <typename FN>
+inline auto dispatch(int precision, int logmc, FN &fn) -> decltype(fn.template run<float, 4, 32, 2>()) {
+    if (precision == 0) {
+        switch (logmc) {
+            VEILS_P2_CASE(float, 4, 32) VEILS_P2_CASE(float, 5, 32) VEILS_P2_CASE(float, 6, 32)
+            VEILS_P2_CASE(float, 7, 32) VEILS_P2_CASE(float, 8, 32) VEILS_P2_CASE(float, 9, 32)
+            VEILS_P2_CASE(float, 10, 16) VEILS_P2_CASE(float, 11, 8) VEILS_P2_CASE(float, 12, 4)
+        }
+    } else {
+        switch (logmc) {
+            VEILS_P2_CASE(double, 4, 32) VEILS_P2_CASE(double, 5, 32) VEILS_P2_CASE(double, 6, 32)
+            VEILS_P2_CASE(double, 7, 32) VEILS_P2_CASE(double, 8, 16) VEILS_P2_CASE(double, 9, 16)
+            VEILS_P2_CASE(double, 10, 8) VEILS_P2_CASE(double, 11, 4) VEILS_P2_CASE(double, 12, 2)
+        }
+    }
+    return decltype(fn.template run<float, 4, 32, 2>())(-1);
+}
+
+}  // namespace p2
+}  // namespace veils

@@ -1,0 +1,559 @@
+// pow2_tile_impl.cuh -- the power-of-two "slice-lane" kernel family, written as phase functions
+// that compile both for the device (pow2_tile.cu) and for a host emulation used by the CPU tests
+// (tests/emu/pow2_emu.cu), so the index algebra can be checked without a GPU.
+//
+// Design:
+//   * One CTA owns a tile of TF consecutive time slices of one signal.  Thread t = (sub, f):
+//     f = t % TF is the slice ("lane <-> slice"), sub = t / TF selects the butterfly group.
+//     Because all threads of a row share (group, element) and differ only in the slice,
+//       - every shared-memory access of a row is to TF consecutive words  -> conflict free,
+//       - twiddles and window samples are uniform across a row            -> broadcast loads,
+//       - the final store of bin k for TF consecutive slices is contiguous in the reference's
+//         [f_pts][P] layout (src/lib.rs:735-746)                          -> coalesced, no
+//         shared-memory transpose of the output.
+//   * The real input (window * signal, src/lib.rs:715-729) is transformed with a half-length
+//     complex FFT (Mc = mfft/2): z[m] = x'[2m] + i x'[2m+1]; the split into the mfft/2+1 one-sided
+//     bins happens in registers in the last pass because a thread holds the groups (g, G-g)
+//     whose bins are each other's mirror images.
+//   * Stockham-free in-place decimation: pass 1 reads straight from the staged signal tile
+//     (frame extraction, zero padding, windowing and the phase-shift roll of
+//     src/lib.rs:336-345, 612-652 are pure load-index arithmetic), middle pass in place,
+//     last pass from shared memory to global memory (mode epilogue src/lib.rs:354-408).
+//   * The inverse mirrors this: pass 1 loads S columns (coalesced over slices) and undoes the
+//     mode (src/lib.rs:414-487), the last pass multiplies by the dual window (:869-873) and the
+//     overlap-add (:876-910) is a deterministic gather in increasing q owned by this CTA.
+#pragma once
+#include "kernels.cuh"
+
+#if defined(__CUDACC__)
+#define VHD __host__ __device__ __forceinline__
+#else
+#define VHD inline
+#endif
+
+namespace veils {
+namespace p2 {
+
+// ------------------------------------------------------------------ complex helpers
+template <typename T>
+struct cx {
+    T x, y;
+};
+template <typename T> VHD cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
+template <typename T> VHD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x + b.x, a.y + b.y); }
+template <typename T> VHD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
+template <typename T> VHD cx<T> cmul(cx<T> a, cx<T> b) {
+    return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename T> VHD cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
+// multiply by -i (forward) / +i (inverse)
+template <bool INV, typename T> VHD cx<T> rot(cx<T> a) {
+    return INV ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x);
+}
+// multiply by the constant (c, -s) forward, (c, +s) inverse
+template <bool INV, typename T> VHD cx<T> cmulc(cx<T> a, double c, double s) {
+    const T cc = (T)c, ss = INV ? (T)(-s) : (T)s;          // w = cc - i ss
+    return mk<T>(a.x * cc + a.y * ss, a.y * cc - a.x * ss);
+}
+
+template <typename T> VHD T ldg(const T *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+template <typename T> VHD cx<T> ldgc(const T *p) {   // complex at p[0], p[1]
+#if defined(__CUDA_ARCH__)
+    if (sizeof(T) == 4) {
+        const float2 v = __ldg((const float2 *)p);
+        return mk<T>((T)v.x, (T)v.y);
+    } else {
+        const double2 v = __ldg((const double2 *)p);
+        return mk<T>((T)v.x, (T)v.y);
+    }
+#else
+    return mk<T>(p[0], p[1]);
+#endif
+}
+
+// ------------------------------------------------------------------ in-register DFTs
+// Natural-order in, natural-order out.  INV selects exp(+i...) (unnormalised).
+template <bool INV, typename T> VHD void dft2(cx<T> &a, cx<T> &b) {
+    const cx<T> t = a - b;
+    a = a + b;
+    b = t;
+}
+template <bool INV, typename T> VHD void dft4(cx<T> &a0, cx<T> &a1, cx<T> &a2, cx<T> &a3) {
+    const cx<T> t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = rot<INV>(a1 - a3);
+    a0 = t0 + t2;
+    a2 = t0 - t2;
+    a1 = t1 + t3;
+    a3 = t1 - t3;
+}
+template <int R, bool INV, typename T> struct Dft;
+template <bool INV, typename T> struct Dft<2, INV, T> {
+    VHD static void run(cx<T> (&v)[2]) { dft2<INV>(v[0], v[1]); }
+};
+template <bool INV, typename T> struct Dft<4, INV, T> {
+    VHD static void run(cx<T> (&v)[4]) { dft4<INV>(v[0], v[1], v[2], v[3]); }
+};
+template <bool INV, typename T> struct Dft<8, INV, T> {
+    // n = 2 n1 + n2, k = k1 + 4 k2
+    VHD static void run(cx<T> (&v)[8]) {
+        const double h = 0.70710678118654752440;
+        dft4<INV>(v[0], v[2], v[4], v[6]);                // n2 = 0 -> t0[k1]
+        dft4<INV>(v[1], v[3], v[5], v[7]);                // n2 = 1 -> t1[k1]
+        v[3] = cmulc<INV>(v[3], h, h);                    // W8^1
+        v[5] = rot<INV>(v[5]);                            // W8^2
+        v[7] = cmulc<INV>(v[7], -h, h);                   // W8^3
+        // X[k1] = t0 + t1 W, X[k1+4] = t0 - t1 W ; t0[k1] = v[2k1], t1[k1] = v[2k1+1]
+        cx<T> o[8];
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            o[k1] = v[2 * k1] + v[2 * k1 + 1];
+            o[k1 + 4] = v[2 * k1] - v[2 * k1 + 1];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = o[i];
+    }
+};
+template <bool INV, typename T> struct Dft<16, INV, T> {
+    // n = 4 n1 + n2, k = k1 + 4 k2
+    VHD static void run(cx<T> (&v)[16]) {
+        const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+        const double h = 0.70710678118654752440;
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) dft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+        // now v[4 k1 + n2] = t[n2][k1]; twiddle W16^(n2 k1)
+        v[4 + 1] = cmulc<INV>(v[4 + 1], c1, s1);          // W^1
+        v[4 + 2] = cmulc<INV>(v[4 + 2], h, h);            // W^2
+        v[4 + 3] = cmulc<INV>(v[4 + 3], s1, c1);          // W^3
+        v[8 + 1] = cmulc<INV>(v[8 + 1], h, h);            // W^2
+        v[8 + 2] = rot<INV>(v[8 + 2]);                    // W^4
+        v[8 + 3] = cmulc<INV>(v[8 + 3], -h, h);           // W^6
+        v[12 + 1] = cmulc<INV>(v[12 + 1], s1, c1);        // W^3
+        v[12 + 2] = cmulc<INV>(v[12 + 2], -h, h);         // W^6
+        v[12 + 3] = cmulc<INV>(v[12 + 3], -c1, -s1);      // W^9
+        cx<T> o[16];
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            cx<T> a0 = v[4 * k1], a1 = v[4 * k1 + 1], a2 = v[4 * k1 + 2], a3 = v[4 * k1 + 3];
+            dft4<INV>(a0, a1, a2, a3);                    // over n2 -> k2
+            o[k1] = a0;
+            o[k1 + 4] = a1;
+            o[k1 + 8] = a2;
+            o[k1 + 12] = a3;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = o[i];
+    }
+};
+
+// ------------------------------------------------------------------ factorisation of Mc = mfft/2
+template <int LOGMC> struct Fac;
+template <> struct Fac<4>  { static constexpr int NP = 2, R1 = 4,  R2 = 4,  R3 = 1; };
+template <> struct Fac<5>  { static constexpr int NP = 2, R1 = 8,  R2 = 4,  R3 = 1; };
+template <> struct Fac<6>  { static constexpr int NP = 2, R1 = 8,  R2 = 8,  R3 = 1; };
+template <> struct Fac<7>  { static constexpr int NP = 2, R1 = 16, R2 = 8,  R3 = 1; };
+template <> struct Fac<8>  { static constexpr int NP = 2, R1 = 16, R2 = 16, R3 = 1; };
+template <> struct Fac<9>  { static constexpr int NP = 3, R1 = 8,  R2 = 8,  R3 = 8; };
+template <> struct Fac<10> { static constexpr int NP = 3, R1 = 16, R2 = 8,  R3 = 8; };
+template <> struct Fac<11> { static constexpr int NP = 3, R1 = 16, R2 = 16, R3 = 8; };
+template <> struct Fac<12> { static constexpr int NP = 3, R1 = 16, R2 = 16, R3 = 16; };
+
+// radices / table offsets for a runtime log2(Mc) (host side: twiddle table layout)
+inline void fac_of(int logmc, int *np, int *r1, int *r2, int *r3) {
+    static const int tab[13][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0},
+                                   {2, 4, 4, 1}, {2, 8, 4, 1}, {2, 8, 8, 1}, {2, 16, 8, 1},
+                                   {2, 16, 16, 1}, {3, 8, 8, 8}, {3, 16, 8, 8}, {3, 16, 16, 8},
+                                   {3, 16, 16, 16}};
+    *np = tab[logmc][0]; *r1 = tab[logmc][1]; *r2 = tab[logmc][2]; *r3 = tab[logmc][3];
+}
+
+template <typename T, int LOGMC, int TF_, int NSUB_>
+struct Geo {
+    using F = Fac<LOGMC>;
+    static constexpr int MC = 1 << LOGMC, M = 2 * MC;
+    static constexpr int TF = TF_, NSUB = NSUB_, NT = TF_ * NSUB_;
+    static constexpr int NP = F::NP, R1 = F::R1, R2 = F::R2, R3 = F::R3;
+    static constexpr int RL = (NP == 2) ? R2 : R3;        // radix of the last pass
+    static constexpr int L1 = MC / R1;                    // groups of pass 1
+    static constexpr int L2 = (NP == 3) ? L1 / R2 : 1;    // groups per block of the middle pass
+    static constexpr int G = MC / RL;                     // groups of the last pass
+    // twiddle table (complex T, interleaved): [tw1: MC][tw2: L1][twp: MC + 1]
+    static constexpr int TW1 = 0, TW2 = 2 * MC, TWP = 2 * (MC + L1);
+    // work-memory offset (in complex elements) of last-pass group g: bins k = g + G d
+    VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
+};
+
+// Shared-memory layout of the staged signal: sample i of the tile lives at
+// i + (i / H) * padw, so that the slice stride H + padw keeps lane accesses conflict free.
+struct TileLayout {
+    int H, padw, logH;        // logH >= 0 if H is a power of two
+    VHD int row(int i) const { return logH >= 0 ? (i >> logH) : (i / H); }
+    VHD int addr(int i) const { return i + row(i) * padw; }
+};
+
+// ================================================================== FORWARD
+template <typename T>
+struct FwdCtx {
+    const T *x;
+    void *out;
+    FwdParams prm;
+    const T *win;            // [N] window * 0.5 (the 1/2 of the real-FFT split, exact)
+    const T *tw;
+    T *xin;                  // staged signal tile (shared)
+    cx<T> *work;             // [MC][TF] (shared)
+    int64_t b, pt;           // signal, tile index
+    TileLayout lay;
+    int vec;                 // ps, H, N even -> paired loads
+};
+
+template <typename T, int LOGMC, int TF_, int NSUB_>
+struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
+    using GEO = Geo<T, LOGMC, TF_, NSUB_>;
+    using C = cx<T>;
+    using GEO::MC; using GEO::M; using GEO::TF; using GEO::NSUB; using GEO::NT; using GEO::NP;
+    using GEO::R1; using GEO::R2; using GEO::R3; using GEO::RL; using GEO::L1; using GEO::L2;
+    using GEO::G;
+
+    // ---- phase 0: stage the tile's samples, zero outside [0, n)  (src/lib.rs:631-645)
+    VHD static void fill(const FwdCtx<T> &c, int tid) {
+        const FwdParams &p = c.prm;
+        const int span = (TF - 1) * (int)p.H + (int)p.N;
+        const int64_t s0 = (p.p0 + c.pt * TF) * p.H + p.k_offset - p.mid;
+        const T *xb = c.x + c.b * p.x_pitch;
+        for (int i = tid; i < span; i += NT) {
+            const int64_t s = s0 + i;
+            T v = (T)0;
+            if (s >= 0 && s < p.n) v = ldg(xb + s);
+            c.xin[c.lay.addr(i)] = v;
+        }
+    }
+
+    // windowed, rolled, zero-padded sample pair x'[2m], x'[2m+1] of slice f
+    VHD static C load_pair(const FwdCtx<T> &c, int f, int m) {
+        const FwdParams &p = c.prm;
+        const int ps = (int)p.ps, N = (int)p.N, H = (int)p.H;
+        int j0 = 2 * m + ps;
+        if (j0 >= M) j0 -= M;
+        if (c.vec) {
+            if (j0 >= N) return mk<T>(0, 0);
+            const int a = c.lay.addr(f * H + j0);           // even
+            const C w = ldgc(c.win + j0);
+            return mk<T>(c.xin[a] * w.x, c.xin[a + 1] * w.y);
+        }
+        int j1 = j0 + 1;
+        if (j1 >= M) j1 -= M;
+        T v0 = 0, v1 = 0;
+        if (j0 < N) v0 = c.xin[c.lay.addr(f * H + j0)] * ldg(c.win + j0);
+        if (j1 < N) v1 = c.xin[c.lay.addr(f * H + j1)] * ldg(c.win + j1);
+        return mk<T>(v0, v1);
+    }
+
+    // ---- pass 1: groups j in [0, L1): DFT_R1 over z[j + L1 a], twiddle W_Mc^(j c)
+    VHD static void pass1(const FwdCtx<T> &c, int tid) {
+        const int f = tid % TF, sub = tid / TF;
+        for (int j = sub; j < L1; j += NSUB) {
+            C v[R1];
+#pragma unroll
+            for (int a = 0; a < R1; ++a) v[a] = load_pair(c, f, j + L1 * a);
+            Dft<R1, false, T>::run(v);
+            c.work[(j)*TF + f] = v[0];
+#pragma unroll
+            for (int cc = 1; cc < R1; ++cc) {
+                const C w = ldgc(c.tw + GEO::TW1 + 2 * (j * R1 + cc));
+                c.work[(j + L1 * cc) * TF + f] = cmul(v[cc], w);
+            }
+        }
+    }
+
+    // ---- middle pass (3-pass plans): block cb, groups j2 in [0, L2): DFT_R2, twiddle W_L1^(j2 c2)
+    VHD static void pass_mid(const FwdCtx<T> &c, int tid) {
+        if (NP != 3) return;
+        const int f = tid % TF, sub = tid / TF;
+        for (int u = sub; u < R1 * L2; u += NSUB) {
+            const int cb = u / L2, j2 = u % L2;
+            const int base = cb * L1 + j2;
+            C v[R2];
+#pragma unroll
+            for (int a = 0; a < R2; ++a) v[a] = c.work[(base + L2 * a) * TF + f];
+            Dft<R2, false, T>::run(v);
+            c.work[base * TF + f] = v[0];
+#pragma unroll
+            for (int cc = 1; cc < R2; ++cc) {
+                const C w = ldgc(c.tw + GEO::TW2 + 2 * (j2 * R2 + cc));
+                c.work[(base + L2 * cc) * TF + f] = cmul(v[cc], w);
+            }
+        }
+    }
+
+    // store one-sided bin k (0 <= k <= Mc) of slice column pl according to the mode
+    VHD static void store_bin(const FwdCtx<T> &c, int64_t pl, int k, C X) {
+        const FwdParams &p = c.prm;
+        if (k == 0 || k == MC) X.y = (T)0;                  // src/lib.rs:378-384
+        const int64_t rowb = c.b * p.F;
+        if (p.mode >= 2) {
+            if (p.mode == 3 && k >= 1 && k <= MC - 1) {     // src/lib.rs:397-403
+                X.x *= (T)p.fac2x;
+                X.y *= (T)p.fac2x;
+            }
+            const int64_t o = (rowb + k) * p.ldp + pl;
+            if (p.spectrogram) ((T *)c.out)[o] = X.x * X.x + X.y * X.y;
+            else ((C *)c.out)[o] = X;
+            return;
+        }
+        // two-sided layouts: bin k and its mirror M - k (x is real)
+        int kk = k, km = (k == 0 || k == MC) ? -1 : M - k;
+        if (p.mode == 1) {                                  // fftshift, src/lib.rs:508-513
+            kk = (k + MC) % M;
+            if (km >= 0) km = (km + MC) % M;
+        }
+        const int64_t o = (rowb + kk) * p.ldp + pl;
+        if (p.spectrogram) {
+            const T v = X.x * X.x + X.y * X.y;
+            ((T *)c.out)[o] = v;
+            if (km >= 0) ((T *)c.out)[(rowb + km) * p.ldp + pl] = v;
+        } else {
+            ((C *)c.out)[o] = X;
+            if (km >= 0) ((C *)c.out)[(rowb + km) * p.ldp + pl] = conj(X);
+        }
+    }
+
+    // split of the half-length spectrum: A = Z[k]/2, Zp = Z[Mc-k]/2  ->  X[k], X[Mc-k]
+    VHD static void emit(const FwdCtx<T> &c, int64_t pl, int k, C A, C Zp, bool both) {
+        const C B = conj(Zp);
+        const C E = A + B, Om = A - B;
+        const C w = ldgc(c.tw + GEO::TWP + 2 * k);          // W_M^k
+        const C D = cmul(mk<T>(w.y, -w.x), Om);             // (-i W) (A - B)
+        store_bin(c, pl, k, E + D);
+        if (both) store_bin(c, pl, MC - k, conj(E - D));
+    }
+
+    // ---- last pass: groups (g, G-g): DFT_RL, real-FFT split, mode epilogue, global store
+    VHD static void pass_last(const FwdCtx<T> &c, int tid) {
+        const int f = tid % TF, sub = tid / TF;
+        const int64_t pl = c.pt * TF + f;
+        const bool live = pl < c.prm.P;
+        for (int s = sub; s < G / 2; s += NSUB) {
+            const int g = s, gp = (s == 0) ? G / 2 : G - s;
+            C u[RL], up[RL];
+            const int o1 = GEO::goff(g), o2 = GEO::goff(gp);
+#pragma unroll
+            for (int d = 0; d < RL; ++d) {
+                u[d] = c.work[(o1 + d) * TF + f];
+                up[d] = c.work[(o2 + d) * TF + f];
+            }
+            Dft<RL, false, T>::run(u);
+            Dft<RL, false, T>::run(up);
+            if (!live) continue;
+            if (s != 0) {
+#pragma unroll
+                for (int d = 0; d < RL; ++d) emit(c, pl, g + G * d, u[d], up[RL - 1 - d], true);
+            } else {
+                emit(c, pl, 0, u[0], u[0], true);                         // X[0], X[Mc]
+#pragma unroll
+                for (int d = 1; d < RL / 2; ++d) emit(c, pl, G * d, u[d], u[RL - d], true);
+                emit(c, pl, MC / 2, u[RL / 2], u[RL / 2], false);         // self-mirrored
+#pragma unroll
+                for (int d = 0; d < RL / 2; ++d)
+                    emit(c, pl, G / 2 + G * d, up[d], up[RL - 1 - d], true);
+            }
+        }
+    }
+};
+
+// ================================================================== INVERSE
+template <typename T>
+struct InvCtx {
+    const void *S;
+    T *xo;
+    InvParams prm;
+    const T *dual;           // [N] dual window / M (two-sided modes: / 2M), exact scaling
+    const T *tw;
+    cx<T> *work;             // [MC][TF]  (shared)
+    T *ola;                  // [TF][N + opad] -- ALIASES work
+    int64_t b, qa;           // signal, first slice computed by this tile
+    int halo;                // ceil(N/H) - 1 leading slices recomputed for the overlap
+    int ostride;             // N + opad
+};
+
+template <typename T, int LOGMC, int TF_, int NSUB_>
+struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
+    using GEO = Geo<T, LOGMC, TF_, NSUB_>;
+    using C = cx<T>;
+    using GEO::MC; using GEO::M; using GEO::TF; using GEO::NSUB; using GEO::NT; using GEO::NP;
+    using GEO::R1; using GEO::R2; using GEO::R3; using GEO::RL; using GEO::L1; using GEO::L2;
+    using GEO::G;
+    static constexpr int GPT = (G + NSUB - 1) / NSUB;       // last-pass groups per thread
+
+    // Hermitian one-sided bin k (0 <= k <= Mc) of column col, mode undone (src/lib.rs:414-487);
+    // scaled by 2 for the two-sided layouts (folded into the dual window).
+    VHD static C load_bin(const InvCtx<T> &c, int64_t col, int k) {
+        const InvParams &p = c.prm;
+        const C *S = (const C *)c.S;
+        const int64_t rowb = c.b * p.F;
+        C v;
+        if (p.mode >= 2) {
+            v = S[(rowb + k) * p.ldp + col];
+            if (p.mode == 3 && k >= 1 && k <= MC - 1) {
+                const T r = (T)(1.0 / p.fac2x);
+                v.x *= r;
+                v.y *= r;
+            }
+        } else {
+            int k1 = k, k2 = (k == 0) ? 0 : M - k;          // X[k] + conj(X[M-k])
+            if (p.mode == 1) {                              // ifftshift, src/lib.rs:516-521
+                k1 = (k1 + MC) % M;
+                k2 = (k2 + MC) % M;
+            }
+            const C a = S[(rowb + k1) * p.ldp + col];
+            const C bq = S[(rowb + k2) * p.ldp + col];
+            v = a + conj(bq);
+        }
+        if (k == 0 || k == MC) v.y = (T)0;                  // irfft ignores Im(DC), Im(Nyquist)
+        return v;
+    }
+
+    // Z'[k] = 2 Z[k], Z'[Mc-k] from X[k], X[Mc-k]
+    VHD static void merge(const InvCtx<T> &c, int k, C &a, C &bm) {
+        const C Xk = a, Xm = conj(bm);
+        const C E = Xk + Xm, Dm = Xk - Xm;
+        const C w = ldgc(c.tw + GEO::TWP + 2 * k);          // W_M^k ; need conj(W) * Dm
+        const C O = cmul(conj(w), Dm);
+        const C iO = mk<T>(-O.y, O.x);
+        a = E + iO;
+        bm = conj(E - iO);
+    }
+
+    // ---- pass 1: load S columns (coalesced over slices), undo mode, real-IFFT merge, IDFT_R1
+    VHD static void pass1(const InvCtx<T> &c, int tid) {
+        const InvParams &p = c.prm;
+        const int f = tid % TF, sub = tid / TF;
+        const int64_t q = c.qa + f;
+        const int64_t col = q - p.p_min;
+        const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+        for (int s = sub; s < L1 / 2; s += NSUB) {
+            const int j = s, jp = (s == 0) ? L1 / 2 : L1 - s;
+            C v[R1], vp[R1];
+            if (live) {
+#pragma unroll
+                for (int a = 0; a < R1; ++a) {
+                    v[a] = load_bin(c, col, j + L1 * a);
+                    vp[a] = load_bin(c, col, jp + L1 * a);
+                }
+                if (s != 0) {
+#pragma unroll
+                    for (int a = 0; a < R1; ++a) merge(c, j + L1 * a, v[a], vp[R1 - 1 - a]);
+                } else {
+                    const C xn = load_bin(c, col, MC);       // Nyquist pairs with DC
+                    v[0] = mk<T>(v[0].x + xn.x, v[0].x - xn.x);
+#pragma unroll
+                    for (int a = 1; a < R1 / 2; ++a) merge(c, L1 * a, v[a], v[R1 - a]);
+                    {
+                        C t = v[R1 / 2];
+                        merge(c, MC / 2, v[R1 / 2], t);
+                    }
+#pragma unroll
+                    for (int a = 0; a < R1 / 2; ++a) merge(c, jp + L1 * a, vp[a], vp[R1 - 1 - a]);
+                }
+            } else {
+#pragma unroll
+                for (int a = 0; a < R1; ++a) v[a] = vp[a] = mk<T>(0, 0);
+            }
+            Dft<R1, true, T>::run(v);
+            Dft<R1, true, T>::run(vp);
+            c.work[j * TF + f] = v[0];
+            c.work[jp * TF + f] = vp[0];
+#pragma unroll
+            for (int cc = 1; cc < R1; ++cc) {
+                const C w = conj(ldgc(c.tw + GEO::TW1 + 2 * (j * R1 + cc)));
+                const C wp = conj(ldgc(c.tw + GEO::TW1 + 2 * (jp * R1 + cc)));
+                c.work[(j + L1 * cc) * TF + f] = cmul(v[cc], w);
+                c.work[(jp + L1 * cc) * TF + f] = cmul(vp[cc], wp);
+            }
+        }
+    }
+
+    VHD static void pass_mid(const InvCtx<T> &c, int tid) {
+        if (NP != 3) return;
+        const int f = tid % TF, sub = tid / TF;
+        for (int u = sub; u < R1 * L2; u += NSUB) {
+            const int cb = u / L2, j2 = u % L2;
+            const int base = cb * L1 + j2;
+            C v[R2];
+#pragma unroll
+            for (int a = 0; a < R2; ++a) v[a] = c.work[(base + L2 * a) * TF + f];
+            Dft<R2, true, T>::run(v);
+            c.work[base * TF + f] = v[0];
+#pragma unroll
+            for (int cc = 1; cc < R2; ++cc) {
+                const C w = conj(ldgc(c.tw + GEO::TW2 + 2 * (j2 * R2 + cc)));
+                c.work[(base + L2 * cc) * TF + f] = cmul(v[cc], w);
+            }
+        }
+    }
+
+    // ---- last pass, part A: IDFT_RL into registers (work is about to be reused as `ola`)
+    VHD static void last_load(const InvCtx<T> &c, int tid, C (&r)[GPT][RL]) {
+        const int f = tid % TF, sub = tid / TF;
+#pragma unroll
+        for (int i = 0; i < GPT; ++i) {
+            const int g = sub + NSUB * i;
+            if (g < G) {
+                const int o = GEO::goff(g);
+#pragma unroll
+                for (int d = 0; d < RL; ++d) r[i][d] = c.work[(o + d) * TF + f];
+                Dft<RL, true, T>::run(r[i]);
+            }
+        }
+    }
+    // ---- last pass, part B: roll back (src/lib.rs:499-500), truncate to N, dual window
+    VHD static void last_store(const InvCtx<T> &c, int tid, const C (&r)[GPT][RL]) {
+        const InvParams &p = c.prm;
+        const int f = tid % TF, sub = tid / TF;
+        const int ps = (int)p.ps, N = (int)p.N;
+        T *row = c.ola + (size_t)f * c.ostride;
+#pragma unroll
+        for (int i = 0; i < GPT; ++i) {
+            const int g = sub + NSUB * i;
+            if (g < G) {
+#pragma unroll
+                for (int d = 0; d < RL; ++d) {
+                    const int m = g + G * d;                // z[m] = (y[2m], y[2m+1])
+                    int j0 = 2 * m + ps;
+                    if (j0 >= M) j0 -= M;
+                    int j1 = j0 + 1;
+                    if (j1 >= M) j1 -= M;
+                    if (j0 < N) row[j0] = r[i][d].x * ldg(c.dual + j0);
+                    if (j1 < N) row[j1] = r[i][d].y * ldg(c.dual + j1);
+                }
+            }
+        }
+    }
+
+    // ---- overlap-add as a gather over the samples this tile owns, increasing q
+    VHD static void gather(const InvCtx<T> &c, int tid) {
+        const InvParams &p = c.prm;
+        const int64_t H = p.H, N = p.N, mid = p.mid;
+        const int64_t qo = c.qa + c.halo;                    // first owned "latest slice"
+        int64_t ka = qo * H - mid, kb = (c.qa + TF) * H - mid;
+        if (ka < p.k0) ka = p.k0;
+        if (kb > p.k1) kb = p.k1;
+        T *xo = c.xo + c.b * p.out_pitch;
+        for (int64_t k = ka + tid; k < kb; k += NT) {
+            const int64_t a = k + mid;
+            const int64_t qhi = (a >= 0) ? a / H : -((-a + H - 1) / H);
+            T acc = (T)0;
+            for (int64_t q = qhi - c.halo; q <= qhi; ++q) {
+                const int64_t jj = a - q * H;
+                if (jj < N) acc += c.ola[(size_t)(q - c.qa) * c.ostride + jj];
+            }
+            xo[k - p.k0] = acc;
+        }
+    }
+};
+
+}  // namespace p2
+}  // namespace veils
