@@ -29,19 +29,16 @@ struct EmuFwd {
     template <typename T, int LOGMC, int TF, int NSUB>
     int run() {
         using K = Fwd<T, LOGMC, TF, NSUB>;
-        const bool vec = fwd_vec(prm.ps, prm.H, prm.N);
-        const TileLayout lay = tile_layout(prm.H, vec);
-        std::vector<cx<T>> work((size_t)K::MC * TF);
-        std::vector<T> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, lay));
         std::vector<double> twd((size_t)twiddle_count(prm.M));
         twiddle_fill(prm.M, twd.data());
         std::vector<T> tw = conv<T>(twd), win = conv<T>(pl->win, 0.5);
         FwdCtx<T> c;
-        c.x = (const T *)x; c.out = out; c.prm = prm; c.win = win.data(); c.tw = tw.data();
-        c.work = work.data(); c.xin = xin.data(); c.lay = lay; c.vec = vec;
-        const int64_t ptiles = (prm.P + TF - 1) / TF;
-        for (int64_t blk = 0; blk < ptiles * prm.batch; ++blk) {
-            c.b = blk / ptiles; c.pt = blk % ptiles;
+        c.a = make_fwd_args<T>((const T *)x, out, prm, win.data(), tw.data(), TF);
+        std::vector<cx<T>> work((size_t)K::MC * TF);
+        std::vector<T> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay));
+        c.work = work.data(); c.xin = xin.data();
+        for (int64_t blk = 0; blk < c.a.ptiles * prm.batch; ++blk) {
+            c.b = blk / c.a.ptiles; c.pt = blk % c.a.ptiles;
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
@@ -56,23 +53,20 @@ struct EmuInv {
     template <typename T, int LOGMC, int TF, int NSUB>
     int run() {
         using K = Inv<T, LOGMC, TF, NSUB>;
-        const int halo = inv_halo(prm.N, prm.H), own = TF - halo;
-        const int ostride = inv_ostride(prm.N);
-        size_t elems = (size_t)K::MC * TF * 2;
-        if ((size_t)TF * ostride > elems) elems = (size_t)TF * ostride;
-        std::vector<T> buf(elems);
         std::vector<double> twd((size_t)twiddle_count(prm.M));
         twiddle_fill(prm.M, twd.data());
         const double sc = 1.0 / ((double)prm.M * (prm.mode >= 2 ? 1.0 : 2.0));
         std::vector<T> tw = conv<T>(twd), dual = conv<T>(pl->dual, sc);
         InvCtx<T> c;
-        c.S = S; c.xo = (T *)xo; c.prm = prm; c.dual = dual.data(); c.tw = tw.data();
-        c.work = (cx<T> *)buf.data(); c.ola = buf.data(); c.halo = halo; c.ostride = ostride;
-        const int64_t qh0 = floordiv(prm.k0 + prm.mid, prm.H), qh1 = floordiv(prm.k1 - 1 + prm.mid, prm.H);
-        const int64_t ntiles = (qh1 - qh0 + 1 + own - 1) / own;
+        c.a = make_inv_args<T>(S, (T *)xo, prm, dual.data(), tw.data(), TF);
+        size_t elems = (size_t)K::MC * TF * 2;
+        if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
+        std::vector<T> buf(elems + 4);
+        c.work = (cx<T> *)buf.data(); c.ola = buf.data();
+        const int own = TF - c.a.halo;
         std::vector<cx<T>> regs((size_t)K::NT * K::GPT * K::RL);
-        for (int64_t blk = 0; blk < ntiles * prm.batch; ++blk) {
-            c.b = blk / ntiles; c.qa = qh0 - halo + (blk % ntiles) * own;
+        for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
+            c.b = blk / c.a.ntiles; c.qa = c.a.qa0 + (blk % c.a.ntiles) * own;
             for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
             for (int t = 0; t < K::NT; ++t) {

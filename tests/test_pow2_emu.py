@@ -74,7 +74,7 @@ CASES = [  # (mfft, m_num, hop, mode, phase_shift, scale)
     (512, 511, 97, "onesided", 3, None), (1024, 1024, 256, "twosided", 0, None),
     (2048, 2048, 512, "onesided", 0, None), (4096, 4096, 1024, "onesided", 0, None),
     (8192, 8192, 2048, "onesided2X", 0, "magnitude"), (256, 100, 25, "centered", -7, None),
-    (64, 33, 11, "onesided", 5, None),
+    (64, 33, 11, "onesided", 5, None), (64, 64, 2, "onesided", 0, None), (32, 20, 3, "twosided", 0, None),
 ]
 
 

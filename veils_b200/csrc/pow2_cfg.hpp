@@ -90,12 +90,12 @@ inline void twiddle_fill(int64_t M, double *t) {
 inline TileLayout tile_layout(int64_t H, bool vec) {
     TileLayout l;
     l.H = (int)H;
-    l.logH = ilog2_exact(H);
+    l.magic = (unsigned)((0x100000000ULL + (unsigned long long)H - 1) / (unsigned long long)H);
     if (vec) l.padw = (int)((2 - (H % 4) + 4) % 4);   // H even -> padw in {2, 0}
     else l.padw = (H % 2 == 0) ? 1 : 0;
     return l;
 }
-inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H % 2 == 0 && N % 2 == 0; }
+inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H % 2 == 0 && N % 2 == 0 && H >= 4; }
 
 inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) {
     const int64_t span = (int64_t)(tf - 1) * H + N;
@@ -117,10 +117,51 @@ inline size_t inv_smem_bytes(int64_t M, int64_t N, int precision, const Cfg &c) 
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
+template <typename T>
+inline FwdArgs<T> make_fwd_args(const T *x, void *out, const FwdParams &p, const T *win_half, const T *tw, int tf) {
+    FwdArgs<T> a;
+    a.x = x; a.out = out; a.win = win_half; a.tw = tw;
+    a.n = p.n; a.x_pitch = p.x_pitch; a.ldp = p.ldp; a.p0 = p.p0; a.P = p.P; a.k_offset = p.k_offset;
+    a.ptiles = (p.P + tf - 1) / tf;
+    a.N = (int)p.N; a.H = (int)p.H; a.mid = (int)p.mid; a.ps = (int)p.ps; a.F = (int)p.F;
+    a.vec = fwd_vec(p.ps, p.H, p.N) ? 1 : 0;
+    a.lay = tile_layout(p.H, a.vec != 0);
+    a.magic_hp = a.vec ? (unsigned)((0x100000000ULL + (unsigned long long)(p.H / 2) - 1) / (unsigned long long)(p.H / 2)) : 0u;
+    a.padded = p.N < p.M ? 1 : 0;
+    a.mode = p.mode;
+    a.shift = p.mode == 1 ? (int)(p.M / 2) : 0;
+    a.spectrogram = p.spectrogram;
+    a.fac2x = p.mode == 3 ? (T)p.fac2x : (T)1;
+    return a;
+}
+inline int64_t fdiv64(int64_t a, int64_t b) {
+    int64_t q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+template <typename T>
+inline InvArgs<T> make_inv_args(const void *S, T *xo, const InvParams &p, const T *dual_scaled, const T *tw, int tf) {
+    InvArgs<T> a;
+    a.S = S; a.xo = xo; a.dual = dual_scaled; a.tw = tw;
+    a.P = p.P; a.ldp = p.ldp; a.out_pitch = p.out_pitch; a.p_min = p.p_min;
+    a.k0 = p.k0; a.k1 = p.k1; a.q0 = p.q0; a.q1 = p.q1;
+    a.N = (int)p.N; a.H = (int)p.H; a.mid = (int)p.mid; a.ps = (int)p.ps; a.F = (int)p.F;
+    a.mode = p.mode;
+    a.shift = p.mode == 1 ? (int)(p.M / 2) : 0;
+    a.rfac2x = p.mode == 3 ? (T)(1.0 / p.fac2x) : (T)1;
+    a.magic_h = (unsigned)((0x100000000ULL + (unsigned long long)p.H - 1) / (unsigned long long)p.H);
+    a.halo = inv_halo(p.N, p.H);
+    a.ostride = inv_ostride(p.N);
+    const int own = tf - a.halo;
+    const int64_t qh0 = fdiv64(p.k0 + p.mid, p.H), qh1 = fdiv64(p.k1 - 1 + p.mid, p.H);
+    a.ntiles = (qh1 - qh0 + 1 + own - 1) / own;
+    a.qa0 = qh0 - a.halo;
+    return a;
+}
+
 inline bool supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse) {
     Cfg c;
     if (!cfg_for(M, precision, &c)) return false;
-    if (N > M || H < 1) return false;
+    if (N > M || H < 2 || H >= 65536) return false;
     if (!inverse) return fwd_smem_bytes(M, N, H, ps, precision, c) <= SMEM_LIMIT;
     if (H > N) return false;
     if (inv_halo(N, H) >= c.tf) return false;         // at least one owned slice per tile

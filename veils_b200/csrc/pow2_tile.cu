@@ -8,21 +8,21 @@ namespace {
 
 using namespace p2;
 
+// two CTAs per SM whenever the work buffer (Mc * TF complex) allows it
+template <typename T, int LOGMC, int TF>
+constexpr int min_ctas() { return sizeof(T) * 2 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
+
 template <typename T, int LOGMC, int TF, int NSUB>
-__global__ void __launch_bounds__(TF *NSUB)
-pow2_fwd_kernel(const T *__restrict__ x, void *__restrict__ out, FwdParams prm,
-                const T *__restrict__ win, const T *__restrict__ tw, TileLayout lay, int vec) {
+__global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
+pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = Fwd<T, LOGMC, TF, NSUB>;
     FwdCtx<T> c;
-    c.x = x; c.out = out; c.prm = prm; c.win = win; c.tw = tw;
+    c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
     c.xin = reinterpret_cast<T *>(smem + sizeof(cx<T>) * K::MC * TF);
-    const int64_t ptiles = (prm.P + TF - 1) / TF;
-    c.b = blockIdx.x / ptiles;
-    c.pt = blockIdx.x % ptiles;
-    c.lay = lay;
-    c.vec = vec;
+    c.b = blockIdx.y;
+    c.pt = blockIdx.x;
     const int tid = threadIdx.x;
     K::fill(c, tid);
     __syncthreads();
@@ -36,20 +36,16 @@ pow2_fwd_kernel(const T *__restrict__ x, void *__restrict__ out, FwdParams prm,
 }
 
 template <typename T, int LOGMC, int TF, int NSUB>
-__global__ void __launch_bounds__(TF *NSUB)
-pow2_inv_kernel(const void *__restrict__ S, T *__restrict__ xo, InvParams prm,
-                const T *__restrict__ dual, const T *__restrict__ tw, int64_t qa0, int64_t ntiles,
-                int halo, int ostride) {
+__global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
+pow2_inv_kernel(const __grid_constant__ InvArgs<T> args) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = Inv<T, LOGMC, TF, NSUB>;
     InvCtx<T> c;
-    c.S = S; c.xo = xo; c.prm = prm; c.dual = dual; c.tw = tw;
+    c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
     c.ola = reinterpret_cast<T *>(smem);
-    c.b = blockIdx.x / ntiles;
-    c.qa = qa0 + (int64_t)(blockIdx.x % ntiles) * (TF - halo);
-    c.halo = halo;
-    c.ostride = ostride;
+    c.b = blockIdx.y;
+    c.qa = args.qa0 + (int64_t)blockIdx.x * (TF - args.halo);
     const int tid = threadIdx.x;
     K::pass1(c, tid);
     __syncthreads();
@@ -65,24 +61,28 @@ pow2_inv_kernel(const void *__restrict__ S, T *__restrict__ xo, InvParams prm,
     K::gather(c, tid);
 }
 
+// batch is mapped to gridDim.y (<= 65535 per launch); larger batches are launched in slabs
 struct FwdLaunch {
     const void *x; void *out; const FwdParams *prm; const void *win; const void *tw; cudaStream_t st;
     template <typename T, int LOGMC, int TF, int NSUB>
     cudaError_t run() {
         const FwdParams &p = *prm;
-        const bool vec = fwd_vec(p.ps, p.H, p.N);
-        const TileLayout lay = tile_layout(p.H, vec);
+        FwdArgs<T> a = make_fwd_args<T>((const T *)x, out, p, (const T *)win, (const T *)tw, TF);
         const size_t smem = sizeof(cx<T>) * (size_t)(1 << LOGMC) * TF +
-                            sizeof(T) * (size_t)fwd_xin_elems(p.N, p.H, TF, lay);
+                            sizeof(T) * (size_t)fwd_xin_elems(p.N, p.H, TF, a.lay);
         auto kern = pow2_fwd_kernel<T, LOGMC, TF, NSUB>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        const int64_t ptiles = (p.P + TF - 1) / TF;
-        const int64_t blocks = ptiles * p.batch;
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        kern<<<(unsigned)blocks, TF * NSUB, smem, st>>>((const T *)x, out, p, (const T *)win,
-                                                        (const T *)tw, lay, vec ? 1 : 0);
-        ++g_launch_count;
+        if (a.ptiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        const size_t osz = p.spectrogram ? sizeof(T) : sizeof(cx<T>);
+        for (int64_t b0 = 0; b0 < p.batch; b0 += 65535) {
+            const int64_t nb = p.batch - b0 < 65535 ? p.batch - b0 : 65535;
+            FwdArgs<T> as = a;
+            as.x = a.x + b0 * p.x_pitch;
+            as.out = (char *)out + (size_t)b0 * p.F * p.ldp * osz;
+            kern<<<dim3((unsigned)a.ptiles, (unsigned)nb), TF * NSUB, smem, st>>>(as);
+            ++g_launch_count;
+        }
         return cudaGetLastError();
     }
 };
@@ -92,29 +92,24 @@ struct InvLaunch {
     template <typename T, int LOGMC, int TF, int NSUB>
     cudaError_t run() {
         const InvParams &p = *prm;
-        const int halo = inv_halo(p.N, p.H);
-        const int own = TF - halo;
-        if (own < 1) return cudaErrorInvalidConfiguration;
-        const int64_t qh0 = floordiv_i64(p.k0 + p.mid, p.H);
-        const int64_t qh1 = floordiv_i64(p.k1 - 1 + p.mid, p.H);
-        const int64_t ntiles = (qh1 - qh0 + 1 + own - 1) / own;
-        const int ostride = inv_ostride(p.N);
+        if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
+        InvArgs<T> a = make_inv_args<T>(S, (T *)xo, p, (const T *)dual, (const T *)tw, TF);
         size_t smem = sizeof(cx<T>) * (size_t)(1 << LOGMC) * TF;
-        const size_t ola = sizeof(T) * (size_t)TF * ostride;
+        const size_t ola = sizeof(T) * (size_t)TF * a.ostride;
         if (ola > smem) smem = ola;
         auto kern = pow2_inv_kernel<T, LOGMC, TF, NSUB>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        const int64_t blocks = ntiles * p.batch;
-        if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        kern<<<(unsigned)blocks, TF * NSUB, smem, st>>>(S, (T *)xo, p, (const T *)dual, (const T *)tw,
-                                                        qh0 - halo, ntiles, halo, ostride);
-        ++g_launch_count;
+        if (a.ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        for (int64_t b0 = 0; b0 < p.batch; b0 += 65535) {
+            const int64_t nb = p.batch - b0 < 65535 ? p.batch - b0 : 65535;
+            InvArgs<T> as = a;
+            as.S = (const char *)S + (size_t)b0 * p.F * p.ldp * sizeof(cx<T>);
+            as.xo = a.xo + b0 * p.out_pitch;
+            kern<<<dim3((unsigned)a.ntiles, (unsigned)nb), TF * NSUB, smem, st>>>(as);
+            ++g_launch_count;
+        }
         return cudaGetLastError();
-    }
-    static int64_t floordiv_i64(int64_t a, int64_t b) {
-        int64_t q = a / b;
-        return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
     }
 };
 

@@ -15,10 +15,10 @@
 //     complex FFT (Mc = mfft/2): z[m] = x'[2m] + i x'[2m+1]; the split into the mfft/2+1 one-sided
 //     bins happens in registers in the last pass because a thread holds the groups (g, G-g)
 //     whose bins are each other's mirror images.
-//   * Stockham-free in-place decimation: pass 1 reads straight from the staged signal tile
-//     (frame extraction, zero padding, windowing and the phase-shift roll of
-//     src/lib.rs:336-345, 612-652 are pure load-index arithmetic), middle pass in place,
-//     last pass from shared memory to global memory (mode epilogue src/lib.rs:354-408).
+//   * In-place decimation: pass 1 reads straight from the staged signal tile (frame extraction,
+//     zero padding, windowing and the phase-shift roll of src/lib.rs:336-345, 612-652 are pure
+//     load-index arithmetic), middle pass in place, last pass from shared memory to global
+//     memory (mode epilogue src/lib.rs:354-408).
 //   * The inverse mirrors this: pass 1 loads S columns (coalesced over slices) and undoes the
 //     mode (src/lib.rs:414-487), the last pass multiplies by the dual window (:869-873) and the
 //     overlap-add (:876-910) is a deterministic gather in increasing q owned by this CTA.
@@ -36,7 +36,7 @@ namespace p2 {
 
 // ------------------------------------------------------------------ complex helpers
 template <typename T>
-struct cx {
+struct alignas(2 * sizeof(T)) cx {
     T x, y;
 };
 template <typename T> VHD cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
@@ -44,6 +44,9 @@ template <typename T> VHD cx<T> operator+(cx<T> a, cx<T> b) { return mk<T>(a.x +
 template <typename T> VHD cx<T> operator-(cx<T> a, cx<T> b) { return mk<T>(a.x - b.x, a.y - b.y); }
 template <typename T> VHD cx<T> cmul(cx<T> a, cx<T> b) {
     return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename T> VHD cx<T> cmulconj(cx<T> a, cx<T> w) {      // a * conj(w)
+    return mk<T>(a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y);
 }
 template <typename T> VHD cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
 // multiply by -i (forward) / +i (inverse)
@@ -63,7 +66,7 @@ template <typename T> VHD T ldg(const T *p) {
     return *p;
 #endif
 }
-template <typename T> VHD cx<T> ldgc(const T *p) {   // complex at p[0], p[1]
+template <typename T> VHD cx<T> ldgc(const T *p) {   // complex at p[0], p[1] (aligned)
 #if defined(__CUDA_ARCH__)
     if (sizeof(T) == 4) {
         const float2 v = __ldg((const float2 *)p);
@@ -74,6 +77,13 @@ template <typename T> VHD cx<T> ldgc(const T *p) {   // complex at p[0], p[1]
     }
 #else
     return mk<T>(p[0], p[1]);
+#endif
+}
+VHD unsigned mulhi_u32(unsigned a, unsigned b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (unsigned)(((unsigned long long)a * b) >> 32);
 #endif
 }
 
@@ -107,7 +117,6 @@ template <bool INV, typename T> struct Dft<8, INV, T> {
         v[3] = cmulc<INV>(v[3], h, h);                    // W8^1
         v[5] = rot<INV>(v[5]);                            // W8^2
         v[7] = cmulc<INV>(v[7], -h, h);                   // W8^3
-        // X[k1] = t0 + t1 W, X[k1+4] = t0 - t1 W ; t0[k1] = v[2k1], t1[k1] = v[2k1+1]
         cx<T> o[8];
 #pragma unroll
         for (int k1 = 0; k1 < 4; ++k1) {
@@ -187,27 +196,40 @@ struct Geo {
     VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
 };
 
-// Shared-memory layout of the staged signal: sample i of the tile lives at
-// i + (i / H) * padw, so that the slice stride H + padw keeps lane accesses conflict free.
+// Shared-memory layout of the staged signal: sample i = r * H + c of the tile lives at
+// r * (H + padw) + c, so that the slice stride H + padw keeps lane accesses conflict free.
 struct TileLayout {
-    int H, padw, logH;        // logH >= 0 if H is a power of two
-    VHD int row(int i) const { return logH >= 0 ? (i >> logH) : (i / H); }
-    VHD int addr(int i) const { return i + row(i) * padw; }
+    int H, padw;
+    unsigned magic;           // ceil(2^32 / H): j / H == umulhi(j, magic) for j, H < 2^16
+    VHD int row(int j) const { return (int)mulhi_u32((unsigned)j, magic); }
+    VHD int addr(int j) const { return j + row(j) * padw; }      // j < 2^16
 };
 
 // ================================================================== FORWARD
 template <typename T>
-struct FwdCtx {
+struct FwdArgs {
     const T *x;
     void *out;
-    FwdParams prm;
     const T *win;            // [N] window * 0.5 (the 1/2 of the real-FFT split, exact)
     const T *tw;
+    int64_t n, x_pitch, ldp, p0, P, k_offset, ptiles;
+    int N, H, mid, ps, F;
+    TileLayout lay;
+    unsigned magic_hp;       // ceil(2^32 / (H/2)) (paired staging)
+    int vec;                 // ps, H, N even -> paired shared-memory loads
+    int padded;              // N < M
+    int mode;                // Mode
+    int shift;               // centered: Mc (fftshift), else 0
+    int spectrogram;         // 1: |X|^2 real output
+    T fac2x;                 // onesided2X factor, 1 otherwise
+};
+
+template <typename T>
+struct FwdCtx {
+    FwdArgs<T> a;
     T *xin;                  // staged signal tile (shared)
     cx<T> *work;             // [MC][TF] (shared)
     int64_t b, pt;           // signal, tile index
-    TileLayout lay;
-    int vec;                 // ps, H, N even -> paired loads
 };
 
 template <typename T, int LOGMC, int TF_, int NSUB_>
@@ -219,164 +241,234 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
     using GEO::G;
 
     // ---- phase 0: stage the tile's samples, zero outside [0, n)  (src/lib.rs:631-645)
+    // Flat, unrolled (all loads in flight before the first store).  Global index of tile sample i
+    // is s0 + i; its shared address is (i / H) * (H + padw) + i % H.
     VHD static void fill(const FwdCtx<T> &c, int tid) {
-        const FwdParams &p = c.prm;
-        const int span = (TF - 1) * (int)p.H + (int)p.N;
-        const int64_t s0 = (p.p0 + c.pt * TF) * p.H + p.k_offset - p.mid;
-        const T *xb = c.x + c.b * p.x_pitch;
-        for (int i = tid; i < span; i += NT) {
-            const int64_t s = s0 + i;
-            T v = (T)0;
-            if (s >= 0 && s < p.n) v = ldg(xb + s);
-            c.xin[c.lay.addr(i)] = v;
+        const FwdArgs<T> &p = c.a;
+        const int H = p.H;
+        const int span = (TF - 1) * H + p.N;
+        const int hs = H + p.lay.padw;
+        const int64_t s0 = (p.p0 + c.pt * TF) * (int64_t)H + p.k_offset - p.mid;
+        const T *xb = p.x + c.b * p.x_pitch;
+        constexpr int U = 4;
+        if (p.vec && (((c.b * p.x_pitch + s0) & 1) == 0) && ((p.n & 1) == 0) &&
+            ((((size_t)p.x) & (2 * sizeof(T) - 1)) == 0)) {
+            // pairs: never straddle the signal borders (s0, n even) nor a tile row (H even)
+            const int np = span >> 1, hp = H >> 1;
+            for (int e0 = tid; e0 < np; e0 += NT * U) {
+                C v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * NT;
+                    const int64_t s = s0 + 2 * (int64_t)e;
+                    v[u] = mk<T>(0, 0);
+                    if (e < np && s >= 0 && s < p.n) v[u] = ldgc(xb + s);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int e = e0 + u * NT;
+                    if (e < np) {
+                        const int r = (int)mulhi_u32((unsigned)e, p.magic_hp);     // e / (H/2)
+                        *reinterpret_cast<C *>(c.xin + r * hs + 2 * (e - r * hp)) = v[u];
+                    }
+                }
+            }
+            return;
+        }
+        for (int e0 = tid; e0 < span; e0 += NT * U) {
+            T v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * NT;
+                const int64_t s = s0 + e;
+                v[u] = (T)0;
+                if (e < span && s >= 0 && s < p.n) v[u] = ldg(xb + s);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * NT;
+                if (e < span) {
+                    const int r = e / H;
+                    c.xin[r * hs + (e - r * H)] = v[u];
+                }
+            }
         }
     }
 
-    // windowed, rolled, zero-padded sample pair x'[2m], x'[2m+1] of slice f
-    VHD static C load_pair(const FwdCtx<T> &c, int f, int m) {
-        const FwdParams &p = c.prm;
-        const int ps = (int)p.ps, N = (int)p.N, H = (int)p.H;
-        int j0 = 2 * m + ps;
-        if (j0 >= M) j0 -= M;
-        if (c.vec) {
-            if (j0 >= N) return mk<T>(0, 0);
-            const int a = c.lay.addr(f * H + j0);           // even
-            const C w = ldgc(c.win + j0);
-            return mk<T>(c.xin[a] * w.x, c.xin[a + 1] * w.y);
+    // windowed, rolled, zero-padded sample pair x'[2m], x'[2m+1] of the slice whose tile base is xf
+    template <bool VEC, bool PADDED>
+    VHD static C load_pair(const FwdArgs<T> &p, const T *xf, int m) {
+        const int j0 = (2 * m + p.ps) & (M - 1);
+        if (VEC) {
+            if (PADDED && j0 >= p.N) return mk<T>(0, 0);
+            const C xv = *reinterpret_cast<const C *>(xf + p.lay.addr(j0));
+            const C w = ldgc(p.win + j0);
+            return mk<T>(xv.x * w.x, xv.y * w.y);
         }
-        int j1 = j0 + 1;
-        if (j1 >= M) j1 -= M;
+        const int j1 = (j0 + 1) & (M - 1);
         T v0 = 0, v1 = 0;
-        if (j0 < N) v0 = c.xin[c.lay.addr(f * H + j0)] * ldg(c.win + j0);
-        if (j1 < N) v1 = c.xin[c.lay.addr(f * H + j1)] * ldg(c.win + j1);
+        if (j0 < p.N) v0 = xf[p.lay.addr(j0)] * ldg(p.win + j0);
+        if (j1 < p.N) v1 = xf[p.lay.addr(j1)] * ldg(p.win + j1);
         return mk<T>(v0, v1);
     }
 
     // ---- pass 1: groups j in [0, L1): DFT_R1 over z[j + L1 a], twiddle W_Mc^(j c)
-    VHD static void pass1(const FwdCtx<T> &c, int tid) {
+    template <bool VEC, bool PADDED>
+    VHD static void pass1_t(const FwdCtx<T> &c, int tid) {
+        const FwdArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
+        const T *xf = c.xin + f * (p.H + p.lay.padw);
         for (int j = sub; j < L1; j += NSUB) {
             C v[R1];
 #pragma unroll
-            for (int a = 0; a < R1; ++a) v[a] = load_pair(c, f, j + L1 * a);
+            for (int a = 0; a < R1; ++a) v[a] = load_pair<VEC, PADDED>(p, xf, j + L1 * a);
             Dft<R1, false, T>::run(v);
-            c.work[(j)*TF + f] = v[0];
+            C *wj = c.work + j * TF + f;
+            const T *twj = p.tw + GEO::TW1 + 2 * j * R1;
+            wj[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R1; ++cc) {
-                const C w = ldgc(c.tw + GEO::TW1 + 2 * (j * R1 + cc));
-                c.work[(j + L1 * cc) * TF + f] = cmul(v[cc], w);
-            }
+            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmul(v[cc], ldgc(twj + 2 * cc));
+        }
+    }
+    VHD static void pass1(const FwdCtx<T> &c, int tid) {
+        if (c.a.vec) {
+            if (c.a.padded) pass1_t<true, true>(c, tid);
+            else pass1_t<true, false>(c, tid);
+        } else {
+            pass1_t<false, true>(c, tid);
         }
     }
 
     // ---- middle pass (3-pass plans): block cb, groups j2 in [0, L2): DFT_R2, twiddle W_L1^(j2 c2)
     VHD static void pass_mid(const FwdCtx<T> &c, int tid) {
         if (NP != 3) return;
+        const FwdArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
-            const int base = cb * L1 + j2;
+            C *wb = c.work + (cb * L1 + j2) * TF + f;
+            const T *twj = p.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
-            for (int a = 0; a < R2; ++a) v[a] = c.work[(base + L2 * a) * TF + f];
+            for (int a = 0; a < R2; ++a) v[a] = wb[L2 * a * TF];
             Dft<R2, false, T>::run(v);
-            c.work[base * TF + f] = v[0];
+            wb[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R2; ++cc) {
-                const C w = ldgc(c.tw + GEO::TW2 + 2 * (j2 * R2 + cc));
-                c.work[(base + L2 * cc) * TF + f] = cmul(v[cc], w);
-            }
+            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmul(v[cc], ldgc(twj + 2 * cc));
         }
     }
 
-    // store one-sided bin k (0 <= k <= Mc) of slice column pl according to the mode
-    VHD static void store_bin(const FwdCtx<T> &c, int64_t pl, int k, C X) {
-        const FwdParams &p = c.prm;
+    // store one-sided bin k (0 <= k <= Mc) of this thread's slice column.
+    // ONES: one-sided layouts (modes 2, 3); SPEC: |X|^2 real output.  ob: byte pointer of
+    // (row 0, this column); rb: row pitch in bytes.
+    template <bool ONES, bool SPEC>
+    VHD static void store_bin(const FwdArgs<T> &p, char *ob, int64_t rb, int k, C X) {
         if (k == 0 || k == MC) X.y = (T)0;                  // src/lib.rs:378-384
-        const int64_t rowb = c.b * p.F;
-        if (p.mode >= 2) {
-            if (p.mode == 3 && k >= 1 && k <= MC - 1) {     // src/lib.rs:397-403
-                X.x *= (T)p.fac2x;
-                X.y *= (T)p.fac2x;
+        if (ONES) {
+            if (k >= 1 && k <= MC - 1) {                    // src/lib.rs:397-403 (fac2x == 1 for mode 2)
+                X.x *= p.fac2x;
+                X.y *= p.fac2x;
             }
-            const int64_t o = (rowb + k) * p.ldp + pl;
-            if (p.spectrogram) ((T *)c.out)[o] = X.x * X.x + X.y * X.y;
-            else ((C *)c.out)[o] = X;
+            if (SPEC) *reinterpret_cast<T *>(ob + k * rb) = X.x * X.x + X.y * X.y;
+            else *reinterpret_cast<C *>(ob + k * rb) = X;
             return;
         }
-        // two-sided layouts: bin k and its mirror M - k (x is real)
-        int kk = k, km = (k == 0 || k == MC) ? -1 : M - k;
-        if (p.mode == 1) {                                  // fftshift, src/lib.rs:508-513
-            kk = (k + MC) % M;
-            if (km >= 0) km = (km + MC) % M;
-        }
-        const int64_t o = (rowb + kk) * p.ldp + pl;
-        if (p.spectrogram) {
+        // two-sided layouts: bin k and its mirror M - k (x is real); fftshift for centered
+        const int kk = (k + p.shift) & (M - 1);
+        const int km = (M - k + p.shift) & (M - 1);
+        const bool mir = !(k == 0 || k == MC);
+        if (SPEC) {
             const T v = X.x * X.x + X.y * X.y;
-            ((T *)c.out)[o] = v;
-            if (km >= 0) ((T *)c.out)[(rowb + km) * p.ldp + pl] = v;
+            *reinterpret_cast<T *>(ob + kk * rb) = v;
+            if (mir) *reinterpret_cast<T *>(ob + km * rb) = v;
         } else {
-            ((C *)c.out)[o] = X;
-            if (km >= 0) ((C *)c.out)[(rowb + km) * p.ldp + pl] = conj(X);
+            *reinterpret_cast<C *>(ob + kk * rb) = X;
+            if (mir) *reinterpret_cast<C *>(ob + km * rb) = conj(X);
         }
     }
 
     // split of the half-length spectrum: A = Z[k]/2, Zp = Z[Mc-k]/2  ->  X[k], X[Mc-k]
-    VHD static void emit(const FwdCtx<T> &c, int64_t pl, int k, C A, C Zp, bool both) {
+    template <bool ONES, bool SPEC>
+    VHD static void emit(const FwdArgs<T> &p, char *ob, int64_t rb, int k, C A, C Zp, bool both) {
         const C B = conj(Zp);
         const C E = A + B, Om = A - B;
-        const C w = ldgc(c.tw + GEO::TWP + 2 * k);          // W_M^k
+        const C w = ldgc(p.tw + GEO::TWP + 2 * k);          // W_M^k
         const C D = cmul(mk<T>(w.y, -w.x), Om);             // (-i W) (A - B)
-        store_bin(c, pl, k, E + D);
-        if (both) store_bin(c, pl, MC - k, conj(E - D));
+        store_bin<ONES, SPEC>(p, ob, rb, k, E + D);
+        if (both) store_bin<ONES, SPEC>(p, ob, rb, MC - k, conj(E - D));
     }
 
     // ---- last pass: groups (g, G-g): DFT_RL, real-FFT split, mode epilogue, global store
-    VHD static void pass_last(const FwdCtx<T> &c, int tid) {
+    template <bool ONES, bool SPEC>
+    VHD static void pass_last_t(const FwdCtx<T> &c, int tid) {
+        const FwdArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
         const int64_t pl = c.pt * TF + f;
-        const bool live = pl < c.prm.P;
+        const bool live = pl < p.P;
+        const int64_t esz = SPEC ? sizeof(T) : sizeof(C);
+        const int64_t rb = p.ldp * esz;
+        char *ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
         for (int s = sub; s < G / 2; s += NSUB) {
             const int g = s, gp = (s == 0) ? G / 2 : G - s;
             C u[RL], up[RL];
-            const int o1 = GEO::goff(g), o2 = GEO::goff(gp);
+            const C *w1 = c.work + GEO::goff(g) * TF + f, *w2 = c.work + GEO::goff(gp) * TF + f;
 #pragma unroll
             for (int d = 0; d < RL; ++d) {
-                u[d] = c.work[(o1 + d) * TF + f];
-                up[d] = c.work[(o2 + d) * TF + f];
+                u[d] = w1[d * TF];
+                up[d] = w2[d * TF];
             }
             Dft<RL, false, T>::run(u);
             Dft<RL, false, T>::run(up);
             if (!live) continue;
             if (s != 0) {
 #pragma unroll
-                for (int d = 0; d < RL; ++d) emit(c, pl, g + G * d, u[d], up[RL - 1 - d], true);
+                for (int d = 0; d < RL; ++d)
+                    emit<ONES, SPEC>(p, ob, rb, g + G * d, u[d], up[RL - 1 - d], true);
             } else {
-                emit(c, pl, 0, u[0], u[0], true);                         // X[0], X[Mc]
+                emit<ONES, SPEC>(p, ob, rb, 0, u[0], u[0], true);                  // X[0], X[Mc]
 #pragma unroll
-                for (int d = 1; d < RL / 2; ++d) emit(c, pl, G * d, u[d], u[RL - d], true);
-                emit(c, pl, MC / 2, u[RL / 2], u[RL / 2], false);         // self-mirrored
+                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC>(p, ob, rb, G * d, u[d], u[RL - d], true);
+                emit<ONES, SPEC>(p, ob, rb, MC / 2, u[RL / 2], u[RL / 2], false);  // self-mirrored
 #pragma unroll
                 for (int d = 0; d < RL / 2; ++d)
-                    emit(c, pl, G / 2 + G * d, up[d], up[RL - 1 - d], true);
+                    emit<ONES, SPEC>(p, ob, rb, G / 2 + G * d, up[d], up[RL - 1 - d], true);
             }
+        }
+    }
+    VHD static void pass_last(const FwdCtx<T> &c, int tid) {
+        const int spectrogram = c.a.spectrogram;
+        if (c.a.mode >= 2) {
+            if (spectrogram) pass_last_t<true, true>(c, tid);
+            else pass_last_t<true, false>(c, tid);
+        } else {
+            if (spectrogram) pass_last_t<false, true>(c, tid);
+            else pass_last_t<false, false>(c, tid);
         }
     }
 };
 
 // ================================================================== INVERSE
 template <typename T>
-struct InvCtx {
+struct InvArgs {
     const void *S;
     T *xo;
-    InvParams prm;
     const T *dual;           // [N] dual window / M (two-sided modes: / 2M), exact scaling
     const T *tw;
-    cx<T> *work;             // [MC][TF]  (shared)
-    T *ola;                  // [TF][N + opad] -- ALIASES work
-    int64_t b, qa;           // signal, first slice computed by this tile
+    int64_t P, ldp, out_pitch, p_min, k0, k1, q0, q1, qa0, ntiles;
+    int N, H, mid, ps, F;
+    int mode, shift;         // shift: centered Mc (ifftshift), else 0
+    T rfac2x;                // 1 / fac2x for onesided2X, 1 otherwise
+    unsigned magic_h;        // ceil(2^32 / H)
     int halo;                // ceil(N/H) - 1 leading slices recomputed for the overlap
-    int ostride;             // N + opad
+    int ostride;             // row stride of the overlap buffer (odd)
+};
+
+template <typename T>
+struct InvCtx {
+    InvArgs<T> a;
+    cx<T> *work;             // [MC][TF]  (shared)
+    T *ola;                  // [TF][ostride] -- ALIASES work
+    int64_t b, qa;           // signal, first slice computed by this tile
 };
 
 template <typename T, int LOGMC, int TF_, int NSUB_>
@@ -388,28 +480,23 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
     using GEO::G;
     static constexpr int GPT = (G + NSUB - 1) / NSUB;       // last-pass groups per thread
 
-    // Hermitian one-sided bin k (0 <= k <= Mc) of column col, mode undone (src/lib.rs:414-487);
-    // scaled by 2 for the two-sided layouts (folded into the dual window).
-    VHD static C load_bin(const InvCtx<T> &c, int64_t col, int k) {
-        const InvParams &p = c.prm;
-        const C *S = (const C *)c.S;
-        const int64_t rowb = c.b * p.F;
+    // Hermitian one-sided bin k (0 <= k <= Mc) of this thread's column, mode undone
+    // (src/lib.rs:414-487); scaled by 2 for the two-sided layouts (folded into the dual window).
+    // sb: byte pointer of (row 0, this column); rb: row pitch in bytes.
+    template <bool ONES>
+    VHD static C load_bin(const InvArgs<T> &p, const char *sb, int64_t rb, int k) {
         C v;
-        if (p.mode >= 2) {
-            v = S[(rowb + k) * p.ldp + col];
-            if (p.mode == 3 && k >= 1 && k <= MC - 1) {
-                const T r = (T)(1.0 / p.fac2x);
-                v.x *= r;
-                v.y *= r;
+        if (ONES) {
+            v = *reinterpret_cast<const C *>(sb + k * rb);
+            if (k >= 1 && k <= MC - 1) {                    // src/lib.rs:454-470 (rfac2x == 1 for mode 2)
+                v.x *= p.rfac2x;
+                v.y *= p.rfac2x;
             }
         } else {
-            int k1 = k, k2 = (k == 0) ? 0 : M - k;          // X[k] + conj(X[M-k])
-            if (p.mode == 1) {                              // ifftshift, src/lib.rs:516-521
-                k1 = (k1 + MC) % M;
-                k2 = (k2 + MC) % M;
-            }
-            const C a = S[(rowb + k1) * p.ldp + col];
-            const C bq = S[(rowb + k2) * p.ldp + col];
+            const int k1 = (k + p.shift) & (M - 1);         // X[k] + conj(X[M-k]); ifftshift :516-521
+            const int k2 = (M - k + p.shift) & (M - 1);
+            const C a = *reinterpret_cast<const C *>(sb + k1 * rb);
+            const C bq = *reinterpret_cast<const C *>(sb + k2 * rb);
             v = a + conj(bq);
         }
         if (k == 0 || k == MC) v.y = (T)0;                  // irfft ignores Im(DC), Im(Nyquist)
@@ -417,46 +504,48 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
     }
 
     // Z'[k] = 2 Z[k], Z'[Mc-k] from X[k], X[Mc-k]
-    VHD static void merge(const InvCtx<T> &c, int k, C &a, C &bm) {
+    VHD static void merge(const InvArgs<T> &p, int k, C &a, C &bm) {
         const C Xk = a, Xm = conj(bm);
         const C E = Xk + Xm, Dm = Xk - Xm;
-        const C w = ldgc(c.tw + GEO::TWP + 2 * k);          // W_M^k ; need conj(W) * Dm
-        const C O = cmul(conj(w), Dm);
+        const C O = cmulconj(Dm, ldgc(p.tw + GEO::TWP + 2 * k));   // conj(W_M^k) (Xk - conj Xm)
         const C iO = mk<T>(-O.y, O.x);
         a = E + iO;
         bm = conj(E - iO);
     }
 
     // ---- pass 1: load S columns (coalesced over slices), undo mode, real-IFFT merge, IDFT_R1
-    VHD static void pass1(const InvCtx<T> &c, int tid) {
-        const InvParams &p = c.prm;
+    template <bool ONES>
+    VHD static void pass1_t(const InvCtx<T> &c, int tid) {
+        const InvArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
         const int64_t q = c.qa + f;
         const int64_t col = q - p.p_min;
         const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+        const int64_t rb = p.ldp * (int64_t)sizeof(C);
+        const char *sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * (int64_t)sizeof(C);
         for (int s = sub; s < L1 / 2; s += NSUB) {
             const int j = s, jp = (s == 0) ? L1 / 2 : L1 - s;
             C v[R1], vp[R1];
             if (live) {
 #pragma unroll
                 for (int a = 0; a < R1; ++a) {
-                    v[a] = load_bin(c, col, j + L1 * a);
-                    vp[a] = load_bin(c, col, jp + L1 * a);
+                    v[a] = load_bin<ONES>(p, sb, rb, j + L1 * a);
+                    vp[a] = load_bin<ONES>(p, sb, rb, jp + L1 * a);
                 }
                 if (s != 0) {
 #pragma unroll
-                    for (int a = 0; a < R1; ++a) merge(c, j + L1 * a, v[a], vp[R1 - 1 - a]);
+                    for (int a = 0; a < R1; ++a) merge(p, j + L1 * a, v[a], vp[R1 - 1 - a]);
                 } else {
-                    const C xn = load_bin(c, col, MC);       // Nyquist pairs with DC
+                    const C xn = load_bin<ONES>(p, sb, rb, MC);   // Nyquist pairs with DC
                     v[0] = mk<T>(v[0].x + xn.x, v[0].x - xn.x);
 #pragma unroll
-                    for (int a = 1; a < R1 / 2; ++a) merge(c, L1 * a, v[a], v[R1 - a]);
+                    for (int a = 1; a < R1 / 2; ++a) merge(p, L1 * a, v[a], v[R1 - a]);
                     {
                         C t = v[R1 / 2];
-                        merge(c, MC / 2, v[R1 / 2], t);
+                        merge(p, MC / 2, v[R1 / 2], t);
                     }
 #pragma unroll
-                    for (int a = 0; a < R1 / 2; ++a) merge(c, jp + L1 * a, vp[a], vp[R1 - 1 - a]);
+                    for (int a = 0; a < R1 / 2; ++a) merge(p, jp + L1 * a, vp[a], vp[R1 - 1 - a]);
                 }
             } else {
 #pragma unroll
@@ -464,34 +553,37 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             }
             Dft<R1, true, T>::run(v);
             Dft<R1, true, T>::run(vp);
-            c.work[j * TF + f] = v[0];
-            c.work[jp * TF + f] = vp[0];
+            C *wj = c.work + j * TF + f, *wp = c.work + jp * TF + f;
+            const T *twj = p.tw + GEO::TW1 + 2 * j * R1, *twp = p.tw + GEO::TW1 + 2 * jp * R1;
+            wj[0] = v[0];
+            wp[0] = vp[0];
 #pragma unroll
             for (int cc = 1; cc < R1; ++cc) {
-                const C w = conj(ldgc(c.tw + GEO::TW1 + 2 * (j * R1 + cc)));
-                const C wp = conj(ldgc(c.tw + GEO::TW1 + 2 * (jp * R1 + cc)));
-                c.work[(j + L1 * cc) * TF + f] = cmul(v[cc], w);
-                c.work[(jp + L1 * cc) * TF + f] = cmul(vp[cc], wp);
+                wj[L1 * cc * TF] = cmulconj(v[cc], ldgc(twj + 2 * cc));
+                wp[L1 * cc * TF] = cmulconj(vp[cc], ldgc(twp + 2 * cc));
             }
         }
+    }
+    VHD static void pass1(const InvCtx<T> &c, int tid) {
+        if (c.a.mode >= 2) pass1_t<true>(c, tid);
+        else pass1_t<false>(c, tid);
     }
 
     VHD static void pass_mid(const InvCtx<T> &c, int tid) {
         if (NP != 3) return;
+        const InvArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
-            const int base = cb * L1 + j2;
+            C *wb = c.work + (cb * L1 + j2) * TF + f;
+            const T *twj = p.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
-            for (int a = 0; a < R2; ++a) v[a] = c.work[(base + L2 * a) * TF + f];
+            for (int a = 0; a < R2; ++a) v[a] = wb[L2 * a * TF];
             Dft<R2, true, T>::run(v);
-            c.work[base * TF + f] = v[0];
+            wb[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R2; ++cc) {
-                const C w = conj(ldgc(c.tw + GEO::TW2 + 2 * (j2 * R2 + cc)));
-                c.work[(base + L2 * cc) * TF + f] = cmul(v[cc], w);
-            }
+            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmulconj(v[cc], ldgc(twj + 2 * cc));
         }
     }
 
@@ -502,19 +594,19 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         for (int i = 0; i < GPT; ++i) {
             const int g = sub + NSUB * i;
             if (g < G) {
-                const int o = GEO::goff(g);
+                const C *w = c.work + GEO::goff(g) * TF + f;
 #pragma unroll
-                for (int d = 0; d < RL; ++d) r[i][d] = c.work[(o + d) * TF + f];
+                for (int d = 0; d < RL; ++d) r[i][d] = w[d * TF];
                 Dft<RL, true, T>::run(r[i]);
             }
         }
     }
     // ---- last pass, part B: roll back (src/lib.rs:499-500), truncate to N, dual window
     VHD static void last_store(const InvCtx<T> &c, int tid, const C (&r)[GPT][RL]) {
-        const InvParams &p = c.prm;
+        const InvArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
-        const int ps = (int)p.ps, N = (int)p.N;
-        T *row = c.ola + (size_t)f * c.ostride;
+        const int ps = p.ps, N = p.N;
+        T *row = c.ola + (size_t)f * p.ostride;
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
             const int g = sub + NSUB * i;
@@ -522,12 +614,10 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
 #pragma unroll
                 for (int d = 0; d < RL; ++d) {
                     const int m = g + G * d;                // z[m] = (y[2m], y[2m+1])
-                    int j0 = 2 * m + ps;
-                    if (j0 >= M) j0 -= M;
-                    int j1 = j0 + 1;
-                    if (j1 >= M) j1 -= M;
-                    if (j0 < N) row[j0] = r[i][d].x * ldg(c.dual + j0);
-                    if (j1 < N) row[j1] = r[i][d].y * ldg(c.dual + j1);
+                    const int j0 = (2 * m + ps) & (M - 1);
+                    const int j1 = (j0 + 1) & (M - 1);
+                    if (j0 < N) row[j0] = r[i][d].x * ldg(p.dual + j0);
+                    if (j1 < N) row[j1] = r[i][d].y * ldg(p.dual + j1);
                 }
             }
         }
@@ -535,22 +625,30 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
 
     // ---- overlap-add as a gather over the samples this tile owns, increasing q
     VHD static void gather(const InvCtx<T> &c, int tid) {
-        const InvParams &p = c.prm;
-        const int64_t H = p.H, N = p.N, mid = p.mid;
-        const int64_t qo = c.qa + c.halo;                    // first owned "latest slice"
-        int64_t ka = qo * H - mid, kb = (c.qa + TF) * H - mid;
+        const InvArgs<T> &p = c.a;
+        const int H = p.H, N = p.N, halo = p.halo;
+        const int64_t qo = c.qa + halo;                      // first owned "latest slice"
+        int64_t ka = qo * H - p.mid, kb = (c.qa + TF) * (int64_t)H - p.mid;
         if (ka < p.k0) ka = p.k0;
         if (kb > p.k1) kb = p.k1;
-        T *xo = c.xo + c.b * p.out_pitch;
-        for (int64_t k = ka + tid; k < kb; k += NT) {
-            const int64_t a = k + mid;
-            const int64_t qhi = (a >= 0) ? a / H : -((-a + H - 1) / H);
+        // local sample index u = k + mid - qa * H = (r + halo) * H + c0, r = first contributing slice
+        const int64_t base = c.qa * (int64_t)H - p.mid;      // k = base + u
+        T *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
+        const int ua = (int)(ka - base), ub = (int)(kb - base);
+        const int cnt = (TF - halo) * H, hH = halo * H, step = p.ostride - H;
+        for (int e = tid; e < cnt; e += NT) {
+            const int u = e + hH;
+            if (u < ua || u >= ub) continue;
+            const int r = (int)mulhi_u32((unsigned)e, p.magic_h);   // e / H
+            int jj = e - r * H + hH;                         // offset inside slice r
+            int idx = r * p.ostride + jj;
             T acc = (T)0;
-            for (int64_t q = qhi - c.halo; q <= qhi; ++q) {
-                const int64_t jj = a - q * H;
-                if (jj < N) acc += c.ola[(size_t)(q - c.qa) * c.ostride + jj];
+            for (int h = 0; h <= halo; ++h) {                // increasing q (src/lib.rs:853)
+                if (jj < N) acc += c.ola[idx];
+                jj -= H;
+                idx += step;
             }
-            xo[k - p.k0] = acc;
+            xo[u] = acc;
         }
     }
 };
