@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libpow2_emu.so")
 SRCS = [os.path.join(HERE, "pow2_emu.cu"), os.path.join(ROOT, "veils_b200", "csrc", "plan.cpp")]
 DEPS = SRCS + [os.path.join(ROOT, "veils_b200", "csrc", f) for f in
-               ("pow2_tile_impl.cuh", "pow2_cfg.hpp", "kernels.cuh", "plan.hpp")]
+               ("pow2_tile_impl.cuh", "pow2_cfg.hpp", "kernels.cuh", "plan.hpp", "pow2_pk_impl.cuh",
+                "pow2_pk_cfg.hpp", "f32x2.cuh")]
 
 
 def build():

@@ -9,6 +9,7 @@
 
 #include "../../veils_b200/csrc/plan.hpp"
 #include "../../veils_b200/csrc/pow2_cfg.hpp"
+#include "../../veils_b200/csrc/pow2_pk_cfg.hpp"
 
 using namespace veils;
 using namespace veils::p2;
@@ -36,7 +37,7 @@ struct EmuFwd {
         c.a = make_fwd_args<T>((const T *)x, out, prm, win.data(), tw.data(), TF);
         std::vector<cx<T>> work((size_t)K::MC * TF);
         std::vector<T> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay));
-        c.work = work.data(); c.xin = xin.data();
+        c.work = work.data(); c.xin = xin.data(); c.tw = tw.data(); c.win = win.data();
         for (int64_t blk = 0; blk < c.a.ptiles * prm.batch; ++blk) {
             c.b = blk / c.a.ptiles; c.pt = blk % c.a.ptiles;
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
@@ -62,7 +63,7 @@ struct EmuInv {
         size_t elems = (size_t)K::MC * TF * 2;
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<T> buf(elems + 4);
-        c.work = (cx<T> *)buf.data(); c.ola = buf.data();
+        c.work = (cx<T> *)buf.data(); c.ola = buf.data(); c.tw = tw.data(); c.dual = dual.data();
         const int own = TF - c.a.halo;
         std::vector<cx<T>> regs((size_t)K::NT * K::GPT * K::RL);
         for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
@@ -85,6 +86,68 @@ struct EmuInv {
     }
 };
 
+struct EmuPkFwd {
+    const void *x; void *out; FwdParams prm; const Plan *pl;
+    template <int LOGMC, int TF, int NSUB>
+    int run() {
+        using K = PkFwd<LOGMC, TF, NSUB>;
+        std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
+        p2::pk_twiddle_fill(prm.M, twd.data());
+        std::vector<float> tw = conv<float>(twd), win = conv<float>(pl->win, 0.5);
+        tw.resize(tw.size() + 8); win.resize(win.size() + 8);
+        PkFwdCtx c;
+        c.a = make_fwd_args<float>((const float *)x, out, prm, win.data(), tw.data(), TF);
+        std::vector<fl4> work((size_t)K::MC * 2 * TF / 4 + 4);
+        std::vector<fl4> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay) / 4 + 4);
+        c.work = (float *)work.data(); c.xin = (float *)xin.data(); c.tw = tw.data(); c.win = win.data();
+        for (int64_t blk = 0; blk < c.a.ptiles * prm.batch; ++blk) {
+            c.b = blk / c.a.ptiles; c.pt = blk % c.a.ptiles;
+            for (int t = 0; t < K::NT; ++t) K::fill(c, t);
+            for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
+            for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
+            for (int t = 0; t < K::NT; ++t) K::pass_last(c, t);
+        }
+        return 0;
+    }
+};
+
+struct EmuPkInv {
+    const void *S; void *xo; InvParams prm; const Plan *pl;
+    template <int LOGMC, int TF, int NSUB>
+    int run() {
+        using K = PkInv<LOGMC, TF, NSUB>;
+        std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
+        p2::pk_twiddle_fill(prm.M, twd.data());
+        const double sc = 1.0 / ((double)prm.M * (prm.mode >= 2 ? 1.0 : 2.0));
+        std::vector<float> tw = conv<float>(twd), dual = conv<float>(pl->dual, sc);
+        PkInvCtx c;
+        c.a = make_inv_args<float>(S, (float *)xo, prm, dual.data(), tw.data(), TF);
+        size_t elems = (size_t)K::MC * 2 * TF;
+        if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
+        std::vector<fl4> buf(elems / 4 + 4);
+        c.work = (float *)buf.data(); c.ola = (float *)buf.data(); c.tw = tw.data(); c.dual = dual.data();
+        const int own = TF - c.a.halo;
+        std::vector<C2> regs((size_t)K::NT * K::GPT * K::RL);
+        for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
+            c.b = blk / c.a.ntiles; c.qa = c.a.qa0 + (blk % c.a.ntiles) * own;
+            for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
+            for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
+            for (int t = 0; t < K::NT; ++t) {
+                C2 r[K::GPT][K::RL];
+                K::last_load(c, t, r);
+                std::memcpy(&regs[(size_t)t * K::GPT * K::RL], r, sizeof(r));
+            }
+            for (int t = 0; t < K::NT; ++t) {
+                C2 r[K::GPT][K::RL];
+                std::memcpy(r, &regs[(size_t)t * K::GPT * K::RL], sizeof(r));
+                K::last_store(c, t, r);
+            }
+            for (int t = 0; t < K::NT; ++t) K::gather(c, t);
+        }
+        return 0;
+    }
+};
+
 extern "C" {
 
 const char *emu_last_error() { return e_err.c_str(); }
@@ -93,27 +156,32 @@ const char *emu_last_error() { return e_err.c_str(); }
 int emu_stft(const double *win, int64_t m_num, int64_t hop, double fs, const char *mode, int64_t mfft,
              const char *scale_to, int64_t phase_shift, int precision, const void *x, int64_t n,
              int64_t batch, const int64_t *p0, const int64_t *p1, int64_t k_offset, void *out,
-             int spectrogram) {
+             int spectrogram, int family) {
     Plan pl;
     std::string e = plan_init(pl, win, m_num, hop, fs, mode, mfft, nullptr, scale_to, phase_shift, precision, 0);
     if (!e.empty()) { e_err = e; return 1; }
     int64_t a, b;
     e = plan_p_range(pl, n, p0, p1, &a, &b);
     if (!e.empty()) { e_err = e; return 1; }
-    if (!supported(pl.M, pl.N, pl.H, pl.ps, precision, false)) return 2;
+    if (family == 1 ? !(precision == 0 && p2::pk_supported(pl.M, pl.N, pl.H, pl.ps, false))
+                    : !supported(pl.M, pl.N, pl.H, pl.ps, precision, false)) return 2;
     FwdParams prm;
     prm.n = n; prm.x_pitch = n; prm.batch = batch; prm.N = pl.N; prm.H = pl.H; prm.M = pl.M;
     prm.F = pl.F; prm.mid = pl.mid; prm.ps = pl.ps; prm.p0 = a; prm.P = b - a; prm.k_offset = k_offset;
     prm.ldp = b - a; prm.mode = pl.mode; prm.fac2x = pl.fac2x; prm.spectrogram = spectrogram;
     Cfg c;
     cfg_for(pl.M, precision, &c);
+    if (family == 1) {
+        EmuPkFwd f{x, out, prm, &pl};
+        return pk_dispatch(c.logmc, f);
+    }
     EmuFwd f{x, out, prm, &pl};
     return dispatch(precision, c.logmc, f);
 }
 
 int emu_istft(const double *win, int64_t m_num, int64_t hop, double fs, const char *mode, int64_t mfft,
               const char *scale_to, int64_t phase_shift, int precision, const void *S, int64_t P,
-              int64_t batch, const int64_t *k0, const int64_t *k1, void *xo) {
+              int64_t batch, const int64_t *k0, const int64_t *k1, void *xo, int family) {
     Plan pl;
     std::string e = plan_init(pl, win, m_num, hop, fs, mode, mfft, nullptr, scale_to, phase_shift, precision, 0);
     if (!e.empty()) { e_err = e; return 1; }
@@ -121,13 +189,18 @@ int emu_istft(const double *win, int64_t m_num, int64_t hop, double fs, const ch
     e = plan_istft_range(pl, P, k0, k1, &r);
     if (e.empty()) e = plan_dual(pl);
     if (!e.empty()) { e_err = e; return 1; }
-    if (!supported(pl.M, pl.N, pl.H, pl.ps, precision, true)) return 2;
+    if (family == 1 ? !(precision == 0 && p2::pk_supported(pl.M, pl.N, pl.H, pl.ps, true))
+                    : !supported(pl.M, pl.N, pl.H, pl.ps, precision, true)) return 2;
     InvParams prm;
     prm.P = P; prm.ldp = P; prm.batch = batch; prm.N = pl.N; prm.H = pl.H; prm.M = pl.M; prm.F = pl.F;
     prm.mid = pl.mid; prm.ps = pl.ps; prm.p_min = pl.p_min; prm.k0 = r.k0; prm.k1 = r.k1; prm.q0 = r.q0;
     prm.q1 = r.q1; prm.out_pitch = r.k1 - r.k0; prm.mode = pl.mode; prm.fac2x = pl.fac2x;
     Cfg c;
     cfg_for(pl.M, precision, &c);
+    if (family == 1) {
+        EmuPkInv f{S, xo, prm, &pl};
+        return pk_dispatch(c.logmc, f);
+    }
     EmuInv f{S, xo, prm, &pl};
     return dispatch(precision, c.logmc, f);
 }

@@ -28,7 +28,7 @@ def _i64(v):
     return None if v is None else C.byref(C.c_int64(v))
 
 
-def emu_stft(lib, o, prec, x, p0=None, p1=None, k_offset=0, spectrogram=False):
+def emu_stft(lib, o, prec, x, p0=None, p1=None, k_offset=0, spectrogram=False, family=0):
     rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
     x = np.ascontiguousarray(np.atleast_2d(x), dtype=rdt)
     a, b = o.p_range(x.shape[1], p0, p1)
@@ -39,12 +39,14 @@ def emu_stft(lib, o, prec, x, p0=None, p1=None, k_offset=0, spectrogram=False):
                       None if o.scaling is None else o.scaling.encode(), C.c_int64(o.phase_shift),
                       C.c_int(prec), C.c_void_p(x.ctypes.data), C.c_int64(x.shape[1]),
                       C.c_int64(x.shape[0]), _i64(p0), _i64(p1), C.c_int64(k_offset),
-                      C.c_void_p(out.ctypes.data), C.c_int(int(spectrogram)))
+                      C.c_void_p(out.ctypes.data), C.c_int(int(spectrogram)), C.c_int(family))
+    if rc == 2:
+        return None
     assert rc == 0, (rc, lib.emu_last_error())
     return out
 
 
-def emu_istft(lib, o, prec, S, k0=None, k1=None):
+def emu_istft(lib, o, prec, S, k0=None, k1=None, family=0):
     rdt, cdt = (np.float32, np.complex64) if prec == 0 else (np.float64, np.complex128)
     S = np.ascontiguousarray(S, dtype=cdt)
     a, b, _, _ = o.istft_range(S.shape[2], k0, k1)
@@ -54,7 +56,8 @@ def emu_istft(lib, o, prec, S, k0=None, k1=None):
                        C.c_double(o.fs), o.fft_mode.encode(), C.c_int64(o.mfft),
                        None if o.scaling is None else o.scaling.encode(), C.c_int64(o.phase_shift),
                        C.c_int(prec), C.c_void_p(S.ctypes.data), C.c_int64(S.shape[2]),
-                       C.c_int64(S.shape[0]), _i64(k0), _i64(k1), C.c_void_p(out.ctypes.data))
+                       C.c_int64(S.shape[0]), _i64(k0), _i64(k1), C.c_void_p(out.ctypes.data),
+                       C.c_int(family))
     if rc == 2:
         return None                          # not covered by the pow2 family -> generic kernels
     assert rc == 0, (rc, lib.emu_last_error())
@@ -109,3 +112,34 @@ def test_emulated_kernels_match_oracle(emu, case, prec):
         k0, k1 = H + 3, 2 * N + 5
         y2 = emu_istft(emu, o, prec, Sref, k0, k1)
         assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= TOL[prec]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[f"M{c[0]}_N{c[1]}_H{c[2]}_{c[3]}" for c in CASES])
+def test_emulated_packed_kernels_match_oracle(emu, case):
+    """Packed f32 family (two slices per lane, FADD2/FFMA2): same cases, f32 tolerance."""
+    M, N, H, mode, ps, scale = case
+    rng = np.random.default_rng(M + N + H + 1)
+    win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(N) / N)) + 0.02
+    o = mk(win, H, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale)
+    n = 3 * N + 2 * H + 13
+    x = rng.uniform(-1, 1, (2, n)).astype(np.float32).astype(np.float64)
+    Sref = np.stack([o.stft(r) for r in x])
+    S = emu_stft(emu, o, 0, x, family=1)
+    fwd_ok = ps % 2 == 0 and H % 2 == 0 and N % 2 == 0 and H >= 4
+    assert (S is not None) == fwd_ok
+    if S is not None:
+        assert rel_err(S, Sref) <= 1e-5
+        sp = emu_stft(emu, o, 0, x, spectrogram=True, family=1)
+        assert rel_err(sp, np.abs(Sref) ** 2) <= 4e-5
+        a, b = o.p_min + 1, o.p_min + 4
+        S2 = emu_stft(emu, o, 0, x, p0=a, p1=b, k_offset=2, family=1)
+        assert rel_err(S2, np.stack([o.stft(r, a, b, 2) for r in x])) <= 1e-5
+        # odd row pitch / odd slice counts are covered by P = S.shape[2] being odd or even here
+    yref = np.stack([o.istft(s) for s in Sref])
+    y = emu_istft(emu, o, 0, Sref, family=1)
+    assert y is not None and not np.isnan(y).any()
+    assert rel_err(y, yref) <= 1e-5
+    if M <= 512:
+        k0, k1 = H + 3, 2 * N + 5
+        y2 = emu_istft(emu, o, 0, Sref, k0, k1, family=1)
+        assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= 1e-5

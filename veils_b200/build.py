@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libveils_cuda.so")
-SOURCES = ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu"]
+SOURCES = ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--use_fast_math=false"]
 

@@ -23,6 +23,7 @@ struct DeviceTables {
     void *win_half = nullptr;     // pow2 path (exact power-of-two rescalings, see pow2_tile_impl.cuh)
     void *dual_scaled = nullptr;
     void *tw_pow2 = nullptr;
+    float *tw_pk = nullptr;
 };
 }  // namespace veils
 
@@ -92,7 +93,12 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
             pow2_twiddle_fill(pl.M, tw.data());
             e = upload_prec(pl, tw, &d->tw_pow2);
         }
-        if (e == cudaSuccess && !(pl.pow2_fwd && pl.pow2_inv)) {
+        if (e == cudaSuccess && (pl.pk_fwd || pl.pk_inv)) {
+            std::vector<double> tw((size_t)pk_twiddle_count(pl.M));
+            pk_twiddle_fill(pl.M, tw.data());
+            e = upload_as<float>(tw, (void **)&d->tw_pk);
+        }
+        if (e == cudaSuccess && !((pl.pow2_fwd || pl.pk_fwd) && (pl.pow2_inv || pl.pk_inv))) {
             std::vector<double> tw((size_t)pl.M * 2);
             for (int64_t m = 0; m < pl.M; ++m) twiddle(m, pl.M, &tw[2 * m], &tw[2 * m + 1]);
             e = cudaMalloc((void **)&d->tw_full, tw.size() * sizeof(double));
@@ -100,7 +106,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) {
-            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full);
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk);
             delete d;
             return cuda_fail(e, "upload plan tables");
         }
@@ -125,6 +131,7 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.win_half = (const T *)pl.dev->win_half;
     tb.dual_scaled = (const T *)pl.dev->dual_scaled;
     tb.tw_pow2 = (const T *)pl.dev->tw_pow2;
+    tb.tw_pk = pl.dev->tw_pk;
     return tb;
 }
 
@@ -149,6 +156,9 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         const bool force_generic = d->precision >= 0 && getenv("VEILS_FORCE_GENERIC") != nullptr;
         pl.pow2_fwd = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, false);
         pl.pow2_inv = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, true);
+        const bool no_pk = getenv("VEILS_NO_PACKED") != nullptr;
+        pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
+        pl.pk_inv = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, true);
     }
     *out = p;
     return VEILS_OK;
@@ -164,6 +174,7 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->win_half);
         cudaFree(p->pl.dev->dual_scaled);
         cudaFree(p->pl.dev->tw_pow2);
+        cudaFree(p->pl.dev->tw_pk);
         delete p->pl.dev;
     }
     delete p;
@@ -299,8 +310,9 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
-                          : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
+        ce = pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
+             : pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
+                           : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_fwd ? pow2_forward<double>((const double *)x, out, prm, tb, st)
@@ -345,8 +357,9 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
-                          : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
+        ce = pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
+             : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
+                           : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_inv ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
@@ -501,6 +514,7 @@ int32_t veils_stream_sync(void *stream) {
 
 uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
 const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse) {
+    if (inverse ? p->pl.pk_inv : p->pl.pk_fwd) return "pow2_packed";
     return (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) ? "pow2_tile" : "dft_generic";
 }
 

@@ -37,6 +37,7 @@ struct Tables {
     const T *win_half = nullptr;        // [N] window / 2           (pow2 forward)
     const T *dual_scaled = nullptr;     // [N] dual / M or / (2M)   (pow2 inverse)
     const T *tw_pow2 = nullptr;         // pow2 twiddles (layout: pow2_cfg.hpp)
+    const float *tw_pk = nullptr;       // packed-f32 twiddles (layout: pow2_pk_cfg.hpp)
 };
 
 extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library
@@ -60,5 +61,12 @@ cudaError_t pow2_inverse(const void *S, T *x_out, const InvParams &prm, const Ta
 // size (in T elements) and contents of the fast-path twiddle table for mfft = M
 int64_t pow2_twiddle_count(int64_t M);
 void pow2_twiddle_fill(int64_t M, double *re_im_pairs);
+
+// ---- packed f32 family: two slices per lane, FADD2/FFMA2 (pow2_pk.cu) ----------------------
+bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse);
+int64_t pk_twiddle_count(int64_t M);
+void pk_twiddle_fill(int64_t M, double *re_im_pairs);
+cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st);
+cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const Tables<float> &tb, cudaStream_t st);
 
 }  // namespace veils

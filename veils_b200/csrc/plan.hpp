@@ -49,6 +49,8 @@ struct Plan {
     DeviceTables *dev = nullptr;
     bool pow2_fwd = false;    // dispatch decisions (see api.cu)
     bool pow2_inv = false;
+    bool pk_fwd = false;      // packed f32 family (preferred over pow2 when available)
+    bool pk_inv = false;
 };
 
 // Each returns "" on success or the reference's error text.

@@ -101,19 +101,40 @@ inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) 
     const int64_t span = (int64_t)(tf - 1) * H + N;
     return span + (span / H + 1) * l.padw + 2;
 }
-inline size_t fwd_smem_bytes(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, const Cfg &c) {
-    const size_t es = precision == 0 ? 4 : 8;
-    const TileLayout l = tile_layout(H, fwd_vec(ps, H, N));
-    return (size_t)(M / 2) * c.tf * 2 * es + (size_t)fwd_xin_elems(N, H, c.tf, l) * es;
+// exact shared-memory footprints of the instantiated kernels (see pow2_tile.cu)
+template <typename T, int LOGMC, int TF>
+inline size_t fwd_smem_bytes_t(int64_t N, int64_t xin_elems) {
+    using G = Geo<T, LOGMC, TF, 1>;
+    size_t b = sizeof(cx<T>) * (size_t)G::MC * TF + sizeof(T) * (size_t)xin_elems * (G::DBUF ? 2 : 1);
+    if (G::STAB) b += sizeof(T) * ((size_t)G::TWN + (size_t)N);
+    return b;
 }
+template <typename T, int LOGMC, int TF>
+inline size_t inv_work_bytes_t(int64_t N) {
+    using G = Geo<T, LOGMC, TF, 1>;
+    size_t work = sizeof(cx<T>) * (size_t)G::MC * TF;
+    const size_t ola = sizeof(T) * (size_t)TF * (size_t)(N | 1);
+    if (ola > work) work = ola;
+    return (work + 15) & ~(size_t)15;
+}
+template <typename T, int LOGMC, int TF>
+inline size_t inv_smem_bytes_t(int64_t N) {
+    using G = Geo<T, LOGMC, TF, 1>;
+    size_t b = inv_work_bytes_t<T, LOGMC, TF>(N);
+    if (G::STAB) b += sizeof(T) * ((size_t)G::TWN + (size_t)N);
+    return b;
+}
+struct SmemQuery {
+    int64_t N, H, ps; bool inverse;
+    template <typename T, int LOGMC, int TF, int NSUB>
+    long long run() {
+        if (inverse) return (long long)inv_smem_bytes_t<T, LOGMC, TF>(N);
+        const TileLayout l = tile_layout(H, fwd_vec(ps, H, N));
+        return (long long)fwd_smem_bytes_t<T, LOGMC, TF>(N, fwd_xin_elems(N, H, TF, l));
+    }
+};
 inline int inv_halo(int64_t N, int64_t H) { return (int)((N + H - 1) / H) - 1; }
 inline int inv_ostride(int64_t N) { return (int)(N | 1); }   // odd stride: lane writes conflict free
-inline size_t inv_smem_bytes(int64_t M, int64_t N, int precision, const Cfg &c) {
-    const size_t es = precision == 0 ? 4 : 8;
-    const size_t work = (size_t)(M / 2) * c.tf * 2 * es;
-    const size_t ola = (size_t)c.tf * inv_ostride(N) * es;
-    return work > ola ? work : ola;
-}
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 
@@ -158,16 +179,6 @@ inline InvArgs<T> make_inv_args(const void *S, T *xo, const InvParams &p, const 
     return a;
 }
 
-inline bool supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse) {
-    Cfg c;
-    if (!cfg_for(M, precision, &c)) return false;
-    if (N > M || H < 2 || H >= 65536) return false;
-    if (!inverse) return fwd_smem_bytes(M, N, H, ps, precision, c) <= SMEM_LIMIT;
-    if (H > N) return false;
-    if (inv_halo(N, H) >= c.tf) return false;         // at least one owned slice per tile
-    return inv_smem_bytes(M, N, precision, c) <= SMEM_LIMIT;
-}
-
 // Calls fn.template run<T, LOGMC, TF, NSUB>() for the configuration of (M, precision).
 #define VEILS_P2_CASE(T, LM, TFV)                                             \
     case LM: {                                                                \
@@ -193,6 +204,19 @@ inline auto dispatch(int precision, int logmc, FN &fn) -> decltype(fn.template r
         }
     }
     return decltype(fn.template run<float, 4, 32, 2>())(-1);
+}
+
+inline bool supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse) {
+    Cfg c;
+    if (!cfg_for(M, precision, &c)) return false;
+    if (N > M || H < 2 || H >= 65536) return false;
+    if (inverse) {
+        if (H > N) return false;
+        if (inv_halo(N, H) >= c.tf) return false;     // at least one owned slice per tile
+    }
+    SmemQuery q{N, H, ps, inverse};
+    const long long need = dispatch(precision, c.logmc, q);
+    return need > 0 && (size_t)need <= SMEM_LIMIT;
 }
 
 }  // namespace p2

@@ -1,0 +1,205 @@
+// pow2_pk.cu -- CUDA kernels and launchers of the packed f32 family (two slices per lane,
+// FADD2/FMUL2/FFMA2).  Phase code: pow2_pk_impl.cuh.  Persistent CTAs walk the (signal, tile)
+// list; plan tables live in shared memory and the signal tile is double-buffered with cp.async
+// for mfft <= 512.
+#include "pow2_pk_cfg.hpp"
+
+namespace veils {
+
+namespace {
+
+using namespace p2;
+
+__device__ __forceinline__ void copy_table_f(float *dst, const float *src, int n, int tid, int nt) {
+    for (int i = tid; i < n; i += nt) dst[i] = __ldg(src + i);
+}
+
+template <int LOGMC, int TF>
+constexpr int pk_min_ctas() { return 8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
+
+template <int LOGMC, int TF, int NSUB>
+__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
+pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const int64_t total, const int xin_elems) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    using K = PkFwd<LOGMC, TF, NSUB>;
+    const int tid = threadIdx.x;
+    PkFwdCtx c;
+    c.a = args;
+    c.work = reinterpret_cast<float *>(smem);
+    float *xin0 = c.work + (size_t)K::MC * 2 * TF;
+    float *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
+    if (K::STAB) {
+        float *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;     // xin_elems is a multiple of 4
+        float *swin = stw + K::TWN;
+        copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
+        copy_table_f(swin, args.win, args.N, tid, K::NT);
+        c.tw = stw;
+        c.win = swin;
+    } else {
+        c.tw = args.tw;
+        c.win = args.win;
+    }
+    int64_t w = blockIdx.x;
+    if (w < total) {
+        c.b = w / args.ptiles;
+        c.pt = w - c.b * args.ptiles;
+        c.xin = xin0;
+        K::fill(c, tid);
+        cp_async_commit();
+    }
+    for (int it = 0; w < total; w += gridDim.x, ++it) {
+        cp_async_wait_all();
+        __syncthreads();
+        float *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
+        const int64_t wn = w + gridDim.x;
+        if (K::DBUF && wn < total) {
+            c.b = wn / args.ptiles;
+            c.pt = wn - c.b * args.ptiles;
+            c.xin = (it & 1) ? xin0 : xin1;
+            K::fill(c, tid);
+            cp_async_commit();
+        }
+        c.b = w / args.ptiles;
+        c.pt = w - c.b * args.ptiles;
+        c.xin = cur;
+        K::pass1(c, tid);
+        __syncthreads();
+        if (!K::DBUF && wn < total) {
+            PkFwdCtx cn = c;
+            cn.b = wn / args.ptiles;
+            cn.pt = wn - cn.b * args.ptiles;
+            K::fill(cn, tid);
+            cp_async_commit();
+        }
+        if (K::NP == 3) {
+            K::pass_mid(c, tid);
+            __syncthreads();
+        }
+        K::pass_last(c, tid);
+    }
+}
+
+template <int LOGMC, int TF, int NSUB>
+__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
+pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const int64_t total, const int work_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    using K = PkInv<LOGMC, TF, NSUB>;
+    const int tid = threadIdx.x;
+    PkInvCtx c;
+    c.a = args;
+    c.work = reinterpret_cast<float *>(smem);
+    c.ola = reinterpret_cast<float *>(smem);
+    if (K::STAB) {
+        float *stw = reinterpret_cast<float *>(smem + work_bytes);
+        float *sdual = stw + K::TWN;
+        copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
+        copy_table_f(sdual, args.dual, args.N, tid, K::NT);
+        c.tw = stw;
+        c.dual = sdual;
+    } else {
+        c.tw = args.tw;
+        c.dual = args.dual;
+    }
+    __syncthreads();
+    const int own = TF - args.halo;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        c.b = w / args.ntiles;
+        c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
+        K::pass1(c, tid);
+        __syncthreads();
+        if (K::NP == 3) {
+            K::pass_mid(c, tid);
+            __syncthreads();
+        }
+        C2 r[K::GPT][K::RL];
+        K::last_load(c, tid, r);
+        __syncthreads();
+        K::last_store(c, tid, r);
+        __syncthreads();
+        K::gather(c, tid);
+        __syncthreads();
+    }
+}
+
+int pk_num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
+struct PkFwdLaunch {
+    const float *x; void *out; const FwdParams *prm; const float *win; const float *tw; cudaStream_t st;
+    template <int LOGMC, int TF, int NSUB>
+    cudaError_t run() {
+        const FwdParams &p = *prm;
+        FwdArgs<float> a = make_fwd_args<float>(x, out, p, win, tw, TF);
+        const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
+        const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
+        auto kern = pk_fwd_kernel<LOGMC, TF, NSUB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int64_t total = a.ptiles * p.batch;
+        const int64_t cap = (int64_t)per_sm * pk_num_sms();
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, total, xin_elems);
+        ++g_launch_count;
+        return cudaGetLastError();
+    }
+};
+
+struct PkInvLaunch {
+    const void *S; float *xo; const InvParams *prm; const float *dual; const float *tw; cudaStream_t st;
+    template <int LOGMC, int TF, int NSUB>
+    cudaError_t run() {
+        const InvParams &p = *prm;
+        if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
+        InvArgs<float> a = make_inv_args<float>(S, xo, p, dual, tw, TF);
+        const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
+        const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
+        auto kern = pk_inv_kernel<LOGMC, TF, NSUB>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int64_t total = a.ntiles * p.batch;
+        const int64_t cap = (int64_t)per_sm * pk_num_sms();
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, total, work_bytes);
+        ++g_launch_count;
+        return cudaGetLastError();
+    }
+};
+
+}  // namespace
+
+bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse) {
+    return p2::pk_supported(M, N, H, ps, inverse);
+}
+int64_t pk_twiddle_count(int64_t M) { return p2::pk_twiddle_count(M); }
+void pk_twiddle_fill(int64_t M, double *t) { p2::pk_twiddle_fill(M, t); }
+
+cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st) {
+    if (prm.P <= 0 || prm.batch <= 0) return cudaSuccess;
+    p2::Cfg c;
+    if (!p2::pk_cfg_for(prm.M, &c)) return cudaErrorNotSupported;
+    PkFwdLaunch l{x, out, &prm, tb.win_half, tb.tw_pk, st};
+    return p2::pk_dispatch(c.logmc, l);
+}
+
+cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const Tables<float> &tb, cudaStream_t st) {
+    if (prm.batch <= 0 || prm.k1 <= prm.k0) return cudaSuccess;
+    p2::Cfg c;
+    if (!p2::pk_cfg_for(prm.M, &c)) return cudaErrorNotSupported;
+    PkInvLaunch l{S, x_out, &prm, tb.dual_scaled, tb.tw_pk, st};
+    return p2::pk_dispatch(c.logmc, l);
+}
+
+}  // namespace veils

@@ -1,0 +1,116 @@
+// pow2_pk_cfg.hpp -- host-side configuration of the packed f32 family (pow2_pk_impl.cuh),
+// shared by the CUDA launchers (pow2_pk.cu) and the host emulation (tests/emu/pow2_emu.cu).
+#pragma once
+#include "pow2_cfg.hpp"
+#include "pow2_pk_impl.cuh"
+
+namespace veils {
+namespace p2 {
+
+inline bool pk_cfg_for(int64_t M, Cfg *c) {
+    const int lm = ilog2_exact(M);
+    if (lm < 5 || lm > 13) return false;
+    c->logmc = lm - 1;
+    static const int tf[13] = {0, 0, 0, 0, 32, 32, 32, 32, 32, 32, 16, 8, 4};
+    c->tf = tf[c->logmc];
+    c->nsub = 0;                                      // fixed by the dispatch table below
+    return true;
+}
+
+inline int64_t pk_twiddle_count(int64_t M) {          // floats
+    Cfg c;
+    if (!pk_cfg_for(M, &c)) return 0;
+    int np, r1, r2, r3;
+    fac_of(c.logmc, &np, &r1, &r2, &r3);
+    const int64_t mc = M / 2, l1 = mc / r1;
+    return 4 * (2 * mc + l1 + 1);
+}
+// entries (wr, wi, -wr, -wi): [tw1: W_Mc^(j c) at j*R1+c][tw2: W_L1^(j2 c2)][twp: W_M^k, k <= Mc]
+inline void pk_twiddle_fill(int64_t M, double *t) {
+    Cfg c;
+    if (!pk_cfg_for(M, &c)) return;
+    int np, r1, r2, r3;
+    fac_of(c.logmc, &np, &r1, &r2, &r3);
+    const int64_t mc = M / 2, l1 = mc / r1;
+    double *p = t;
+    auto put = [&](int64_t m, int64_t n) {
+        double re, im;
+        tw_exact(m, n, &re, &im);
+        p[0] = re; p[1] = im; p[2] = -re; p[3] = -im;
+        p += 4;
+    };
+    for (int64_t j = 0; j < l1; ++j)
+        for (int64_t cc = 0; cc < r1; ++cc) put(j * cc, mc);
+    if (np == 3) {
+        const int64_t l2 = l1 / r2;
+        for (int64_t j2 = 0; j2 < l2; ++j2)
+            for (int64_t cc = 0; cc < r2; ++cc) put(j2 * cc, l1);
+    } else {
+        for (int64_t i = 0; i < l1; ++i) put(0, 1);
+    }
+    for (int64_t k = 0; k <= mc; ++k) put(k, M);
+}
+
+template <int LOGMC, int TF>
+inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
+    using G = PkGeo<LOGMC, TF, 1>;
+    size_t b = 4 * ((size_t)G::MC * 2 * TF + (size_t)((xin_elems + 3) & ~3LL) * (G::DBUF ? 2 : 1));
+    if (G::STAB) b += 4 * ((size_t)G::TWN + (size_t)N);
+    return b;
+}
+template <int LOGMC, int TF>
+inline size_t pk_inv_work_bytes(int64_t N) {
+    using G = PkGeo<LOGMC, TF, 1>;
+    size_t work = 4 * (size_t)G::MC * 2 * TF;
+    const size_t ola = 4 * (size_t)TF * (size_t)(N | 1);
+    if (ola > work) work = ola;
+    return (work + 15) & ~(size_t)15;
+}
+template <int LOGMC, int TF>
+inline size_t pk_inv_smem_bytes(int64_t N) {
+    using G = PkGeo<LOGMC, TF, 1>;
+    size_t b = pk_inv_work_bytes<LOGMC, TF>(N);
+    if (G::STAB) b += 4 * ((size_t)G::TWN + (size_t)N);
+    return b;
+}
+
+// Calls fn.template run<LOGMC, TF, NSUB>() for mfft = 2^(logmc+1)
+#define VEILS_PK_CASE(LM, TFV, NS) \
+    case LM: return fn.template run<LM, TFV, NS>();
+template <typename FN>
+inline auto pk_dispatch(int logmc, FN &fn) -> decltype(fn.template run<4, 32, 2>()) {
+    switch (logmc) {
+        VEILS_PK_CASE(4, 32, 2) VEILS_PK_CASE(5, 32, 2) VEILS_PK_CASE(6, 32, 4) VEILS_PK_CASE(7, 32, 4)
+        VEILS_PK_CASE(8, 32, 8) VEILS_PK_CASE(9, 32, 16) VEILS_PK_CASE(10, 16, 32)
+        VEILS_PK_CASE(11, 8, 64) VEILS_PK_CASE(12, 4, 128)
+    }
+    return decltype(fn.template run<4, 32, 2>())(-1);
+}
+
+struct PkSmemQuery {
+    int64_t N, H, ps; bool inverse;
+    template <int LOGMC, int TF, int NSUB>
+    long long run() {
+        if (inverse) return (long long)pk_inv_smem_bytes<LOGMC, TF>(N);
+        const TileLayout l = tile_layout(H, true);
+        return (long long)pk_fwd_smem_bytes<LOGMC, TF>(N, fwd_xin_elems(N, H, TF, l));
+    }
+};
+
+inline bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse) {
+    Cfg c;
+    if (!pk_cfg_for(M, &c)) return false;
+    if (N > M || H < 2 || H >= 65536) return false;
+    if (inverse) {
+        if (H > N) return false;
+        if (inv_halo(N, H) >= c.tf) return false;
+    } else if (!fwd_vec(ps, H, N)) {
+        return false;                                  // paired tile reads need even ps, hop, m_num
+    }
+    PkSmemQuery q{N, H, ps, inverse};
+    const long long need = pk_dispatch(c.logmc, q);
+    return need > 0 && (size_t)need <= SMEM_LIMIT;
+}
+
+}  // namespace p2
+}  // namespace veils

@@ -12,77 +12,151 @@ using namespace p2;
 template <typename T, int LOGMC, int TF>
 constexpr int min_ctas() { return sizeof(T) * 2 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
 
+// cooperative copy of a plan table into shared memory
+template <typename T>
+__device__ __forceinline__ void copy_table(T *dst, const T *src, int n, int tid, int nt) {
+    for (int i = tid; i < n; i += nt) dst[i] = __ldg(src + i);
+}
+
+// Persistent forward kernel: each CTA walks the (signal, tile) list with stride gridDim.x.
+// Shared memory: work[Mc][TF] | tile buffer(s) | (STAB) twiddles, window.
 template <typename T, int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
-pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args) {
+pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, const int xin_elems) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = Fwd<T, LOGMC, TF, NSUB>;
+    const int tid = threadIdx.x;
     FwdCtx<T> c;
     c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
-    c.xin = reinterpret_cast<T *>(smem + sizeof(cx<T>) * K::MC * TF);
-    c.b = blockIdx.y;
-    c.pt = blockIdx.x;
-    const int tid = threadIdx.x;
-    K::fill(c, tid);
-    __syncthreads();
-    K::pass1(c, tid);
-    __syncthreads();
-    if (K::NP == 3) {
-        K::pass_mid(c, tid);
-        __syncthreads();
+    T *xin0 = reinterpret_cast<T *>(smem + sizeof(cx<T>) * K::MC * TF);
+    T *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
+    if (K::STAB) {
+        T *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;
+        T *swin = stw + K::TWN;
+        copy_table(stw, args.tw, K::TWN, tid, K::NT);
+        copy_table(swin, args.win, args.N, tid, K::NT);
+        c.tw = stw;
+        c.win = swin;
+    } else {
+        c.tw = args.tw;
+        c.win = args.win;
     }
-    K::pass_last(c, tid);
+    int64_t w = blockIdx.x;
+    if (w < total) {
+        c.b = w / args.ptiles;
+        c.pt = w - c.b * args.ptiles;
+        c.xin = xin0;
+        K::fill(c, tid);
+        cp_async_commit();
+    }
+    for (int it = 0; w < total; w += gridDim.x, ++it) {
+        cp_async_wait_all();
+        __syncthreads();                   // tile w staged; previous tile's reads of `work` done
+        T *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
+        const int64_t wn = w + gridDim.x;
+        if (K::DBUF && wn < total) {       // prefetch the next tile into the other buffer
+            c.b = wn / args.ptiles;
+            c.pt = wn - c.b * args.ptiles;
+            c.xin = (it & 1) ? xin0 : xin1;
+            K::fill(c, tid);
+            cp_async_commit();
+        }
+        c.b = w / args.ptiles;
+        c.pt = w - c.b * args.ptiles;
+        c.xin = cur;
+        K::pass1(c, tid);
+        __syncthreads();
+        if (!K::DBUF && wn < total) {      // single buffer: free once pass 1 is done
+            FwdCtx<T> cn = c;
+            cn.b = wn / args.ptiles;
+            cn.pt = wn - cn.b * args.ptiles;
+            K::fill(cn, tid);
+            cp_async_commit();
+        }
+        if (K::NP == 3) {
+            K::pass_mid(c, tid);
+            __syncthreads();
+        }
+        K::pass_last(c, tid);
+    }
 }
 
+// Persistent inverse kernel.  Shared memory: work[Mc][TF] (aliased by ola) | (STAB) twiddles, dual.
 template <typename T, int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
-pow2_inv_kernel(const __grid_constant__ InvArgs<T> args) {
+pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, const int work_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = Inv<T, LOGMC, TF, NSUB>;
+    const int tid = threadIdx.x;
     InvCtx<T> c;
     c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
     c.ola = reinterpret_cast<T *>(smem);
-    c.b = blockIdx.y;
-    c.qa = args.qa0 + (int64_t)blockIdx.x * (TF - args.halo);
-    const int tid = threadIdx.x;
-    K::pass1(c, tid);
-    __syncthreads();
-    if (K::NP == 3) {
-        K::pass_mid(c, tid);
-        __syncthreads();
+    if (K::STAB) {
+        T *stw = reinterpret_cast<T *>(smem + work_bytes);
+        T *sdual = stw + K::TWN;
+        copy_table(stw, args.tw, K::TWN, tid, K::NT);
+        copy_table(sdual, args.dual, args.N, tid, K::NT);
+        c.tw = stw;
+        c.dual = sdual;
+    } else {
+        c.tw = args.tw;
+        c.dual = args.dual;
     }
-    cx<T> r[K::GPT][K::RL];
-    K::last_load(c, tid, r);
-    __syncthreads();                       // all reads of `work` done before it becomes `ola`
-    K::last_store(c, tid, r);
     __syncthreads();
-    K::gather(c, tid);
+    const int own = TF - args.halo;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+        c.b = w / args.ntiles;
+        c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
+        K::pass1(c, tid);
+        __syncthreads();
+        if (K::NP == 3) {
+            K::pass_mid(c, tid);
+            __syncthreads();
+        }
+        cx<T> r[K::GPT][K::RL];
+        K::last_load(c, tid, r);
+        __syncthreads();                   // all reads of `work` done before it becomes `ola`
+        K::last_store(c, tid, r);
+        __syncthreads();
+        K::gather(c, tid);
+        __syncthreads();                   // `ola` consumed before the next tile overwrites `work`
+    }
 }
 
-// batch is mapped to gridDim.y (<= 65535 per launch); larger batches are launched in slabs
+static int num_sms() {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return sms;
+}
+
 struct FwdLaunch {
     const void *x; void *out; const FwdParams *prm; const void *win; const void *tw; cudaStream_t st;
     template <typename T, int LOGMC, int TF, int NSUB>
     cudaError_t run() {
+        using K = Fwd<T, LOGMC, TF, NSUB>;
         const FwdParams &p = *prm;
         FwdArgs<T> a = make_fwd_args<T>((const T *)x, out, p, (const T *)win, (const T *)tw, TF);
-        const size_t smem = sizeof(cx<T>) * (size_t)(1 << LOGMC) * TF +
-                            sizeof(T) * (size_t)fwd_xin_elems(p.N, p.H, TF, a.lay);
+        const int xin_elems = (int)fwd_xin_elems(p.N, p.H, TF, a.lay);
+        const size_t smem = fwd_smem_bytes_t<T, LOGMC, TF>(p.N, xin_elems);
         auto kern = pow2_fwd_kernel<T, LOGMC, TF, NSUB>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (a.ptiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        const size_t osz = p.spectrogram ? sizeof(T) : sizeof(cx<T>);
-        for (int64_t b0 = 0; b0 < p.batch; b0 += 65535) {
-            const int64_t nb = p.batch - b0 < 65535 ? p.batch - b0 : 65535;
-            FwdArgs<T> as = a;
-            as.x = a.x + b0 * p.x_pitch;
-            as.out = (char *)out + (size_t)b0 * p.F * p.ldp * osz;
-            kern<<<dim3((unsigned)a.ptiles, (unsigned)nb), TF * NSUB, smem, st>>>(as);
-            ++g_launch_count;
-        }
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TF * NSUB, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int64_t total = a.ptiles * p.batch;
+        const int64_t cap = (int64_t)per_sm * num_sms();
+        const unsigned grid = (unsigned)(total < cap ? total : cap);
+        (void)sizeof(K);
+        kern<<<grid, TF * NSUB, smem, st>>>(a, total, xin_elems);
+        ++g_launch_count;
         return cudaGetLastError();
     }
 };
@@ -94,21 +168,20 @@ struct InvLaunch {
         const InvParams &p = *prm;
         if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
         InvArgs<T> a = make_inv_args<T>(S, (T *)xo, p, (const T *)dual, (const T *)tw, TF);
-        size_t smem = sizeof(cx<T>) * (size_t)(1 << LOGMC) * TF;
-        const size_t ola = sizeof(T) * (size_t)TF * a.ostride;
-        if (ola > smem) smem = ola;
+        const int work_bytes = (int)inv_work_bytes_t<T, LOGMC, TF>(p.N);
+        const size_t smem = inv_smem_bytes_t<T, LOGMC, TF>(p.N);
         auto kern = pow2_inv_kernel<T, LOGMC, TF, NSUB>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if (a.ntiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-        for (int64_t b0 = 0; b0 < p.batch; b0 += 65535) {
-            const int64_t nb = p.batch - b0 < 65535 ? p.batch - b0 : 65535;
-            InvArgs<T> as = a;
-            as.S = (const char *)S + (size_t)b0 * p.F * p.ldp * sizeof(cx<T>);
-            as.xo = a.xo + b0 * p.out_pitch;
-            kern<<<dim3((unsigned)a.ntiles, (unsigned)nb), TF * NSUB, smem, st>>>(as);
-            ++g_launch_count;
-        }
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TF * NSUB, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int64_t total = a.ntiles * p.batch;
+        const int64_t cap = (int64_t)per_sm * num_sms();
+        const unsigned grid = (unsigned)(total < cap ? total : cap);
+        kern<<<grid, TF * NSUB, smem, st>>>(a, total, work_bytes);
+        ++g_launch_count;
         return cudaGetLastError();
     }
 };

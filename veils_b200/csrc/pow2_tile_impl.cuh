@@ -23,13 +23,8 @@
 //     mode (src/lib.rs:414-487), the last pass multiplies by the dual window (:869-873) and the
 //     overlap-add (:876-910) is a deterministic gather in increasing q owned by this CTA.
 #pragma once
+#include "f32x2.cuh"
 #include "kernels.cuh"
-
-#if defined(__CUDACC__)
-#define VHD __host__ __device__ __forceinline__
-#else
-#define VHD inline
-#endif
 
 namespace veils {
 namespace p2 {
@@ -53,10 +48,17 @@ template <typename T> VHD cx<T> conj(cx<T> a) { return mk<T>(a.x, -a.y); }
 template <bool INV, typename T> VHD cx<T> rot(cx<T> a) {
     return INV ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x);
 }
-// multiply by the constant (c, -s) forward, (c, +s) inverse
+// multiply by the constant (c, -s) forward, (c, +s) inverse; T may be float, double or f2
 template <bool INV, typename T> VHD cx<T> cmulc(cx<T> a, double c, double s) {
-    const T cc = (T)c, ss = INV ? (T)(-s) : (T)s;          // w = cc - i ss
-    return mk<T>(a.x * cc + a.y * ss, a.y * cc - a.x * ss);
+    const T cc = vconst<T>(c), ss = vconst<T>(INV ? -s : s), ns = vconst<T>(INV ? s : -s);
+    return mk<T>(vfma(a.y, ss, a.x * cc), vfma(a.x, ns, a.y * cc));   // w = cc - i ss
+}
+// multiply by a table twiddle given as (wr, wi, -wi):  a * w   and   a * conj(w)
+template <typename T> VHD cx<T> cmulw(cx<T> a, T wr, T wi, T nwi) {
+    return mk<T>(vfma(a.y, nwi, a.x * wr), vfma(a.y, wr, a.x * wi));
+}
+template <typename T> VHD cx<T> cmulwc(cx<T> a, T wr, T wi, T nwi) {
+    return mk<T>(vfma(a.y, wi, a.x * wr), vfma(a.x, nwi, a.y * wr));
 }
 
 template <typename T> VHD T ldg(const T *p) {
@@ -87,6 +89,33 @@ VHD unsigned mulhi_u32(unsigned a, unsigned b) {
 #endif
 }
 
+// Asynchronous global -> shared copy of BYTES (4, 8 or 16) with zero fill when !valid.
+// Device: cp.async (LDGSTS), completed by cp_async_wait_all(); host emulation: synchronous.
+template <int BYTES> VHD void cp_async_zfill(void *sdst, const void *gsrc, bool valid) {
+#if defined(__CUDA_ARCH__)
+    const unsigned d = (unsigned)__cvta_generic_to_shared(sdst);
+    const int sz = valid ? BYTES : 0;
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+#else
+    for (int i = 0; i < BYTES; ++i) ((char *)sdst)[i] = valid ? ((const char *)gsrc)[i] : 0;
+#endif
+}
+VHD void cp_async_commit() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+VHD void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
 // ------------------------------------------------------------------ in-register DFTs
 // Natural-order in, natural-order out.  INV selects exp(+i...) (unnormalised).
 template <bool INV, typename T> VHD void dft2(cx<T> &a, cx<T> &b) {
@@ -95,7 +124,9 @@ template <bool INV, typename T> VHD void dft2(cx<T> &a, cx<T> &b) {
     b = t;
 }
 template <bool INV, typename T> VHD void dft4(cx<T> &a0, cx<T> &a1, cx<T> &a2, cx<T> &a3) {
-    const cx<T> t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = rot<INV>(a1 - a3);
+    const cx<T> t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3;
+    // t3 = (-/+ i)(a1 - a3) without a negation
+    const cx<T> t3 = INV ? mk<T>(a3.y - a1.y, a1.x - a3.x) : mk<T>(a1.y - a3.y, a3.x - a1.x);
     a0 = t0 + t2;
     a2 = t0 - t2;
     a1 = t1 + t3;
@@ -194,6 +225,19 @@ struct Geo {
     static constexpr int TW1 = 0, TW2 = 2 * MC, TWP = 2 * (MC + L1);
     // work-memory offset (in complex elements) of last-pass group g: bins k = g + G d
     VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
+    // small transforms: persistent CTAs keep the plan tables in shared memory and double-buffer
+    // the staged signal tile (cp.async); large ones read the tables through the read-only path.
+    static constexpr bool STAB = LOGMC <= 8;
+    static constexpr bool DBUF = LOGMC <= 8;
+    static constexpr int TWN = 2 * (MC + L1 + MC + 1);    // reals in the twiddle table
+    VHD static cx<T> tlc(const T *q) {                     // complex table entry
+        if (STAB) return *reinterpret_cast<const cx<T> *>(q);
+        return ldgc(q);
+    }
+    VHD static T tl(const T *q) {
+        if (STAB) return *q;
+        return ldg(q);
+    }
 };
 
 // Shared-memory layout of the staged signal: sample i = r * H + c of the tile lives at
@@ -227,6 +271,7 @@ struct FwdArgs {
 template <typename T>
 struct FwdCtx {
     FwdArgs<T> a;
+    const T *tw, *win;       // plan tables: shared-memory copies (STAB) or the global tables
     T *xin;                  // staged signal tile (shared)
     cx<T> *work;             // [MC][TF] (shared)
     int64_t b, pt;           // signal, tile index
@@ -241,8 +286,8 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
     using GEO::G;
 
     // ---- phase 0: stage the tile's samples, zero outside [0, n)  (src/lib.rs:631-645)
-    // Flat, unrolled (all loads in flight before the first store).  Global index of tile sample i
-    // is s0 + i; its shared address is (i / H) * (H + padw) + i % H.
+    // Asynchronous (cp.async with zero fill); the caller commits and waits.  Global index of tile
+    // sample i is s0 + i; its shared address is (i / H) * (H + padw) + i % H.
     VHD static void fill(const FwdCtx<T> &c, int tid) {
         const FwdArgs<T> &p = c.a;
         const int H = p.H;
@@ -250,65 +295,40 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
         const int hs = H + p.lay.padw;
         const int64_t s0 = (p.p0 + c.pt * TF) * (int64_t)H + p.k_offset - p.mid;
         const T *xb = p.x + c.b * p.x_pitch;
-        constexpr int U = 4;
         if (p.vec && (((c.b * p.x_pitch + s0) & 1) == 0) && ((p.n & 1) == 0) &&
             ((((size_t)p.x) & (2 * sizeof(T) - 1)) == 0)) {
             // pairs: never straddle the signal borders (s0, n even) nor a tile row (H even)
             const int np = span >> 1, hp = H >> 1;
-            for (int e0 = tid; e0 < np; e0 += NT * U) {
-                C v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = e0 + u * NT;
-                    const int64_t s = s0 + 2 * (int64_t)e;
-                    v[u] = mk<T>(0, 0);
-                    if (e < np && s >= 0 && s < p.n) v[u] = ldgc(xb + s);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = e0 + u * NT;
-                    if (e < np) {
-                        const int r = (int)mulhi_u32((unsigned)e, p.magic_hp);     // e / (H/2)
-                        *reinterpret_cast<C *>(c.xin + r * hs + 2 * (e - r * hp)) = v[u];
-                    }
-                }
+            for (int e = tid; e < np; e += NT) {
+                const int64_t s = s0 + 2 * (int64_t)e;
+                const bool ok = s >= 0 && s < p.n;
+                const int r = (int)mulhi_u32((unsigned)e, p.magic_hp);         // e / (H/2)
+                cp_async_zfill<2 * (int)sizeof(T)>(c.xin + r * hs + 2 * (e - r * hp), ok ? xb + s : xb, ok);
             }
             return;
         }
-        for (int e0 = tid; e0 < span; e0 += NT * U) {
-            T v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * NT;
-                const int64_t s = s0 + e;
-                v[u] = (T)0;
-                if (e < span && s >= 0 && s < p.n) v[u] = ldg(xb + s);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int e = e0 + u * NT;
-                if (e < span) {
-                    const int r = e / H;
-                    c.xin[r * hs + (e - r * H)] = v[u];
-                }
-            }
+        for (int e = tid; e < span; e += NT) {
+            const int64_t s = s0 + e;
+            const bool ok = s >= 0 && s < p.n;
+            const int r = e / H;
+            cp_async_zfill<(int)sizeof(T)>(c.xin + r * hs + (e - r * H), ok ? xb + s : xb, ok);
         }
     }
 
     // windowed, rolled, zero-padded sample pair x'[2m], x'[2m+1] of the slice whose tile base is xf
     template <bool VEC, bool PADDED>
-    VHD static C load_pair(const FwdArgs<T> &p, const T *xf, int m) {
+    VHD static C load_pair(const FwdArgs<T> &p, const T *win, const T *xf, int m) {
         const int j0 = (2 * m + p.ps) & (M - 1);
         if (VEC) {
             if (PADDED && j0 >= p.N) return mk<T>(0, 0);
             const C xv = *reinterpret_cast<const C *>(xf + p.lay.addr(j0));
-            const C w = ldgc(p.win + j0);
+            const C w = GEO::tlc(win + j0);
             return mk<T>(xv.x * w.x, xv.y * w.y);
         }
         const int j1 = (j0 + 1) & (M - 1);
         T v0 = 0, v1 = 0;
-        if (j0 < p.N) v0 = xf[p.lay.addr(j0)] * ldg(p.win + j0);
-        if (j1 < p.N) v1 = xf[p.lay.addr(j1)] * ldg(p.win + j1);
+        if (j0 < p.N) v0 = xf[p.lay.addr(j0)] * GEO::tl(win + j0);
+        if (j1 < p.N) v1 = xf[p.lay.addr(j1)] * GEO::tl(win + j1);
         return mk<T>(v0, v1);
     }
 
@@ -321,13 +341,13 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
         for (int j = sub; j < L1; j += NSUB) {
             C v[R1];
 #pragma unroll
-            for (int a = 0; a < R1; ++a) v[a] = load_pair<VEC, PADDED>(p, xf, j + L1 * a);
+            for (int a = 0; a < R1; ++a) v[a] = load_pair<VEC, PADDED>(p, c.win, xf, j + L1 * a);
             Dft<R1, false, T>::run(v);
             C *wj = c.work + j * TF + f;
-            const T *twj = p.tw + GEO::TW1 + 2 * j * R1;
+            const T *twj = c.tw + GEO::TW1 + 2 * j * R1;
             wj[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmul(v[cc], ldgc(twj + 2 * cc));
+            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmul(v[cc], GEO::tlc(twj + 2 * cc));
         }
     }
     VHD static void pass1(const FwdCtx<T> &c, int tid) {
@@ -347,14 +367,14 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
             C *wb = c.work + (cb * L1 + j2) * TF + f;
-            const T *twj = p.tw + GEO::TW2 + 2 * j2 * R2;
+            const T *twj = c.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
             for (int a = 0; a < R2; ++a) v[a] = wb[L2 * a * TF];
             Dft<R2, false, T>::run(v);
             wb[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmul(v[cc], ldgc(twj + 2 * cc));
+            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmul(v[cc], GEO::tlc(twj + 2 * cc));
         }
     }
 
@@ -389,10 +409,10 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
 
     // split of the half-length spectrum: A = Z[k]/2, Zp = Z[Mc-k]/2  ->  X[k], X[Mc-k]
     template <bool ONES, bool SPEC>
-    VHD static void emit(const FwdArgs<T> &p, char *ob, int64_t rb, int k, C A, C Zp, bool both) {
+    VHD static void emit(const FwdArgs<T> &p, const T *twp, char *ob, int64_t rb, int k, C A, C Zp, bool both) {
         const C B = conj(Zp);
         const C E = A + B, Om = A - B;
-        const C w = ldgc(p.tw + GEO::TWP + 2 * k);          // W_M^k
+        const C w = GEO::tlc(twp + 2 * k);                   // W_M^k
         const C D = cmul(mk<T>(w.y, -w.x), Om);             // (-i W) (A - B)
         store_bin<ONES, SPEC>(p, ob, rb, k, E + D);
         if (both) store_bin<ONES, SPEC>(p, ob, rb, MC - k, conj(E - D));
@@ -408,6 +428,7 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
         const int64_t esz = SPEC ? sizeof(T) : sizeof(C);
         const int64_t rb = p.ldp * esz;
         char *ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+        const T *twp = c.tw + GEO::TWP;
         for (int s = sub; s < G / 2; s += NSUB) {
             const int g = s, gp = (s == 0) ? G / 2 : G - s;
             C u[RL], up[RL];
@@ -423,15 +444,15 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
             if (s != 0) {
 #pragma unroll
                 for (int d = 0; d < RL; ++d)
-                    emit<ONES, SPEC>(p, ob, rb, g + G * d, u[d], up[RL - 1 - d], true);
+                    emit<ONES, SPEC>(p, twp, ob, rb, g + G * d, u[d], up[RL - 1 - d], true);
             } else {
-                emit<ONES, SPEC>(p, ob, rb, 0, u[0], u[0], true);                  // X[0], X[Mc]
+                emit<ONES, SPEC>(p, twp, ob, rb, 0, u[0], u[0], true);                  // X[0], X[Mc]
 #pragma unroll
-                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC>(p, ob, rb, G * d, u[d], u[RL - d], true);
-                emit<ONES, SPEC>(p, ob, rb, MC / 2, u[RL / 2], u[RL / 2], false);  // self-mirrored
+                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC>(p, twp, ob, rb, G * d, u[d], u[RL - d], true);
+                emit<ONES, SPEC>(p, twp, ob, rb, MC / 2, u[RL / 2], u[RL / 2], false);  // self-mirrored
 #pragma unroll
                 for (int d = 0; d < RL / 2; ++d)
-                    emit<ONES, SPEC>(p, ob, rb, G / 2 + G * d, up[d], up[RL - 1 - d], true);
+                    emit<ONES, SPEC>(p, twp, ob, rb, G / 2 + G * d, up[d], up[RL - 1 - d], true);
             }
         }
     }
@@ -466,6 +487,7 @@ struct InvArgs {
 template <typename T>
 struct InvCtx {
     InvArgs<T> a;
+    const T *tw, *dual;      // plan tables: shared-memory copies (STAB) or the global tables
     cx<T> *work;             // [MC][TF]  (shared)
     T *ola;                  // [TF][ostride] -- ALIASES work
     int64_t b, qa;           // signal, first slice computed by this tile
@@ -504,10 +526,10 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
     }
 
     // Z'[k] = 2 Z[k], Z'[Mc-k] from X[k], X[Mc-k]
-    VHD static void merge(const InvArgs<T> &p, int k, C &a, C &bm) {
+    VHD static void merge(const T *twp, int k, C &a, C &bm) {
         const C Xk = a, Xm = conj(bm);
         const C E = Xk + Xm, Dm = Xk - Xm;
-        const C O = cmulconj(Dm, ldgc(p.tw + GEO::TWP + 2 * k));   // conj(W_M^k) (Xk - conj Xm)
+        const C O = cmulconj(Dm, GEO::tlc(twp + 2 * k));     // conj(W_M^k) (Xk - conj Xm)
         const C iO = mk<T>(-O.y, O.x);
         a = E + iO;
         bm = conj(E - iO);
@@ -523,6 +545,7 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
         const int64_t rb = p.ldp * (int64_t)sizeof(C);
         const char *sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * (int64_t)sizeof(C);
+        const T *twp0 = c.tw + GEO::TWP;
         for (int s = sub; s < L1 / 2; s += NSUB) {
             const int j = s, jp = (s == 0) ? L1 / 2 : L1 - s;
             C v[R1], vp[R1];
@@ -534,18 +557,18 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
                 }
                 if (s != 0) {
 #pragma unroll
-                    for (int a = 0; a < R1; ++a) merge(p, j + L1 * a, v[a], vp[R1 - 1 - a]);
+                    for (int a = 0; a < R1; ++a) merge(twp0, j + L1 * a, v[a], vp[R1 - 1 - a]);
                 } else {
                     const C xn = load_bin<ONES>(p, sb, rb, MC);   // Nyquist pairs with DC
                     v[0] = mk<T>(v[0].x + xn.x, v[0].x - xn.x);
 #pragma unroll
-                    for (int a = 1; a < R1 / 2; ++a) merge(p, L1 * a, v[a], v[R1 - a]);
+                    for (int a = 1; a < R1 / 2; ++a) merge(twp0, L1 * a, v[a], v[R1 - a]);
                     {
                         C t = v[R1 / 2];
-                        merge(p, MC / 2, v[R1 / 2], t);
+                        merge(twp0, MC / 2, v[R1 / 2], t);
                     }
 #pragma unroll
-                    for (int a = 0; a < R1 / 2; ++a) merge(p, jp + L1 * a, vp[a], vp[R1 - 1 - a]);
+                    for (int a = 0; a < R1 / 2; ++a) merge(twp0, jp + L1 * a, vp[a], vp[R1 - 1 - a]);
                 }
             } else {
 #pragma unroll
@@ -554,13 +577,13 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             Dft<R1, true, T>::run(v);
             Dft<R1, true, T>::run(vp);
             C *wj = c.work + j * TF + f, *wp = c.work + jp * TF + f;
-            const T *twj = p.tw + GEO::TW1 + 2 * j * R1, *twp = p.tw + GEO::TW1 + 2 * jp * R1;
+            const T *twj = c.tw + GEO::TW1 + 2 * j * R1, *twq = c.tw + GEO::TW1 + 2 * jp * R1;
             wj[0] = v[0];
             wp[0] = vp[0];
 #pragma unroll
             for (int cc = 1; cc < R1; ++cc) {
-                wj[L1 * cc * TF] = cmulconj(v[cc], ldgc(twj + 2 * cc));
-                wp[L1 * cc * TF] = cmulconj(vp[cc], ldgc(twp + 2 * cc));
+                wj[L1 * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
+                wp[L1 * cc * TF] = cmulconj(vp[cc], GEO::tlc(twq + 2 * cc));
             }
         }
     }
@@ -576,14 +599,14 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
             C *wb = c.work + (cb * L1 + j2) * TF + f;
-            const T *twj = p.tw + GEO::TW2 + 2 * j2 * R2;
+            const T *twj = c.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
             for (int a = 0; a < R2; ++a) v[a] = wb[L2 * a * TF];
             Dft<R2, true, T>::run(v);
             wb[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmulconj(v[cc], ldgc(twj + 2 * cc));
+            for (int cc = 1; cc < R2; ++cc) wb[L2 * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
         }
     }
 
@@ -616,8 +639,8 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
                     const int m = g + G * d;                // z[m] = (y[2m], y[2m+1])
                     const int j0 = (2 * m + ps) & (M - 1);
                     const int j1 = (j0 + 1) & (M - 1);
-                    if (j0 < N) row[j0] = r[i][d].x * ldg(p.dual + j0);
-                    if (j1 < N) row[j1] = r[i][d].y * ldg(p.dual + j1);
+                    if (j0 < N) row[j0] = r[i][d].x * GEO::tl(c.dual + j0);
+                    if (j1 < N) row[j1] = r[i][d].y * GEO::tl(c.dual + j1);
                 }
             }
         }
