@@ -3,6 +3,7 @@
 // blocks and threads with __syncthreads() replaced by phase boundaries, so that the index
 // algebra of the CUDA kernels can be checked against the oracle in the CPU test suite.
 // It is NOT linked into libveils_cuda.so and is not a fallback of the product.
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,19 +94,37 @@ struct EmuPkFwd {
         using K = PkFwd<LOGMC, TF, NSUB>;
         std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
         p2::pk_twiddle_fill(prm.M, twd.data());
-        std::vector<float> tw = conv<float>(twd), win = conv<float>(pl->win, 0.5);
-        tw.resize(tw.size() + 8); win.resize(win.size() + 8);
+        std::vector<float> tw = conv<float>(twd);
+        tw.resize(tw.size() + 8);
+        std::vector<PTab> ptab((size_t)K::MC);
+        pk_ptab_fill(prm.M, prm.N, prm.H, prm.ps, pl->win.data(), TF, ptab.data());
         PkFwdCtx c;
-        c.a = make_fwd_args<float>((const float *)x, out, prm, win.data(), tw.data(), TF);
+        c.a = make_fwd_args<float>((const float *)x, out, prm, nullptr, tw.data(), TF);
         std::vector<fl4> work((size_t)K::MC * 2 * TF / 4 + 4);
         std::vector<fl4> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay) / 4 + 4);
-        c.work = (float *)work.data(); c.xin = (float *)xin.data(); c.tw = tw.data(); c.win = win.data();
+        c.work = (float *)work.data(); c.xin = (float *)xin.data(); c.tw = tw.data(); c.ptab = ptab.data();
+        const int zo = pk_zero_off(prm.N, prm.H, TF);
+        std::vector<C2> regs((size_t)K::NT * K::RL);
         for (int64_t blk = 0; blk < c.a.ptiles * prm.batch; ++blk) {
             c.b = blk / c.a.ptiles; c.pt = blk % c.a.ptiles;
+            // poison the tile (NaN) except the zero pair: padded entries must never read it
+            for (size_t i = 0; i < xin.size() * 4; ++i) c.xin[i] = std::nanf("");
+            c.xin[zo] = c.xin[zo + 1] = 0.f;
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
-            for (int t = 0; t < K::NT; ++t) K::pass_last(c, t);
+            for (int i = 0; i < K::WPT; ++i) {
+                for (int t = 0; t < K::NT; ++t) {
+                    C2 u[K::RL];
+                    K::last_dft(c, t, i, u);
+                    std::memcpy(&regs[(size_t)t * K::RL], u, sizeof(u));
+                }
+                for (int t = 0; t < K::NT; ++t) {
+                    C2 u[K::RL];
+                    std::memcpy(u, &regs[(size_t)t * K::RL], sizeof(u));
+                    K::last_emit(c, t, i, u, &regs[(size_t)(t ^ K::LN) * K::RL]);
+                }
+            }
         }
         return 0;
     }
@@ -128,9 +147,24 @@ struct EmuPkInv {
         c.work = (float *)buf.data(); c.ola = (float *)buf.data(); c.tw = tw.data(); c.dual = dual.data();
         const int own = TF - c.a.halo;
         std::vector<C2> regs((size_t)K::NT * K::GPT * K::RL);
+        std::vector<Raw> raws((size_t)K::NT * (K::R1 + 1));
         for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
             c.b = blk / c.a.ntiles; c.qa = c.a.qa0 + (blk % c.a.ntiles) * own;
-            for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
+            for (int i = 0; i < K::WPT; ++i) {
+                for (int t = 0; t < K::NT; ++t) {
+                    Raw xr[K::R1]; Raw xn;
+                    std::memset(xr, 0, sizeof(xr)); std::memset(&xn, 0, sizeof(xn));
+                    K::p1_load(c, t, i, xr, xn);
+                    std::memcpy(&raws[(size_t)t * (K::R1 + 1)], xr, sizeof(xr));
+                    raws[(size_t)t * (K::R1 + 1) + K::R1] = xn;
+                }
+                for (int t = 0; t < K::NT; ++t) {
+                    Raw xr[K::R1];
+                    std::memcpy(xr, &raws[(size_t)t * (K::R1 + 1)], sizeof(xr));
+                    K::p1_rest(c, t, i, xr, raws[(size_t)t * (K::R1 + 1) + K::R1],
+                               &raws[(size_t)(t ^ K::LN) * (K::R1 + 1)]);
+                }
+            }
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
             for (int t = 0; t < K::NT; ++t) {
                 C2 r[K::GPT][K::RL];

@@ -99,7 +99,7 @@ inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H 
 
 inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) {
     const int64_t span = (int64_t)(tf - 1) * H + N;
-    return span + (span / H + 1) * l.padw + 2;
+    return span + (span / H + 1) * l.padw + 6;          // + zero pair used by padded table entries
 }
 // exact shared-memory footprints of the instantiated kernels (see pow2_tile.cu)
 template <typename T, int LOGMC, int TF>

@@ -19,7 +19,8 @@ constexpr int pk_min_ctas() { return 8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1;
 
 template <int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
-pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const int64_t total, const int xin_elems) {
+pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restrict__ ptab_g,
+              const int64_t total, const int xin_elems, const int zero_off) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = PkFwd<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -30,14 +31,18 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const int64_t total, 
     float *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
     if (K::STAB) {
         float *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;     // xin_elems is a multiple of 4
-        float *swin = stw + K::TWN;
+        PTab *sptab = reinterpret_cast<PTab *>(stw + K::TWN);
         copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
-        copy_table_f(swin, args.win, args.N, tid, K::NT);
+        copy_table_f(reinterpret_cast<float *>(sptab), reinterpret_cast<const float *>(ptab_g), 4 * K::MC, tid, K::NT);
         c.tw = stw;
-        c.win = swin;
+        c.ptab = sptab;
     } else {
         c.tw = args.tw;
-        c.win = args.win;
+        c.ptab = ptab_g;
+    }
+    if (tid < 2) {                         // the zero pair behind the staged span
+        xin0[zero_off + tid] = 0.f;
+        xin1[zero_off + tid] = 0.f;
     }
     int64_t w = blockIdx.x;
     if (w < total) {
@@ -75,7 +80,12 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const int64_t total, 
             K::pass_mid(c, tid);
             __syncthreads();
         }
-        K::pass_last(c, tid);
+#pragma unroll 1
+        for (int i = 0; i < K::WPT; ++i) {
+            C2 u[K::RL];
+            K::last_dft(c, tid, i, u);
+            K::last_emit(c, tid, i, u, nullptr);
+        }
     }
 }
 
@@ -105,7 +115,13 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const int64_t total, 
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
         c.b = w / args.ntiles;
         c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
-        K::pass1(c, tid);
+#pragma unroll 1
+        for (int i = 0; i < K::WPT; ++i) {
+            Raw x[K::R1];
+            Raw xn;
+            K::p1_load(c, tid, i, x, xn);
+            K::p1_rest(c, tid, i, x, xn, nullptr);
+        }
         __syncthreads();
         if (K::NP == 3) {
             K::pass_mid(c, tid);
@@ -132,11 +148,11 @@ int pk_num_sms() {
 }
 
 struct PkFwdLaunch {
-    const float *x; void *out; const FwdParams *prm; const float *win; const float *tw; cudaStream_t st;
+    const float *x; void *out; const FwdParams *prm; const PTab *ptab; const float *tw; cudaStream_t st;
     template <int LOGMC, int TF, int NSUB>
     cudaError_t run() {
         const FwdParams &p = *prm;
-        FwdArgs<float> a = make_fwd_args<float>(x, out, p, win, tw, TF);
+        FwdArgs<float> a = make_fwd_args<float>(x, out, p, nullptr, tw, TF);
         const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
         const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
         auto kern = pk_fwd_kernel<LOGMC, TF, NSUB>;
@@ -148,7 +164,8 @@ struct PkFwdLaunch {
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ptiles * p.batch;
         const int64_t cap = (int64_t)per_sm * pk_num_sms();
-        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, total, xin_elems);
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(
+            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF));
         ++g_launch_count;
         return cudaGetLastError();
     }
@@ -184,13 +201,18 @@ bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse) {
     return p2::pk_supported(M, N, H, ps, inverse);
 }
 int64_t pk_twiddle_count(int64_t M) { return p2::pk_twiddle_count(M); }
+void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, void *out16) {
+    p2::Cfg c;
+    if (!p2::pk_cfg_for(M, &c)) return;
+    p2::pk_ptab_fill(M, N, H, ps, win, c.tf, (p2::PTab *)out16);
+}
 void pk_twiddle_fill(int64_t M, double *t) { p2::pk_twiddle_fill(M, t); }
 
 cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st) {
     if (prm.P <= 0 || prm.batch <= 0) return cudaSuccess;
     p2::Cfg c;
     if (!p2::pk_cfg_for(prm.M, &c)) return cudaErrorNotSupported;
-    PkFwdLaunch l{x, out, &prm, tb.win_half, tb.tw_pk, st};
+    PkFwdLaunch l{x, out, &prm, (const PTab *)tb.ptab_pk, tb.tw_pk, st};
     return p2::pk_dispatch(c.logmc, l);
 }
 

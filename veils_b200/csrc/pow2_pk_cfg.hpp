@@ -53,14 +53,43 @@ inline void pk_twiddle_fill(int64_t M, double *t) {
 
 template <int LOGMC, int TF>
 inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
-    using G = PkGeo<LOGMC, TF, 1>;
+    using G = PkGeo<LOGMC, TF, 2>;
+    (void)N;
     size_t b = 4 * ((size_t)G::MC * 2 * TF + (size_t)((xin_elems + 3) & ~3LL) * (G::DBUF ? 2 : 1));
-    if (G::STAB) b += 4 * ((size_t)G::TWN + (size_t)N);
+    if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(PTab) * (size_t)G::MC;
     return b;
+}
+// per-plan tile table: entry m = sample pair (2m, 2m+1) of the rolled, zero-padded, windowed slice
+// (src/lib.rs:336-345, 715-729): tile offset of x[j0], window values * 0.5 (real-FFT split).
+// Padded pairs (j0 >= m_num) point at the zero pair stored behind the staged span.
+inline void pk_ptab_fill(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, int tf, PTab *t) {
+    const TileLayout lay = tile_layout(H, true);
+    const int64_t span = (int64_t)(tf - 1) * H + N;
+    const int zero_off = (int)(lay.addr((int)(span - 1)) + 1 + ((lay.addr((int)(span - 1)) + 1) & 1));
+    for (int64_t m = 0; m < M / 2; ++m) {
+        const int64_t j0 = (2 * m + ps) & (M - 1);
+        PTab e;
+        e.pad = 0;
+        if (j0 < N) {
+            e.aoff = lay.addr((int)j0);
+            e.w0 = (float)(win[j0] * 0.5);
+            e.w1 = (float)(win[j0 + 1] * 0.5);
+        } else {
+            e.aoff = zero_off;
+            e.w0 = e.w1 = 0.f;
+        }
+        t[m] = e;
+    }
+}
+inline int pk_zero_off(int64_t N, int64_t H, int tf) {
+    const TileLayout lay = tile_layout(H, true);
+    const int64_t span = (int64_t)(tf - 1) * H + N;
+    const int a = lay.addr((int)(span - 1)) + 1;
+    return a + (a & 1);
 }
 template <int LOGMC, int TF>
 inline size_t pk_inv_work_bytes(int64_t N) {
-    using G = PkGeo<LOGMC, TF, 1>;
+    using G = PkGeo<LOGMC, TF, 2>;
     size_t work = 4 * (size_t)G::MC * 2 * TF;
     const size_t ola = 4 * (size_t)TF * (size_t)(N | 1);
     if (ola > work) work = ola;
@@ -68,7 +97,7 @@ inline size_t pk_inv_work_bytes(int64_t N) {
 }
 template <int LOGMC, int TF>
 inline size_t pk_inv_smem_bytes(int64_t N) {
-    using G = PkGeo<LOGMC, TF, 1>;
+    using G = PkGeo<LOGMC, TF, 2>;
     size_t b = pk_inv_work_bytes<LOGMC, TF>(N);
     if (G::STAB) b += 4 * ((size_t)G::TWN + (size_t)N);
     return b;
@@ -78,13 +107,13 @@ inline size_t pk_inv_smem_bytes(int64_t N) {
 #define VEILS_PK_CASE(LM, TFV, NS) \
     case LM: return fn.template run<LM, TFV, NS>();
 template <typename FN>
-inline auto pk_dispatch(int logmc, FN &fn) -> decltype(fn.template run<4, 32, 2>()) {
+inline auto pk_dispatch(int logmc, FN &fn) -> decltype(fn.template run<4, 32, 4>()) {
     switch (logmc) {
-        VEILS_PK_CASE(4, 32, 2) VEILS_PK_CASE(5, 32, 2) VEILS_PK_CASE(6, 32, 4) VEILS_PK_CASE(7, 32, 4)
-        VEILS_PK_CASE(8, 32, 8) VEILS_PK_CASE(9, 32, 16) VEILS_PK_CASE(10, 16, 32)
+        VEILS_PK_CASE(4, 32, 4) VEILS_PK_CASE(5, 32, 8) VEILS_PK_CASE(6, 32, 8) VEILS_PK_CASE(7, 32, 16)
+        VEILS_PK_CASE(8, 32, 16) VEILS_PK_CASE(9, 32, 16) VEILS_PK_CASE(10, 16, 32)
         VEILS_PK_CASE(11, 8, 64) VEILS_PK_CASE(12, 4, 128)
     }
-    return decltype(fn.template run<4, 32, 2>())(-1);
+    return decltype(fn.template run<4, 32, 4>())(-1);
 }
 
 struct PkSmemQuery {

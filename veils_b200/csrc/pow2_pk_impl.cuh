@@ -1,17 +1,23 @@
-// pow2_pk_impl.cuh -- f32 "packed slice-lane" kernels: the pow2 tile family with TWO consecutive
-// time slices per lane, the same component of both kept in one f32x2 register pair, so every
-// butterfly add / mul / fma is a single FADD2 / FMUL2 / FFMA2 (see f32x2.cuh).
+// pow2_pk_impl.cuh -- f32 "packed slice-lane" kernels: the pow2 tile family with TWO time slices
+// per lane, the same component of both kept in one f32x2 register pair, so every butterfly
+// add / mul / fma is a single FADD2 / FMUL2 / FFMA2 (see f32x2.cuh).
 //
-// Versus the scalar family (pow2_tile_impl.cuh) this halves the issued instructions per slice:
-// arithmetic is packed, shared-memory traffic moves 8 bytes (two slices) per lane and access, the
-// plan tables are read once per two slices, and S is stored / loaded as 16-byte {re,im,re,im}
-// vectors of two adjacent slices (256-byte runs per row).  Layout differences:
-//   * thread t = (sub, l): l = t % (TF/2) owns slices 2l, 2l+1 of the tile;
-//   * work buffer is planar: work[(e*2 + comp)*TF + slice]  (comp 0 = re, 1 = im);
-//   * twiddle tables hold (wr, wi, -wr, -wi) so that no packed negation is ever needed
-//     (FFMA2 has no negate modifier that ptxas folds for us).
-// The AoS <-> packed transposition is free: it is done by the first scalar op after a load
-// (window multiply / Hermitian merge add) and the last scalar op before a store.
+//   * thread t = (sub, l): l = t % LN (LN = TF/2) owns slices l and l + LN of the tile
+//     (this pairing keeps the 8-byte tile reads of the 16 lanes of a half-warp on 32 distinct
+//     banks; slices 2l, 2l+1 would give 2-way conflicts);
+//   * work buffer is planar: work[(e*2 + comp)*TF + 2*l + s]  (comp 0 = re, 1 = im; s = slice
+//     l + s*LN), so one 8-byte access moves one component of both slices;
+//   * twiddle tables hold (wr, wi, -wr, -wi): no packed negation is ever needed (ptxas does not
+//     fold negations into FFMA2 operands);
+//   * the mirrored groups (g, G-g) of the real-FFT split live in the two HALVES of a warp row
+//     pair (sub, sub^1) and swap one value per bin with __shfl_xor -- each thread keeps ONE
+//     group in registers (<= 128 registers, 16 warps per SM) and produces ONE output row per
+//     bin pair; both halves run the same instruction stream because the table entry of bin
+//     Mc-k is (-wr, wi) of bin k;
+//   * per-plan tile table ptab[m] = (tile offset of sample pair m, -, w[2m'], w[2m'+1]) turns
+//     frame extraction + roll + zero padding + windowing into one 16-byte table read.
+// The AoS <-> packed transposition is free: done by the first scalar op after a load (window
+// multiply / Hermitian merge add) and the last scalar op before a store.
 // Phase functions compile for the device and for the host emulation (tests/emu).
 #pragma once
 #include "pow2_tile_impl.cuh"
@@ -21,6 +27,7 @@ namespace p2 {
 
 struct alignas(8) fl2 { float x, y; };
 struct alignas(16) fl4 { float x, y, z, w; };
+struct alignas(16) PTab { int aoff; int pad; float w0, w1; };   // one sample pair of a slice
 
 template <int LOGMC, int TF_, int NSUB_>
 struct PkGeo {
@@ -35,8 +42,8 @@ struct PkGeo {
     // twiddle table: entries of 4 floats (wr, wi, -wr, -wi): [tw1: MC][tw2: L1][twp: MC + 1]
     static constexpr int TW1 = 0, TW2 = 4 * MC, TWP = 4 * (MC + L1), TWN = 4 * (2 * MC + L1 + 1);
     VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
-    static constexpr bool STAB = LOGMC <= 8;
-    static constexpr bool DBUF = LOGMC <= 8;
+    static constexpr bool STAB = LOGMC <= 8;          // plan tables in shared memory
+    static constexpr bool DBUF = LOGMC <= 7;          // double-buffered signal tile
     VHD static fl4 tw4(const float *q) {
 #if defined(__CUDA_ARCH__)
         if (!STAB) {
@@ -47,15 +54,15 @@ struct PkGeo {
 #endif
         return *reinterpret_cast<const fl4 *>(q);
     }
-    VHD static fl2 t2(const float *q) {
+    VHD static PTab pt4(const PTab *q) {
 #if defined(__CUDA_ARCH__)
         if (!STAB) {
-            const float2 v = __ldg(reinterpret_cast<const float2 *>(q));
-            fl2 r; r.x = v.x; r.y = v.y;
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(q));
+            PTab r; r.aoff = v.x; r.pad = v.y; r.w0 = __int_as_float(v.z); r.w1 = __int_as_float(v.w);
             return r;
         }
 #endif
-        return *reinterpret_cast<const fl2 *>(q);
+        return *q;
     }
     VHD static float t1(const float *q) {
 #if defined(__CUDA_ARCH__)
@@ -67,7 +74,6 @@ struct PkGeo {
 
 using C2 = cx<f2>;
 VHD C2 c2zero() { C2 r; r.x = bc(0.f); r.y = bc(0.f); return r; }
-// planar work-buffer access for the two slices of this lane
 VHD C2 wload(const float *w, int TF) {
     C2 r;
     r.x = *reinterpret_cast<const f2 *>(w);
@@ -79,10 +85,52 @@ VHD void wstore(float *w, int TF, C2 v) {
     *reinterpret_cast<f2 *>(w + TF) = v.y;
 }
 
+// value of the partner thread (lane ^ LN).  Device: warp shuffle.  Host emulation: the partner's
+// copy, handed in by the harness.
+// lanes of the (sub, sub^1) pair this thread belongs to
+template <int LN>
+VHD unsigned pair_mask(int tid) {
+    if (LN >= 16) return 0xffffffffu;
+    const unsigned m = (1u << (2 * LN)) - 1u;
+    return m << (((tid & 31) / (2 * LN)) * (2 * LN));
+}
+template <int LN>
+VHD C2 xchg(C2 v, const C2 *partner_copy, unsigned mask) {
+#if defined(__CUDA_ARCH__)
+    (void)partner_copy;
+    C2 r;
+    r.x.v = __shfl_xor_sync(mask, v.x.v, LN);
+    r.y.v = __shfl_xor_sync(mask, v.y.v, LN);
+    return r;
+#else
+    (void)v; (void)mask;
+    return *partner_copy;
+#endif
+}
+struct Raw {                 // one bin of both slices as loaded: {re0, im0} {re1, im1}
+    float r0, i0, r1, i1;
+};
+template <int LN>
+VHD Raw xchg_raw(Raw v, const Raw *partner_copy, unsigned mask) {
+#if defined(__CUDA_ARCH__)
+    (void)partner_copy;
+    Raw r;
+    r.r0 = __shfl_xor_sync(mask, v.r0, LN);
+    r.i0 = __shfl_xor_sync(mask, v.i0, LN);
+    r.r1 = __shfl_xor_sync(mask, v.r1, LN);
+    r.i1 = __shfl_xor_sync(mask, v.i1, LN);
+    return r;
+#else
+    (void)v; (void)mask;
+    return *partner_copy;
+#endif
+}
+
 // ================================================================== FORWARD (packed)
 struct PkFwdCtx {
     FwdArgs<float> a;
-    const float *tw, *win;
+    const float *tw;
+    const PTab *ptab;        // [MC] tile offset + window of sample pair m
     float *xin;
     float *work;             // planar [MC][2][TF]
     int64_t b, pt;
@@ -94,8 +142,10 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     using GEO::MC; using GEO::M; using GEO::TF; using GEO::LN; using GEO::NSUB; using GEO::NT;
     using GEO::NP; using GEO::R1; using GEO::R2; using GEO::R3; using GEO::RL; using GEO::L1;
     using GEO::L2; using GEO::G;
+    static constexpr int WPT = (G / 2 + NSUB / 2 - 1) / (NSUB / 2);     // last-pass pairs per sub pair
 
-    // staging of the signal tile: identical layout to the scalar family (paired cp.async)
+    // staging of the signal tile (paired cp.async, zero fill outside [0, n)); the two floats
+    // after the staged span are the "zero pair" that padded table entries point to.
     VHD static void fill(const PkFwdCtx &c, int tid) {
         const FwdArgs<float> &p = c.a;
         const int H = p.H;
@@ -121,28 +171,22 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         }
     }
 
-    // ---- pass 1
-    template <bool PADDED>
-    VHD static void pass1_t(const PkFwdCtx &c, int tid) {
+    // ---- pass 1: one group per thread and iteration
+    VHD static void pass1(const PkFwdCtx &c, int tid) {
         const FwdArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
         const int hs = p.H + p.lay.padw;
-        const float *xf0 = c.xin + (2 * l) * hs, *xf1 = xf0 + hs;
+        const float *xf0 = c.xin + l * hs, *xf1 = xf0 + LN * hs;
         for (int j = sub; j < L1; j += NSUB) {
             C2 v[R1];
+            const PTab *pj = c.ptab + j;
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
-                const int j0 = (2 * (j + L1 * a) + p.ps) & (M - 1);
-                if (PADDED && j0 >= p.N) {
-                    v[a] = c2zero();
-                } else {
-                    const int ad = p.lay.addr(j0);
-                    const fl2 x0 = *reinterpret_cast<const fl2 *>(xf0 + ad);
-                    const fl2 x1 = *reinterpret_cast<const fl2 *>(xf1 + ad);
-                    const fl2 w = GEO::t2(c.win + j0);
-                    v[a].x = mk2(x0.x * w.x, x1.x * w.x);      // scalar multiplies transpose for free
-                    v[a].y = mk2(x0.y * w.y, x1.y * w.y);
-                }
+                const PTab e = GEO::pt4(pj + L1 * a);
+                const fl2 x0 = *reinterpret_cast<const fl2 *>(xf0 + e.aoff);
+                const fl2 x1 = *reinterpret_cast<const fl2 *>(xf1 + e.aoff);
+                v[a].x = mk2(x0.x * e.w0, x1.x * e.w0);        // scalar multiplies transpose for free
+                v[a].y = mk2(x0.y * e.w1, x1.y * e.w1);
             }
             Dft<R1, false, f2>::run(v);
             float *wj = c.work + (j * 2) * TF + 2 * l;
@@ -154,10 +198,6 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
                 wstore(wj + (L1 * cc * 2) * TF, TF, cmulw(v[cc], bc(t.x), bc(t.y), bc(t.w)));
             }
         }
-    }
-    VHD static void pass1(const PkFwdCtx &c, int tid) {
-        if (c.a.padded) pass1_t<true>(c, tid);
-        else pass1_t<false>(c, tid);
     }
 
     VHD static void pass_mid(const PkFwdCtx &c, int tid) {
@@ -181,134 +221,121 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     }
 
     struct Out {             // per-thread output cursor
-        char *ob;            // byte pointer of (row 0, column of slice 2l)
+        char *ob;            // byte pointer of (row 0, column of slice l)
         int64_t rb;          // row pitch in bytes
-        bool live0, live1;   // slice 2l / 2l+1 inside [0, P)
+        bool live0, live1;   // slice l / l + LN inside [0, P)
     };
-
-    // complex output of one bin for the two slices (r0,i0) (r1,i1); A16: 16-byte vector store
-    template <bool A16>
-    VHD static void put_c(const Out &o, int row, float r0, float i0, float r1, float i1) {
+    template <bool SPEC>
+    VHD static void put(const Out &o, int row, float r0, float i0, float r1, float i1) {
         char *q = o.ob + row * o.rb;
-        if (A16 && o.live1) {
-            fl4 v; v.x = r0; v.y = i0; v.z = r1; v.w = i1;
-            *reinterpret_cast<fl4 *>(q) = v;
+        if (SPEC) {
+            if (o.live0) *reinterpret_cast<float *>(q) = r0 * r0 + i0 * i0;
+            if (o.live1) *reinterpret_cast<float *>(q + 4 * LN) = r1 * r1 + i1 * i1;
         } else {
             if (o.live0) { fl2 v; v.x = r0; v.y = i0; *reinterpret_cast<fl2 *>(q) = v; }
-            if (o.live1) { fl2 v; v.x = r1; v.y = i1; *reinterpret_cast<fl2 *>(q + 8) = v; }
+            if (o.live1) { fl2 v; v.x = r1; v.y = i1; *reinterpret_cast<fl2 *>(q + 8 * LN) = v; }
         }
     }
-    template <bool A16>
-    VHD static void put_r(const Out &o, int row, f2 v) {
-        char *q = o.ob + row * o.rb;
-        if (A16 && o.live1) {
-            *reinterpret_cast<f2 *>(q) = v;
-        } else {
-            if (o.live0) *reinterpret_cast<float *>(q) = lo(v);
-            if (o.live1) *reinterpret_cast<float *>(q + 4) = hi(v);
-        }
-    }
-
-    // one-sided bin k of both slices, X = E (+/-) D handled by the caller through `sgn`
-    //   plus = true :  X[k]     = E + D
-    //   plus = false:  X[Mc-k]  = conj(E - D)
-    template <bool ONES, bool SPEC, bool A16>
-    VHD static void store_bin(const FwdArgs<float> &p, const Out &o, int k, C2 E, C2 D, bool plus) {
+    // mode epilogue of one-sided bin k (src/lib.rs:367-408) and the store(s)
+    template <bool ONES, bool SPEC>
+    VHD static void store_bin(const FwdArgs<float> &p, const Out &o, int k, float r0, float i0, float r1, float i1) {
         const bool edge = (k == 0 || k == MC);
-        const bool scale = ONES && p.mode == 3 && !edge;                 // src/lib.rs:397-403
-        if (SPEC) {
-            C2 X;
-            if (plus) { X.x = E.x + D.x; X.y = E.y + D.y; }
-            else { X.x = E.x - D.x; X.y = D.y - E.y; }
-            if (edge) X.y = bc(0.f);
-            if (scale) { X.x = X.x * bc(p.fac2x); X.y = X.y * bc(p.fac2x); }
-            const f2 v = vfma(X.y, X.y, X.x * X.x);
-            if (ONES) { put_r<A16>(o, k, v); return; }
-            put_r<A16>(o, (k + p.shift) & (M - 1), v);
-            if (!edge) put_r<A16>(o, (M - k + p.shift) & (M - 1), v);
+        if (edge) { i0 = 0.f; i1 = 0.f; }
+        if (ONES) {
+            if (p.mode == 3 && !edge) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }
+            put<SPEC>(o, k, r0, i0, r1, i1);
             return;
         }
-        // the last add is scalar: it moves (re,re)(im,im) into {re,im,re,im} for free
-        float r0, i0, r1, i1;
-        if (plus) {
-            r0 = lo(E.x) + lo(D.x); i0 = lo(E.y) + lo(D.y);
-            r1 = hi(E.x) + hi(D.x); i1 = hi(E.y) + hi(D.y);
-        } else {
-            r0 = lo(E.x) - lo(D.x); i0 = lo(D.y) - lo(E.y);
-            r1 = hi(E.x) - hi(D.x); i1 = hi(D.y) - hi(E.y);
+        put<SPEC>(o, (k + p.shift) & (M - 1), r0, i0, r1, i1);               // fftshift for centered
+        if (!edge) put<SPEC>(o, (M - k + p.shift) & (M - 1), r0, -i0, r1, -i1);
+    }
+
+    // own = Z[k_own]/2 of this thread's group, rcv = Z[Mc - k_own]/2 from the partner half;
+    // t = table entry of k_own (= (-wr, wi) of the partner's bin).  Produces X[k_own] only.
+    template <bool ONES, bool SPEC>
+    VHD static void emit1(const FwdArgs<float> &p, const Out &o, int k, fl4 t, C2 own, C2 rcv) {
+        const f2 Ex = own.x + rcv.x, Oy = own.y + rcv.y, ey = own.y - rcv.y, ox = own.x - rcv.x;
+        const f2 ax = vfma(bc(t.y), ox, Ex);                 // + wi * ox
+        const f2 ay = vfma(bc(t.y), Oy, ey);                 // + wi * Oy
+        // last fma scalar: moves (re,re)(im,im) into {re,im} per slice for free
+        const float r0 = t.x * lo(Oy) + lo(ax), r1 = t.x * hi(Oy) + hi(ax);
+        const float i0 = t.z * lo(ox) + lo(ay), i1 = t.z * hi(ox) + hi(ay);
+        store_bin<ONES, SPEC>(p, o, k, r0, i0, r1, i1);
+    }
+    // both outputs from values held by one thread (self-mirrored groups 0 and G/2)
+    template <bool ONES, bool SPEC>
+    VHD static void emit2(const FwdArgs<float> &p, const float *twp, const Out &o, int k, C2 A, C2 Zp, bool both) {
+        const fl4 t = GEO::tw4(twp + 4 * k);
+        emit1<ONES, SPEC>(p, o, k, t, A, Zp);
+        if (both) {
+            const fl4 tm = GEO::tw4(twp + 4 * (MC - k));
+            emit1<ONES, SPEC>(p, o, MC - k, tm, Zp, A);
         }
-        if (edge) { i0 = 0.f; i1 = 0.f; }                                // src/lib.rs:378-384
-        if (scale) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }
-        if (ONES) { put_c<A16>(o, k, r0, i0, r1, i1); return; }
-        put_c<A16>(o, (k + p.shift) & (M - 1), r0, i0, r1, i1);         // fftshift for centered
-        if (!edge) put_c<A16>(o, (M - k + p.shift) & (M - 1), r0, -i0, r1, -i1);
     }
 
-    // A = Z[k]/2, Zp = Z[Mc-k]/2  ->  X[k] (and X[Mc-k])
-    template <bool ONES, bool SPEC, bool A16>
-    VHD static void emit(const FwdArgs<float> &p, const float *twp, const Out &o, int k, C2 A, C2 Zp, bool both) {
-        C2 E, Om, D;
-        E.x = A.x + Zp.x;  E.y = A.y - Zp.y;                 // A + conj(Zp)
-        Om.x = A.x - Zp.x; Om.y = A.y + Zp.y;                // A - conj(Zp)
-        const fl4 t = GEO::tw4(twp + 4 * k);                 // (wr, wi, -wr, -wi) of W_M^k
-        D.x = vfma(bc(t.x), Om.y, bc(t.y) * Om.x);           // (-i W) Om
-        D.y = vfma(bc(t.z), Om.x, bc(t.y) * Om.y);
-        store_bin<ONES, SPEC, A16>(p, o, k, E, D, true);
-        if (both) store_bin<ONES, SPEC, A16>(p, o, MC - k, E, D, false);
+    // ---- last pass, part 1: this thread's group -> registers
+    //      sub = 2w + h:  w = 0 -> groups (0, G/2);  w >= 1 -> groups (w, G - w)
+    VHD static int group_of(int w, int h) { return h == 0 ? w : (w == 0 ? G / 2 : G - w); }
+    VHD static void last_dft(const PkFwdCtx &c, int tid, int it, C2 (&u)[RL]) {
+        const int l = tid % LN, sub = tid / LN;
+        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
+        if (w >= G / 2) return;
+        const float *w1 = c.work + (GEO::goff(group_of(w, h)) * 2) * TF + 2 * l;
+#pragma unroll
+        for (int d = 0; d < RL; ++d) u[d] = wload(w1 + (d * 2) * TF, TF);
+        Dft<RL, false, f2>::run(u);
     }
-
-    template <bool ONES, bool SPEC, bool A16>
-    VHD static void pass_last_t(const PkFwdCtx &c, int tid) {
+    // ---- last pass, part 2: exchange with the partner half, split, epilogue, store.
+    //      pu = the partner thread's u[] (host emulation only)
+    template <bool ONES, bool SPEC>
+    VHD static void last_emit_t(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
-        const int64_t pl = c.pt * TF + 2 * l;
+        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
+        if (w >= G / 2) return;
+        const int64_t pl = c.pt * TF + l;
         const int64_t esz = SPEC ? 4 : 8;
         Out o;
         o.live0 = pl < p.P;
-        o.live1 = pl + 1 < p.P;
+        o.live1 = pl + LN < p.P;
         o.rb = p.ldp * esz;
         o.ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
         const float *twp = c.tw + GEO::TWP;
-        for (int s = sub; s < G / 2; s += NSUB) {
-            const int g = s, gp = (s == 0) ? G / 2 : G - s;
-            C2 u[RL], up[RL];
-            const float *w1 = c.work + (GEO::goff(g) * 2) * TF + 2 * l;
-            const float *w2 = c.work + (GEO::goff(gp) * 2) * TF + 2 * l;
+        const int g = group_of(w, h);
+        const unsigned mask = pair_mask<LN>(tid);
+        if (w != 0) {
+            // bin of u[d]: k = g + G d.  Partner of half 0's u[d] is half 1's u[RL-1-d].
+            const float *tg = twp + 4 * g;
 #pragma unroll
             for (int d = 0; d < RL; ++d) {
-                u[d] = wload(w1 + (d * 2) * TF, TF);
-                up[d] = wload(w2 + (d * 2) * TF, TF);
+                // both halves name the same register: half 1 walks its array backwards
+                const int dl = d;                                    // local index, half 0
+                const int dr = RL - 1 - d;                           // local index, half 1
+                const C2 mine = h == 0 ? u[dl] : u[dr];
+                const C2 rcv = xchg<LN>(mine, pu ? pu + (h == 0 ? dr : dl) : nullptr, mask);
+                const int k = g + G * (h == 0 ? dl : dr);
+                const fl4 t = GEO::tw4(tg + 4 * G * (h == 0 ? dl : dr));
+                emit1<ONES, SPEC>(p, o, k, t, mine, rcv);
             }
-            Dft<RL, false, f2>::run(u);
-            Dft<RL, false, f2>::run(up);
-            if (!o.live0) continue;
-            if (s != 0) {
+        } else if (h == 0) {                                         // group 0: mirrors inside
+            emit2<ONES, SPEC>(p, twp, o, 0, u[0], u[0], true);      // X[0], X[Mc]
 #pragma unroll
-                for (int d = 0; d < RL; ++d)
-                    emit<ONES, SPEC, A16>(p, twp, o, g + G * d, u[d], up[RL - 1 - d], true);
-            } else {
-                emit<ONES, SPEC, A16>(p, twp, o, 0, u[0], u[0], true);
+            for (int d = 1; d < RL / 2; ++d) emit2<ONES, SPEC>(p, twp, o, G * d, u[d], u[RL - d], true);
+            emit2<ONES, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
+        } else {                                                     // group G/2: mirrors inside
 #pragma unroll
-                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC, A16>(p, twp, o, G * d, u[d], u[RL - d], true);
-                emit<ONES, SPEC, A16>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
-#pragma unroll
-                for (int d = 0; d < RL / 2; ++d)
-                    emit<ONES, SPEC, A16>(p, twp, o, G / 2 + G * d, up[d], up[RL - 1 - d], true);
-            }
+            for (int d = 0; d < RL / 2; ++d)
+                emit2<ONES, SPEC>(p, twp, o, G / 2 + G * d, u[d], u[RL - 1 - d], true);
         }
     }
-    VHD static void pass_last(const PkFwdCtx &c, int tid) {
+    VHD static void last_emit(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
-        const bool ones = p.mode >= 2;
-        // vector stores of two slices need an even row pitch and an aligned base
-        const int64_t esz = p.spectrogram ? 4 : 8;
-        const bool a16 = (p.ldp % 2 == 0) && ((((size_t)p.out) & (2 * esz - 1)) == 0);
-        if (p.spectrogram) {
-            if (ones) { if (a16) pass_last_t<true, true, true>(c, tid); else pass_last_t<true, true, false>(c, tid); }
-            else { if (a16) pass_last_t<false, true, true>(c, tid); else pass_last_t<false, true, false>(c, tid); }
+        if (p.mode >= 2) {
+            if (p.spectrogram) last_emit_t<true, true>(c, tid, it, u, pu);
+            else last_emit_t<true, false>(c, tid, it, u, pu);
         } else {
-            if (ones) { if (a16) pass_last_t<true, false, true>(c, tid); else pass_last_t<true, false, false>(c, tid); }
-            else { if (a16) pass_last_t<false, false, true>(c, tid); else pass_last_t<false, false, false>(c, tid); }
+            if (p.spectrogram) last_emit_t<false, true>(c, tid, it, u, pu);
+            else last_emit_t<false, false>(c, tid, it, u, pu);
         }
     }
 };
@@ -322,10 +349,6 @@ struct PkInvCtx {
     int64_t b, qa;
 };
 
-struct Raw {                 // one bin of both slices as loaded: {re0, im0, re1, im1}
-    float r0, i0, r1, i1;
-};
-
 template <int LOGMC, int TF_, int NSUB_>
 struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     using GEO = PkGeo<LOGMC, TF_, NSUB_>;
@@ -333,127 +356,126 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     using GEO::NP; using GEO::R1; using GEO::R2; using GEO::R3; using GEO::RL; using GEO::L1;
     using GEO::L2; using GEO::G;
     static constexpr int GPT = (G + NSUB - 1) / NSUB;
+    static constexpr int WPT = (L1 / 2 + NSUB / 2 - 1) / (NSUB / 2);    // pass-1 pairs per sub pair
 
     struct In {
-        const char *sb;      // byte pointer of (row 0, column of slice 2l)
+        const char *sb;      // byte pointer of (row 0, column of slice l)
         int64_t rb;
         bool live0, live1;
     };
-
-    template <bool A16>
     VHD static Raw get(const In &in, int row) {
         const char *q = in.sb + row * in.rb;
         Raw r;
-        if (A16 && in.live0 && in.live1) {
-            const fl4 v = *reinterpret_cast<const fl4 *>(q);
-            r.r0 = v.x; r.i0 = v.y; r.r1 = v.z; r.i1 = v.w;
-        } else {
-            r.r0 = r.i0 = r.r1 = r.i1 = 0.f;
-            if (in.live0) { const fl2 v = *reinterpret_cast<const fl2 *>(q); r.r0 = v.x; r.i0 = v.y; }
-            if (in.live1) { const fl2 v = *reinterpret_cast<const fl2 *>(q + 8); r.r1 = v.x; r.i1 = v.y; }
-        }
+        r.r0 = r.i0 = r.r1 = r.i1 = 0.f;
+        if (in.live0) { const fl2 v = *reinterpret_cast<const fl2 *>(q); r.r0 = v.x; r.i0 = v.y; }
+        if (in.live1) { const fl2 v = *reinterpret_cast<const fl2 *>(q + 8 * LN); r.r1 = v.x; r.i1 = v.y; }
         return r;
     }
-
     // Hermitian one-sided bin k (src/lib.rs:414-487); two-sided layouts: S[k] + conj(S[M-k])
-    template <bool ONES, bool A16>
+    template <bool ONES>
     VHD static Raw load_bin(const InvArgs<float> &p, const In &in, int k) {
         Raw v;
         if (ONES) {
-            v = get<A16>(in, k);
+            v = get(in, k);
             if (p.mode == 3 && k >= 1 && k <= MC - 1) {
                 v.r0 *= p.rfac2x; v.i0 *= p.rfac2x; v.r1 *= p.rfac2x; v.i1 *= p.rfac2x;
             }
         } else {
-            const Raw a = get<A16>(in, (k + p.shift) & (M - 1));
-            const Raw bq = get<A16>(in, (M - k + p.shift) & (M - 1));
+            const Raw a = get(in, (k + p.shift) & (M - 1));
+            const Raw bq = get(in, (M - k + p.shift) & (M - 1));
             v.r0 = a.r0 + bq.r0; v.i0 = a.i0 - bq.i0; v.r1 = a.r1 + bq.r1; v.i1 = a.i1 - bq.i1;
         }
         if (k == 0 || k == MC) { v.i0 = 0.f; v.i1 = 0.f; }
         return v;
     }
-
-    // (X[k], X[Mc-k]) -> (Z'[k], Z'[Mc-k]); the first adds are scalar and pack the two slices
-    VHD static void merge(const float *twp, int k, Raw A, Raw B, C2 &za, C2 &zb) {
-        C2 E, Dm;
-        E.x = mk2(A.r0 + B.r0, A.r1 + B.r1);  E.y = mk2(A.i0 - B.i0, A.i1 - B.i1);   // Xk + conj(Xm)
-        Dm.x = mk2(A.r0 - B.r0, A.r1 - B.r1); Dm.y = mk2(A.i0 + B.i0, A.i1 + B.i1);  // Xk - conj(Xm)
-        const fl4 t = GEO::tw4(twp + 4 * k);
-        const C2 O = cmulwc(Dm, bc(t.x), bc(t.y), bc(t.w));                           // conj(W) Dm
-        za.x = E.x - O.y; za.y = E.y + O.x;                                           // E + iO
-        zb.x = E.x + O.y; zb.y = O.x - E.y;                                           // conj(E - iO)
+    // own = X[k_own], rcv = X[Mc - k_own]; t = table entry of k_own.  Returns Z'[k_own].
+    // The first adds are scalar and pack the two slices.
+    VHD static C2 merge1(fl4 t, Raw own, Raw rcv) {
+        const f2 Ex = mk2(own.r0 + rcv.r0, own.r1 + rcv.r1), Dy = mk2(own.i0 + rcv.i0, own.i1 + rcv.i1);
+        const f2 ey = mk2(own.i0 - rcv.i0, own.i1 - rcv.i1), dx = mk2(own.r0 - rcv.r0, own.r1 - rcv.r1);
+        C2 z;
+        z.x = vfma(bc(t.z), Dy, vfma(bc(t.y), dx, Ex));      // Ex - wr Dy + wi dx
+        z.y = vfma(bc(t.x), dx, vfma(bc(t.y), Dy, ey));      // ey + wr dx + wi Dy
+        return z;
     }
 
-    template <bool ONES, bool A16>
-    VHD static void pass1_t(const PkInvCtx &c, int tid) {
+    // ---- pass 1, part 1: load this thread's group of bins (raw)
+    //      sub = 2w + h:  w = 0 -> groups (0, L1/2);  w >= 1 -> groups (w, L1 - w)
+    VHD static int group_of(int w, int h) { return h == 0 ? w : (w == 0 ? L1 / 2 : L1 - w); }
+    VHD static In make_in(const PkInvCtx &c, int l) {
         const InvArgs<float> &p = c.a;
-        const int l = tid % LN, sub = tid / LN;
-        const int64_t q0 = c.qa + 2 * l;
+        const int64_t q0 = c.qa + l, q1 = q0 + LN;
         const int64_t col = q0 - p.p_min;
         In in;
         in.live0 = q0 >= p.q0 && q0 < p.q1 && col >= 0 && col < p.P;
-        in.live1 = q0 + 1 >= p.q0 && q0 + 1 < p.q1 && col + 1 >= 0 && col + 1 < p.P;
+        in.live1 = q1 >= p.q0 && q1 < p.q1 && col + LN >= 0 && col + LN < p.P;
         in.rb = p.ldp * 8;
         in.sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * 8;
-        const float *twp0 = c.tw + GEO::TWP;
-        const bool any = in.live0 || in.live1;
-        for (int s = sub; s < L1 / 2; s += NSUB) {
-            const int j = s, jp = (s == 0) ? L1 / 2 : L1 - s;
-            C2 v[R1], vp[R1];
-            if (any) {
-                if (s != 0) {
+        return in;
+    }
+    template <bool ONES>
+    VHD static void p1_load_t(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
+        const int l = tid % LN, sub = tid / LN;
+        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
+        if (w >= L1 / 2) return;
+        const In in = make_in(c, l);
+        const int j = group_of(w, h);
 #pragma unroll
-                    for (int a = 0; a < R1; ++a) {
-                        const Raw xa = load_bin<ONES, A16>(p, in, j + L1 * a);
-                        const Raw xb = load_bin<ONES, A16>(p, in, jp + L1 * (R1 - 1 - a));
-                        merge(twp0, j + L1 * a, xa, xb, v[a], vp[R1 - 1 - a]);
-                    }
-                } else {
-                    const Raw x0 = load_bin<ONES, A16>(p, in, 0);
-                    const Raw xn = load_bin<ONES, A16>(p, in, MC);       // Nyquist pairs with DC
-                    v[0].x = mk2(x0.r0 + xn.r0, x0.r1 + xn.r1);
-                    v[0].y = mk2(x0.r0 - xn.r0, x0.r1 - xn.r1);
+        for (int a = 0; a < R1; ++a) x[a] = load_bin<ONES>(c.a, in, j + L1 * a);
+        xn = x[0];
+        if (w == 0 && h == 0) xn = load_bin<ONES>(c.a, in, MC);          // Nyquist pairs with DC
+    }
+    VHD static void p1_load(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
+        if (c.a.mode >= 2) p1_load_t<true>(c, tid, it, x, xn);
+        else p1_load_t<false>(c, tid, it, x, xn);
+    }
+    // ---- pass 1, part 2: exchange, real-IFFT merge, IDFT_R1, twiddle, store
+    //      px = the partner thread's x[] (host emulation only)
+    VHD static void p1_rest(const PkInvCtx &c, int tid, int it, const Raw (&x)[R1], const Raw &xn, const Raw *px) {
+        const int l = tid % LN, sub = tid / LN;
+        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
+        if (w >= L1 / 2) return;
+        const float *twp = c.tw + GEO::TWP;
+        const int j = group_of(w, h);
+        const unsigned mask = pair_mask<LN>(tid);
+        C2 v[R1];
+        if (w != 0) {
+            const float *tj = twp + 4 * j;
 #pragma unroll
-                    for (int a = 1; a < R1 / 2; ++a) {
-                        const Raw xa = load_bin<ONES, A16>(p, in, L1 * a);
-                        const Raw xb = load_bin<ONES, A16>(p, in, L1 * (R1 - a));
-                        merge(twp0, L1 * a, xa, xb, v[a], v[R1 - a]);
-                    }
-                    {
-                        const Raw xm = load_bin<ONES, A16>(p, in, MC / 2);
-                        C2 dummy;
-                        merge(twp0, MC / 2, xm, xm, v[R1 / 2], dummy);
-                    }
-#pragma unroll
-                    for (int a = 0; a < R1 / 2; ++a) {
-                        const Raw xa = load_bin<ONES, A16>(p, in, jp + L1 * a);
-                        const Raw xb = load_bin<ONES, A16>(p, in, jp + L1 * (R1 - 1 - a));
-                        merge(twp0, jp + L1 * a, xa, xb, vp[a], vp[R1 - 1 - a]);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int a = 0; a < R1; ++a) v[a] = vp[a] = c2zero();
+            for (int a = 0; a < R1; ++a) {
+                // bin j + L1 a of half 0 mirrors bin jp + L1 (R1-1-a) of half 1
+                const int al = a, ar = R1 - 1 - a;
+                const Raw mine = h == 0 ? x[al] : x[ar];
+                const Raw rcv = xchg_raw<LN>(mine, px ? px + (h == 0 ? ar : al) : nullptr, mask);
+                const int am = h == 0 ? al : ar;
+                const C2 z = merge1(GEO::tw4(tj + 4 * L1 * am), mine, rcv);
+                if (h == 0) v[al] = z; else v[ar] = z;
             }
-            Dft<R1, true, f2>::run(v);
-            Dft<R1, true, f2>::run(vp);
-            float *wj = c.work + (j * 2) * TF + 2 * l, *wp = c.work + (jp * 2) * TF + 2 * l;
-            const float *twj = c.tw + GEO::TW1 + 4 * j * R1, *twq = c.tw + GEO::TW1 + 4 * jp * R1;
-            wstore(wj, TF, v[0]);
-            wstore(wp, TF, vp[0]);
+        } else if (h == 0) {                                          // group 0: mirrors inside
+            v[0].x = mk2(x[0].r0 + xn.r0, x[0].r1 + xn.r1);
+            v[0].y = mk2(x[0].r0 - xn.r0, x[0].r1 - xn.r1);
 #pragma unroll
-            for (int cc = 1; cc < R1; ++cc) {
-                const fl4 t = GEO::tw4(twj + 4 * cc), tq = GEO::tw4(twq + 4 * cc);
-                wstore(wj + (L1 * cc * 2) * TF, TF, cmulwc(v[cc], bc(t.x), bc(t.y), bc(t.w)));
-                wstore(wp + (L1 * cc * 2) * TF, TF, cmulwc(vp[cc], bc(tq.x), bc(tq.y), bc(tq.w)));
+            for (int a = 1; a < R1 / 2; ++a) {
+                v[a] = merge1(GEO::tw4(twp + 4 * L1 * a), x[a], x[R1 - a]);
+                v[R1 - a] = merge1(GEO::tw4(twp + 4 * L1 * (R1 - a)), x[R1 - a], x[a]);
+            }
+            v[R1 / 2] = merge1(GEO::tw4(twp + 4 * (MC / 2)), x[R1 / 2], x[R1 / 2]);
+        } else {                                                      // group L1/2
+#pragma unroll
+            for (int a = 0; a < R1 / 2; ++a) {
+                v[a] = merge1(GEO::tw4(twp + 4 * (j + L1 * a)), x[a], x[R1 - 1 - a]);
+                v[R1 - 1 - a] = merge1(GEO::tw4(twp + 4 * (j + L1 * (R1 - 1 - a))), x[R1 - 1 - a], x[a]);
             }
         }
-    }
-    VHD static void pass1(const PkInvCtx &c, int tid) {
-        const InvArgs<float> &p = c.a;
-        const bool a16 = (p.ldp % 2 == 0) && ((((size_t)p.S) & 15) == 0) && (((c.qa - p.p_min) & 1) == 0);
-        if (p.mode >= 2) { if (a16) pass1_t<true, true>(c, tid); else pass1_t<true, false>(c, tid); }
-        else { if (a16) pass1_t<false, true>(c, tid); else pass1_t<false, false>(c, tid); }
+        Dft<R1, true, f2>::run(v);
+        float *wj = c.work + (j * 2) * TF + 2 * l;
+        const float *twj = c.tw + GEO::TW1 + 4 * j * R1;
+        wstore(wj, TF, v[0]);
+#pragma unroll
+        for (int cc = 1; cc < R1; ++cc) {
+            const fl4 t = GEO::tw4(twj + 4 * cc);
+            wstore(wj + (L1 * cc * 2) * TF, TF, cmulwc(v[cc], bc(t.x), bc(t.y), bc(t.w)));
+        }
     }
 
     VHD static void pass_mid(const PkInvCtx &c, int tid) {
@@ -494,7 +516,7 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         const InvArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
         const int ps = p.ps, N = p.N;
-        float *row0 = c.ola + (size_t)(2 * l) * p.ostride, *row1 = row0 + p.ostride;
+        float *row0 = c.ola + (size_t)l * p.ostride, *row1 = row0 + (size_t)LN * p.ostride;
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
             const int g = sub + NSUB * i;
@@ -519,7 +541,7 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         }
     }
 
-    // overlap-add gather over the samples this tile owns, increasing q (same as scalar family)
+    // overlap-add gather over the samples this tile owns, increasing q (src/lib.rs:853)
     VHD static void gather(const PkInvCtx &c, int tid) {
         const InvArgs<float> &p = c.a;
         const int H = p.H, N = p.N, halo = p.halo;
