@@ -138,13 +138,18 @@ struct EmuPkInv {
         std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
         p2::pk_twiddle_fill(prm.M, twd.data());
         const double sc = 1.0 / ((double)prm.M * (prm.mode >= 2 ? 1.0 : 2.0));
-        std::vector<float> tw = conv<float>(twd), dual = conv<float>(pl->dual, sc);
+        std::vector<float> tw = conv<float>(twd);
+        std::vector<double> ds(pl->dual);
+        for (double &v : ds) v *= sc;
+        std::vector<ITab> itab((size_t)K::MC);
+        pk_itab_fill(prm.M, prm.N, prm.ps, ds.data(), itab.data());
         PkInvCtx c;
-        c.a = make_inv_args<float>(S, (float *)xo, prm, dual.data(), tw.data(), TF);
+        c.a = make_inv_args<float>(S, (float *)xo, prm, nullptr, tw.data(), TF);
+        c.a.ostride = pk_ostride(prm.N);
         size_t elems = (size_t)K::MC * 2 * TF;
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<fl4> buf(elems / 4 + 4);
-        c.work = (float *)buf.data(); c.ola = (float *)buf.data(); c.tw = tw.data(); c.dual = dual.data();
+        c.work = (float *)buf.data(); c.ola = (float *)buf.data(); c.tw = tw.data(); c.itab = itab.data();
         const int own = TF - c.a.halo;
         std::vector<C2> regs((size_t)K::NT * K::GPT * K::RL);
         std::vector<Raw> raws((size_t)K::NT * (K::R1 + 1));

@@ -25,6 +25,7 @@ struct DeviceTables {
     void *tw_pow2 = nullptr;
     float *tw_pk = nullptr;
     void *ptab_pk = nullptr;
+    void *itab_pk = nullptr;
 };
 }  // namespace veils
 
@@ -124,6 +125,14 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
         const double sc = 1.0 / ((double)pl.M * (pl.mode >= ONESIDED ? 1.0 : 2.0));
         cudaError_t e = upload_prec(pl, pl.dual, &pl.dev->dual_scaled, sc);
         if (e == cudaSuccess) e = upload_prec(pl, pl.dual, &pl.dev->dual);
+        if (e == cudaSuccess && pl.pk_inv) {
+            std::vector<double> ds(pl.dual);
+            for (double &v : ds) v *= sc;
+            std::vector<unsigned char> it((size_t)(pl.M / 2) * 16);
+            pk_itab_fill_host(pl.M, pl.N, pl.ps, ds.data(), it.data());
+            e = cudaMalloc(&pl.dev->itab_pk, it.size());
+            if (e == cudaSuccess) e = cudaMemcpy(pl.dev->itab_pk, it.data(), it.size(), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) return cuda_fail(e, "upload dual window");
     }
     return VEILS_OK;
@@ -140,6 +149,7 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.tw_pow2 = (const T *)pl.dev->tw_pow2;
     tb.tw_pk = pl.dev->tw_pk;
     tb.ptab_pk = pl.dev->ptab_pk;
+    tb.itab_pk = pl.dev->itab_pk;
     return tb;
 }
 
@@ -184,6 +194,7 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->tw_pow2);
         cudaFree(p->pl.dev->tw_pk);
         cudaFree(p->pl.dev->ptab_pk);
+        cudaFree(p->pl.dev->itab_pk);
         delete p->pl.dev;
     }
     delete p;

@@ -39,6 +39,7 @@ struct Tables {
     const T *tw_pow2 = nullptr;         // pow2 twiddles (layout: pow2_cfg.hpp)
     const float *tw_pk = nullptr;       // packed-f32 twiddles (layout: pow2_pk_cfg.hpp)
     const void *ptab_pk = nullptr;      // packed-f32 tile table [M/2] x 16 bytes
+    const void *itab_pk = nullptr;      // packed-f32 inverse table [M/2] x 16 bytes
 };
 
 extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library
@@ -68,6 +69,8 @@ bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse);
 int64_t pk_twiddle_count(int64_t M);
 void pk_twiddle_fill(int64_t M, double *re_im_pairs);
 // tile table (offset + window per sample pair), M/2 entries of 16 bytes, from the unscaled window
+// inverse table (overlap-row offsets + dual / M per sample pair) from the scaled dual window
+void pk_itab_fill_host(int64_t M, int64_t N, int64_t ps, const double *dual_scaled, void *out16);
 void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, void *out16);
 cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st);
 cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const Tables<float> &tb, cudaStream_t st);

@@ -44,10 +44,13 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         xin0[zero_off + tid] = 0.f;
         xin1[zero_off + tid] = 0.f;
     }
+    // (signal, tile) of work item w, advanced incrementally: w += gridDim.x
     int64_t w = blockIdx.x;
+    int64_t cb = w / args.ptiles, cpt = w - cb * args.ptiles;
+    const int64_t gb = gridDim.x / args.ptiles, gr = gridDim.x - gb * args.ptiles;
     if (w < total) {
-        c.b = w / args.ptiles;
-        c.pt = w - c.b * args.ptiles;
+        c.b = cb;
+        c.pt = cpt;
         c.xin = xin0;
         K::fill(c, tid);
         cp_async_commit();
@@ -57,22 +60,24 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         __syncthreads();
         float *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
         const int64_t wn = w + gridDim.x;
+        int64_t nb = cb + gb, npt = cpt + gr;
+        if (npt >= args.ptiles) { npt -= args.ptiles; ++nb; }
         if (K::DBUF && wn < total) {
-            c.b = wn / args.ptiles;
-            c.pt = wn - c.b * args.ptiles;
+            c.b = nb;
+            c.pt = npt;
             c.xin = (it & 1) ? xin0 : xin1;
             K::fill(c, tid);
             cp_async_commit();
         }
-        c.b = w / args.ptiles;
-        c.pt = w - c.b * args.ptiles;
+        c.b = cb;
+        c.pt = cpt;
         c.xin = cur;
         K::pass1(c, tid);
         __syncthreads();
         if (!K::DBUF && wn < total) {
             PkFwdCtx cn = c;
-            cn.b = wn / args.ptiles;
-            cn.pt = wn - cn.b * args.ptiles;
+            cn.b = nb;
+            cn.pt = npt;
             K::fill(cn, tid);
             cp_async_commit();
         }
@@ -86,12 +91,15 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
             K::last_dft(c, tid, i, u);
             K::last_emit(c, tid, i, u, nullptr);
         }
+        cb = nb;
+        cpt = npt;
     }
 }
 
 template <int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
-pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const int64_t total, const int work_bytes) {
+pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
+              const int64_t total, const int work_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = PkInv<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -101,20 +109,25 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const int64_t total, 
     c.ola = reinterpret_cast<float *>(smem);
     if (K::STAB) {
         float *stw = reinterpret_cast<float *>(smem + work_bytes);
-        float *sdual = stw + K::TWN;
+        ITab *sitab = reinterpret_cast<ITab *>(stw + K::TWN);
         copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
-        copy_table_f(sdual, args.dual, args.N, tid, K::NT);
+        copy_table_f(reinterpret_cast<float *>(sitab), reinterpret_cast<const float *>(itab_g), 4 * K::MC, tid, K::NT);
         c.tw = stw;
-        c.dual = sdual;
+        c.itab = sitab;
     } else {
         c.tw = args.tw;
-        c.dual = args.dual;
+        c.itab = itab_g;
     }
     __syncthreads();
     const int own = TF - args.halo;
+    int64_t cb = blockIdx.x / args.ntiles, ct = blockIdx.x - cb * args.ntiles;
+    const int64_t gb = gridDim.x / args.ntiles, gr = gridDim.x - gb * args.ntiles;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        c.b = w / args.ntiles;
-        c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
+        c.b = cb;
+        c.qa = args.qa0 + ct * own;
+        cb += gb;
+        ct += gr;
+        if (ct >= args.ntiles) { ct -= args.ntiles; ++cb; }
 #pragma unroll 1
         for (int i = 0; i < K::WPT; ++i) {
             Raw x[K::R1];
@@ -172,12 +185,13 @@ struct PkFwdLaunch {
 };
 
 struct PkInvLaunch {
-    const void *S; float *xo; const InvParams *prm; const float *dual; const float *tw; cudaStream_t st;
+    const void *S; float *xo; const InvParams *prm; const ITab *itab; const float *tw; cudaStream_t st;
     template <int LOGMC, int TF, int NSUB>
     cudaError_t run() {
         const InvParams &p = *prm;
         if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
-        InvArgs<float> a = make_inv_args<float>(S, xo, p, dual, tw, TF);
+        InvArgs<float> a = make_inv_args<float>(S, xo, p, nullptr, tw, TF);
+        a.ostride = pk_ostride(p.N);
         const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
         const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
         auto kern = pk_inv_kernel<LOGMC, TF, NSUB>;
@@ -189,7 +203,7 @@ struct PkInvLaunch {
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ntiles * p.batch;
         const int64_t cap = (int64_t)per_sm * pk_num_sms();
-        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, total, work_bytes);
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes);
         ++g_launch_count;
         return cudaGetLastError();
     }
@@ -201,6 +215,9 @@ bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse) {
     return p2::pk_supported(M, N, H, ps, inverse);
 }
 int64_t pk_twiddle_count(int64_t M) { return p2::pk_twiddle_count(M); }
+void pk_itab_fill_host(int64_t M, int64_t N, int64_t ps, const double *dual_scaled, void *out16) {
+    p2::pk_itab_fill(M, N, ps, dual_scaled, (p2::ITab *)out16);
+}
 void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, void *out16) {
     p2::Cfg c;
     if (!p2::pk_cfg_for(M, &c)) return;
@@ -220,7 +237,7 @@ cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const 
     if (prm.batch <= 0 || prm.k1 <= prm.k0) return cudaSuccess;
     p2::Cfg c;
     if (!p2::pk_cfg_for(prm.M, &c)) return cudaErrorNotSupported;
-    PkInvLaunch l{S, x_out, &prm, tb.dual_scaled, tb.tw_pk, st};
+    PkInvLaunch l{S, x_out, &prm, (const ITab *)tb.itab_pk, tb.tw_pk, st};
     return p2::pk_dispatch(c.logmc, l);
 }
 

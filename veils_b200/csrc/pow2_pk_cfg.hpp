@@ -81,6 +81,21 @@ inline void pk_ptab_fill(int64_t M, int64_t N, int64_t H, int64_t ps, const doub
         t[m] = e;
     }
 }
+// inverse plan table: sample pair m of a slice -> positions in its overlap row and dual / M.
+// y index i = 2m, 2m+1 is rolled back to j = (i + ps) mod M (src/lib.rs:499-500); j >= m_num is
+// truncated (:503): such samples are written to the dump slot at offset m_num.
+inline void pk_itab_fill(int64_t M, int64_t N, int64_t ps, const double *dual_scaled, ITab *t) {
+    for (int64_t m = 0; m < M / 2; ++m) {
+        const int64_t j0 = (2 * m + ps) & (M - 1), j1 = (j0 + 1) & (M - 1);
+        ITab e;
+        e.o0 = j0 < N ? (int)j0 : (int)N;
+        e.o1 = j1 < N ? (int)j1 : (int)N;
+        e.d0 = j0 < N ? (float)dual_scaled[j0] : 0.f;
+        e.d1 = j1 < N ? (float)dual_scaled[j1] : 0.f;
+        t[m] = e;
+    }
+}
+inline int pk_ostride(int64_t N) { return (int)((N + 1) | 1); }     // odd, > m_num (dump slot)
 inline int pk_zero_off(int64_t N, int64_t H, int tf) {
     const TileLayout lay = tile_layout(H, true);
     const int64_t span = (int64_t)(tf - 1) * H + N;
@@ -91,7 +106,7 @@ template <int LOGMC, int TF>
 inline size_t pk_inv_work_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
     size_t work = 4 * (size_t)G::MC * 2 * TF;
-    const size_t ola = 4 * (size_t)TF * (size_t)(N | 1);
+    const size_t ola = 4 * (size_t)TF * (size_t)pk_ostride(N);
     if (ola > work) work = ola;
     return (work + 15) & ~(size_t)15;
 }
@@ -99,7 +114,7 @@ template <int LOGMC, int TF>
 inline size_t pk_inv_smem_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
     size_t b = pk_inv_work_bytes<LOGMC, TF>(N);
-    if (G::STAB) b += 4 * ((size_t)G::TWN + (size_t)N);
+    if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(ITab) * (size_t)G::MC;
     return b;
 }
 

@@ -28,6 +28,7 @@ namespace p2 {
 struct alignas(8) fl2 { float x, y; };
 struct alignas(16) fl4 { float x, y, z, w; };
 struct alignas(16) PTab { int aoff; int pad; float w0, w1; };   // one sample pair of a slice
+struct alignas(16) ITab { int o0, o1; float d0, d1; };           // inverse: ola offsets + dual/M of a pair
 
 template <int LOGMC, int TF_, int NSUB_>
 struct PkGeo {
@@ -64,9 +65,13 @@ struct PkGeo {
 #endif
         return *q;
     }
-    VHD static float t1(const float *q) {
+    VHD static ITab it4(const ITab *q) {
 #if defined(__CUDA_ARCH__)
-        if (!STAB) return __ldg(q);
+        if (!STAB) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(q));
+            ITab r; r.o0 = v.x; r.o1 = v.y; r.d0 = __int_as_float(v.z); r.d1 = __int_as_float(v.w);
+            return r;
+        }
 #endif
         return *q;
     }
@@ -226,8 +231,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         bool live0, live1;   // slice l / l + LN inside [0, P)
     };
     template <bool SPEC>
-    VHD static void put(const Out &o, int row, float r0, float i0, float r1, float i1) {
-        char *q = o.ob + row * o.rb;
+    VHD static void put_at(const Out &o, char *q, float r0, float i0, float r1, float i1) {
         if (SPEC) {
             if (o.live0) *reinterpret_cast<float *>(q) = r0 * r0 + i0 * i0;
             if (o.live1) *reinterpret_cast<float *>(q + 4 * LN) = r1 * r1 + i1 * i1;
@@ -236,41 +240,40 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             if (o.live1) { fl2 v; v.x = r1; v.y = i1; *reinterpret_cast<fl2 *>(q + 8 * LN) = v; }
         }
     }
-    // mode epilogue of one-sided bin k (src/lib.rs:367-408) and the store(s)
-    template <bool ONES, bool SPEC>
-    VHD static void store_bin(const FwdArgs<float> &p, const Out &o, int k, float r0, float i0, float r1, float i1) {
-        const bool edge = (k == 0 || k == MC);
+    // mode epilogue of one-sided bin k (src/lib.rs:367-408) and the store(s).
+    // MODE: 0 twosided, 1 centered, 2 onesided, 3 onesided2X.  EDGE: k may be 0 or Mc.
+    // q: byte pointer of row k (one-sided layouts only).
+    template <int MODE, bool SPEC, bool EDGE>
+    VHD static void store_bin(const FwdArgs<float> &p, const Out &o, char *q, int k, float r0, float i0, float r1, float i1) {
+        const bool edge = EDGE && (k == 0 || k == MC);
         if (edge) { i0 = 0.f; i1 = 0.f; }
-        if (ONES) {
-            if (p.mode == 3 && !edge) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }
-            put<SPEC>(o, k, r0, i0, r1, i1);
+        if (MODE >= 2) {
+            if (MODE == 3 && !edge) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }
+            put_at<SPEC>(o, q, r0, i0, r1, i1);
             return;
         }
-        put<SPEC>(o, (k + p.shift) & (M - 1), r0, i0, r1, i1);               // fftshift for centered
-        if (!edge) put<SPEC>(o, (M - k + p.shift) & (M - 1), r0, -i0, r1, -i1);
+        const int sh = MODE == 1 ? MC : 0;                                    // fftshift for centered
+        put_at<SPEC>(o, o.ob + ((k + sh) & (M - 1)) * o.rb, r0, i0, r1, i1);
+        if (!edge) put_at<SPEC>(o, o.ob + ((M - k + sh) & (M - 1)) * o.rb, r0, -i0, r1, -i1);
     }
 
-    // own = Z[k_own]/2 of this thread's group, rcv = Z[Mc - k_own]/2 from the partner half;
-    // t = table entry of k_own (= (-wr, wi) of the partner's bin).  Produces X[k_own] only.
-    template <bool ONES, bool SPEC>
-    VHD static void emit1(const FwdArgs<float> &p, const Out &o, int k, fl4 t, C2 own, C2 rcv) {
+    // own = Z[k_own]/2 of this thread's group, rcv = Z[Mc - k_own]/2 (partner half or own
+    // registers); t = table entry of k_own (= (-wr, wi) of the mirrored bin).  Produces X[k_own].
+    template <int MODE, bool SPEC, bool EDGE>
+    VHD static void emit1(const FwdArgs<float> &p, const Out &o, char *q, int k, fl4 t, C2 own, C2 rcv) {
         const f2 Ex = own.x + rcv.x, Oy = own.y + rcv.y, ey = own.y - rcv.y, ox = own.x - rcv.x;
         const f2 ax = vfma(bc(t.y), ox, Ex);                 // + wi * ox
         const f2 ay = vfma(bc(t.y), Oy, ey);                 // + wi * Oy
         // last fma scalar: moves (re,re)(im,im) into {re,im} per slice for free
         const float r0 = t.x * lo(Oy) + lo(ax), r1 = t.x * hi(Oy) + hi(ax);
         const float i0 = t.z * lo(ox) + lo(ay), i1 = t.z * hi(ox) + hi(ay);
-        store_bin<ONES, SPEC>(p, o, k, r0, i0, r1, i1);
+        store_bin<MODE, SPEC, EDGE>(p, o, q, k, r0, i0, r1, i1);
     }
     // both outputs from values held by one thread (self-mirrored groups 0 and G/2)
-    template <bool ONES, bool SPEC>
+    template <int MODE, bool SPEC>
     VHD static void emit2(const FwdArgs<float> &p, const float *twp, const Out &o, int k, C2 A, C2 Zp, bool both) {
-        const fl4 t = GEO::tw4(twp + 4 * k);
-        emit1<ONES, SPEC>(p, o, k, t, A, Zp);
-        if (both) {
-            const fl4 tm = GEO::tw4(twp + 4 * (MC - k));
-            emit1<ONES, SPEC>(p, o, MC - k, tm, Zp, A);
-        }
+        emit1<MODE, SPEC, true>(p, o, o.ob + k * o.rb, k, GEO::tw4(twp + 4 * k), A, Zp);
+        if (both) emit1<MODE, SPEC, true>(p, o, o.ob + (MC - k) * o.rb, MC - k, GEO::tw4(twp + 4 * (MC - k)), Zp, A);
     }
 
     // ---- last pass, part 1: this thread's group -> registers
@@ -287,7 +290,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     }
     // ---- last pass, part 2: exchange with the partner half, split, epilogue, store.
     //      pu = the partner thread's u[] (host emulation only)
-    template <bool ONES, bool SPEC>
+    template <int MODE, bool SPEC>
     VHD static void last_emit_t(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
@@ -304,38 +307,50 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         const int g = group_of(w, h);
         const unsigned mask = pair_mask<LN>(tid);
         if (w != 0) {
-            // bin of u[d]: k = g + G d.  Partner of half 0's u[d] is half 1's u[RL-1-d].
-            const float *tg = twp + 4 * g;
+            // bin of u[d]: k = g + G d.  Partner of half 0's u[d] is half 1's u[RL-1-d]: half 1 walks
+            // its bins backwards, so row pointer, table pointer and k advance by a per-thread stride.
+            int k = g + (h == 0 ? 0 : G * (RL - 1));
+            const int kstep = h == 0 ? G : -G;
+            char *q = o.ob + k * o.rb;
+            const int64_t qstep = kstep * o.rb;
+            const float *tq = twp + 4 * k;
+            const int tstep = 4 * kstep;
 #pragma unroll
             for (int d = 0; d < RL; ++d) {
-                // both halves name the same register: half 1 walks its array backwards
-                const int dl = d;                                    // local index, half 0
-                const int dr = RL - 1 - d;                           // local index, half 1
-                const C2 mine = h == 0 ? u[dl] : u[dr];
-                const C2 rcv = xchg<LN>(mine, pu ? pu + (h == 0 ? dr : dl) : nullptr, mask);
-                const int k = g + G * (h == 0 ? dl : dr);
-                const fl4 t = GEO::tw4(tg + 4 * G * (h == 0 ? dl : dr));
-                emit1<ONES, SPEC>(p, o, k, t, mine, rcv);
+                const C2 mine = h == 0 ? u[d] : u[RL - 1 - d];
+                const C2 rcv = xchg<LN>(mine, pu ? pu + (h == 0 ? RL - 1 - d : d) : nullptr, mask);
+                emit1<MODE, SPEC, false>(p, o, q, k, GEO::tw4(tq), mine, rcv);
+                k += kstep;
+                q += qstep;
+                tq += tstep;
             }
         } else if (h == 0) {                                         // group 0: mirrors inside
-            emit2<ONES, SPEC>(p, twp, o, 0, u[0], u[0], true);      // X[0], X[Mc]
+            emit2<MODE, SPEC>(p, twp, o, 0, u[0], u[0], true);      // X[0], X[Mc]
 #pragma unroll
-            for (int d = 1; d < RL / 2; ++d) emit2<ONES, SPEC>(p, twp, o, G * d, u[d], u[RL - d], true);
-            emit2<ONES, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
+            for (int d = 1; d < RL / 2; ++d) emit2<MODE, SPEC>(p, twp, o, G * d, u[d], u[RL - d], true);
+            emit2<MODE, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
         } else {                                                     // group G/2: mirrors inside
 #pragma unroll
             for (int d = 0; d < RL / 2; ++d)
-                emit2<ONES, SPEC>(p, twp, o, G / 2 + G * d, u[d], u[RL - 1 - d], true);
+                emit2<MODE, SPEC>(p, twp, o, G / 2 + G * d, u[d], u[RL - 1 - d], true);
         }
     }
     VHD static void last_emit(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
-        if (p.mode >= 2) {
-            if (p.spectrogram) last_emit_t<true, true>(c, tid, it, u, pu);
-            else last_emit_t<true, false>(c, tid, it, u, pu);
+        if (p.spectrogram) {
+            switch (p.mode) {
+                case 0: last_emit_t<0, true>(c, tid, it, u, pu); break;
+                case 1: last_emit_t<1, true>(c, tid, it, u, pu); break;
+                case 2: last_emit_t<2, true>(c, tid, it, u, pu); break;
+                default: last_emit_t<3, true>(c, tid, it, u, pu); break;
+            }
         } else {
-            if (p.spectrogram) last_emit_t<false, true>(c, tid, it, u, pu);
-            else last_emit_t<false, false>(c, tid, it, u, pu);
+            switch (p.mode) {
+                case 0: last_emit_t<0, false>(c, tid, it, u, pu); break;
+                case 1: last_emit_t<1, false>(c, tid, it, u, pu); break;
+                case 2: last_emit_t<2, false>(c, tid, it, u, pu); break;
+                default: last_emit_t<3, false>(c, tid, it, u, pu); break;
+            }
         }
     }
 };
@@ -343,7 +358,8 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
 // ================================================================== INVERSE (packed)
 struct PkInvCtx {
     InvArgs<float> a;
-    const float *tw, *dual;
+    const float *tw;
+    const ITab *itab;        // [MC] ola offsets + dual/M of sample pair m
     float *work;             // planar [MC][2][TF]
     float *ola;              // [TF][ostride] -- ALIASES work
     int64_t b, qa;
@@ -363,29 +379,29 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         int64_t rb;
         bool live0, live1;
     };
-    VHD static Raw get(const In &in, int row) {
-        const char *q = in.sb + row * in.rb;
+    VHD static Raw get_at(const In &in, const char *q) {
         Raw r;
         r.r0 = r.i0 = r.r1 = r.i1 = 0.f;
         if (in.live0) { const fl2 v = *reinterpret_cast<const fl2 *>(q); r.r0 = v.x; r.i0 = v.y; }
         if (in.live1) { const fl2 v = *reinterpret_cast<const fl2 *>(q + 8 * LN); r.r1 = v.x; r.i1 = v.y; }
         return r;
     }
-    // Hermitian one-sided bin k (src/lib.rs:414-487); two-sided layouts: S[k] + conj(S[M-k])
-    template <bool ONES>
-    VHD static Raw load_bin(const InvArgs<float> &p, const In &in, int k) {
+    // Hermitian one-sided bin k (src/lib.rs:414-487); two-sided layouts: S[k] + conj(S[M-k]).
+    // q: byte pointer of row k (one-sided layouts).  Im(DC), Im(Nyquist) are cleared by the caller.
+    template <int MODE>
+    VHD static Raw load_bin(const InvArgs<float> &p, const In &in, const char *q, int k) {
         Raw v;
-        if (ONES) {
-            v = get(in, k);
-            if (p.mode == 3 && k >= 1 && k <= MC - 1) {
+        if (MODE >= 2) {
+            v = get_at(in, q);
+            if (MODE == 3 && k >= 1 && k <= MC - 1) {
                 v.r0 *= p.rfac2x; v.i0 *= p.rfac2x; v.r1 *= p.rfac2x; v.i1 *= p.rfac2x;
             }
         } else {
-            const Raw a = get(in, (k + p.shift) & (M - 1));
-            const Raw bq = get(in, (M - k + p.shift) & (M - 1));
+            const int sh = MODE == 1 ? MC : 0;                                // ifftshift :516-521
+            const Raw a = get_at(in, in.sb + ((k + sh) & (M - 1)) * in.rb);
+            const Raw bq = get_at(in, in.sb + ((M - k + sh) & (M - 1)) * in.rb);
             v.r0 = a.r0 + bq.r0; v.i0 = a.i0 - bq.i0; v.r1 = a.r1 + bq.r1; v.i1 = a.i1 - bq.i1;
         }
-        if (k == 0 || k == MC) { v.i0 = 0.f; v.i1 = 0.f; }
         return v;
     }
     // own = X[k_own], rcv = X[Mc - k_own]; t = table entry of k_own.  Returns Z'[k_own].
@@ -413,21 +429,34 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         in.sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * 8;
         return in;
     }
-    template <bool ONES>
+    template <int MODE>
     VHD static void p1_load_t(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
         const int l = tid % LN, sub = tid / LN;
         const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
         if (w >= L1 / 2) return;
         const In in = make_in(c, l);
         const int j = group_of(w, h);
+        const char *q = in.sb + j * in.rb;
+        const int64_t qstep = L1 * in.rb;
 #pragma unroll
-        for (int a = 0; a < R1; ++a) x[a] = load_bin<ONES>(c.a, in, j + L1 * a);
+        for (int a = 0; a < R1; ++a) {
+            x[a] = load_bin<MODE>(c.a, in, q, j + L1 * a);
+            q += qstep;
+        }
         xn = x[0];
-        if (w == 0 && h == 0) xn = load_bin<ONES>(c.a, in, MC);          // Nyquist pairs with DC
+        if (w == 0 && h == 0) {                                           // DC pairs with Nyquist;
+            xn = load_bin<MODE>(c.a, in, in.sb + MC * in.rb, MC);         // irfft ignores their Im
+            x[0].i0 = x[0].i1 = 0.f;
+            xn.i0 = xn.i1 = 0.f;
+        }
     }
     VHD static void p1_load(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
-        if (c.a.mode >= 2) p1_load_t<true>(c, tid, it, x, xn);
-        else p1_load_t<false>(c, tid, it, x, xn);
+        switch (c.a.mode) {
+            case 0: p1_load_t<0>(c, tid, it, x, xn); break;
+            case 1: p1_load_t<1>(c, tid, it, x, xn); break;
+            case 2: p1_load_t<2>(c, tid, it, x, xn); break;
+            default: p1_load_t<3>(c, tid, it, x, xn); break;
+        }
     }
     // ---- pass 1, part 2: exchange, real-IFFT merge, IDFT_R1, twiddle, store
     //      px = the partner thread's x[] (host emulation only)
@@ -511,31 +540,24 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             }
         }
     }
-    // roll back (src/lib.rs:499-500), truncate to N, dual window; one ola row per slice
+    // roll back (src/lib.rs:499-500), truncate to N, dual window -- all folded into the plan table
+    // itab[m] = (ola offset of y[2m], of y[2m+1], dual/M of both); dropped samples go to a dump slot
     VHD static void last_store(const PkInvCtx &c, int tid, const C2 (&r)[GPT][RL]) {
         const InvArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
-        const int ps = p.ps, N = p.N;
         float *row0 = c.ola + (size_t)l * p.ostride, *row1 = row0 + (size_t)LN * p.ostride;
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
             const int g = sub + NSUB * i;
             if (g < G) {
+                const ITab *tg = c.itab + g;
 #pragma unroll
                 for (int d = 0; d < RL; ++d) {
-                    const int m = g + G * d;
-                    const int j0 = (2 * m + ps) & (M - 1);
-                    const int j1 = (j0 + 1) & (M - 1);
-                    if (j0 < N) {
-                        const float dw = GEO::t1(c.dual + j0);
-                        row0[j0] = lo(r[i][d].x) * dw;
-                        row1[j0] = hi(r[i][d].x) * dw;
-                    }
-                    if (j1 < N) {
-                        const float dw = GEO::t1(c.dual + j1);
-                        row0[j1] = lo(r[i][d].y) * dw;
-                        row1[j1] = hi(r[i][d].y) * dw;
-                    }
+                    const ITab e = GEO::it4(tg + G * d);                     // sample pair m = g + G d
+                    row0[e.o0] = lo(r[i][d].x) * e.d0;
+                    row1[e.o0] = hi(r[i][d].x) * e.d0;
+                    row0[e.o1] = lo(r[i][d].y) * e.d1;
+                    row1[e.o1] = hi(r[i][d].y) * e.d1;
                 }
             }
         }
