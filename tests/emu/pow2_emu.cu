@@ -93,7 +93,7 @@ struct EmuPkFwd {
     int run() {
         using K = PkFwd<LOGMC, TF, NSUB>;
         std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
-        p2::pk_twiddle_fill(prm.M, twd.data());
+        p2::pk_twiddle_fill(prm.M, false, twd.data());
         std::vector<float> tw = conv<float>(twd);
         tw.resize(tw.size() + 8);
         std::vector<PTab> ptab((size_t)K::MC);
@@ -136,7 +136,7 @@ struct EmuPkInv {
     int run() {
         using K = PkInv<LOGMC, TF, NSUB>;
         std::vector<double> twd((size_t)p2::pk_twiddle_count(prm.M));
-        p2::pk_twiddle_fill(prm.M, twd.data());
+        p2::pk_twiddle_fill(prm.M, true, twd.data());
         const double sc = 1.0 / ((double)prm.M * (prm.mode >= 2 ? 1.0 : 2.0));
         std::vector<float> tw = conv<float>(twd);
         std::vector<double> ds(pl->dual);
@@ -145,7 +145,8 @@ struct EmuPkInv {
         pk_itab_fill(prm.M, prm.N, prm.ps, ds.data(), itab.data());
         PkInvCtx c;
         c.a = make_inv_args<float>(S, (float *)xo, prm, nullptr, tw.data(), TF);
-        c.a.ostride = pk_ostride(prm.N);
+        c.a.ostride = pk_ostride(prm.N, prm.ps);
+        c.a.pair = pk_pair(prm.N, prm.ps) ? 1 : 0;
         size_t elems = (size_t)K::MC * 2 * TF;
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<fl4> buf(elems / 4 + 4);

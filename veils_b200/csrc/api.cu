@@ -24,6 +24,7 @@ struct DeviceTables {
     void *dual_scaled = nullptr;
     void *tw_pow2 = nullptr;
     float *tw_pk = nullptr;
+    float *tw_pk_inv = nullptr;
     void *ptab_pk = nullptr;
     void *itab_pk = nullptr;
 };
@@ -97,8 +98,12 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
         }
         if (e == cudaSuccess && (pl.pk_fwd || pl.pk_inv)) {
             std::vector<double> tw((size_t)pk_twiddle_count(pl.M));
-            pk_twiddle_fill(pl.M, tw.data());
+            pk_twiddle_fill(pl.M, false, tw.data());
             e = upload_as<float>(tw, (void **)&d->tw_pk);
+            if (e == cudaSuccess) {
+                pk_twiddle_fill(pl.M, true, tw.data());
+                e = upload_as<float>(tw, (void **)&d->tw_pk_inv);
+            }
             if (e == cudaSuccess && pl.pk_fwd) {
                 std::vector<unsigned char> pt((size_t)(pl.M / 2) * 16);
                 pk_ptab_fill_host(pl.M, pl.N, pl.H, pl.ps, pl.win.data(), pt.data());
@@ -114,7 +119,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) {
-            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->ptab_pk);
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk);
             delete d;
             return cuda_fail(e, "upload plan tables");
         }
@@ -148,6 +153,7 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.dual_scaled = (const T *)pl.dev->dual_scaled;
     tb.tw_pow2 = (const T *)pl.dev->tw_pow2;
     tb.tw_pk = pl.dev->tw_pk;
+    tb.tw_pk_inv = pl.dev->tw_pk_inv;
     tb.ptab_pk = pl.dev->ptab_pk;
     tb.itab_pk = pl.dev->itab_pk;
     return tb;
@@ -193,6 +199,7 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->dual_scaled);
         cudaFree(p->pl.dev->tw_pow2);
         cudaFree(p->pl.dev->tw_pk);
+        cudaFree(p->pl.dev->tw_pk_inv);
         cudaFree(p->pl.dev->ptab_pk);
         cudaFree(p->pl.dev->itab_pk);
         delete p->pl.dev;

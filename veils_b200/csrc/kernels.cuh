@@ -37,7 +37,8 @@ struct Tables {
     const T *win_half = nullptr;        // [N] window / 2           (pow2 forward)
     const T *dual_scaled = nullptr;     // [N] dual / M or / (2M)   (pow2 inverse)
     const T *tw_pow2 = nullptr;         // pow2 twiddles (layout: pow2_cfg.hpp)
-    const float *tw_pk = nullptr;       // packed-f32 twiddles (layout: pow2_pk_cfg.hpp)
+    const float *tw_pk = nullptr;       // packed-f32 forward twiddles (layout: pow2_pk_cfg.hpp)
+    const float *tw_pk_inv = nullptr;   // packed-f32 inverse twiddles
     const void *ptab_pk = nullptr;      // packed-f32 tile table [M/2] x 16 bytes
     const void *itab_pk = nullptr;      // packed-f32 inverse table [M/2] x 16 bytes
 };
@@ -67,7 +68,7 @@ void pow2_twiddle_fill(int64_t M, double *re_im_pairs);
 // ---- packed f32 family: two slices per lane, FADD2/FFMA2 (pow2_pk.cu) ----------------------
 bool pk_supported(int64_t M, int64_t N, int64_t H, int64_t ps, bool inverse);
 int64_t pk_twiddle_count(int64_t M);
-void pk_twiddle_fill(int64_t M, double *re_im_pairs);
+void pk_twiddle_fill(int64_t M, bool inverse, double *entries4);
 // tile table (offset + window per sample pair), M/2 entries of 16 bytes, from the unscaled window
 // inverse table (overlap-row offsets + dual / M per sample pair) from the scaled dual window
 void pk_itab_fill_host(int64_t M, int64_t N, int64_t ps, const double *dual_scaled, void *out16);

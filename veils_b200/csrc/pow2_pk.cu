@@ -2,6 +2,8 @@
 // FADD2/FMUL2/FFMA2).  Phase code: pow2_pk_impl.cuh.  Persistent CTAs walk the (signal, tile)
 // list; plan tables live in shared memory and the signal tile is double-buffered with cp.async
 // for mfft <= 512.
+#include <cstdlib>
+
 #include "pow2_pk_cfg.hpp"
 
 namespace veils {
@@ -17,10 +19,11 @@ __device__ __forceinline__ void copy_table_f(float *dst, const float *src, int n
 template <int LOGMC, int TF>
 constexpr int pk_min_ctas() { return 8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
 
-template <int LOGMC, int TF, int NSUB>
+template <int LOGMC, int TF, int NSUB, bool ONES, bool SPEC>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
 pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restrict__ ptab_g,
-              const int64_t total, const int xin_elems, const int zero_off) {
+              const int64_t total, const int xin_elems, const int zero_off, const int stagger_ns,
+              const int num_sms) {
     extern __shared__ __align__(16) unsigned char smem[];
     using K = PkFwd<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -45,6 +48,9 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         xin1[zero_off + tid] = 0.f;
     }
     // (signal, tile) of work item w, advanced incrementally: w += gridDim.x
+    // co-resident CTAs (blockIdx differing by the SM count) would otherwise run their
+    // shared-memory-heavy and FP-heavy phases in lock step; a start offset interleaves them
+    if (stagger_ns > 0 && (int)blockIdx.x >= num_sms) __nanosleep((unsigned)stagger_ns);
     int64_t w = blockIdx.x;
     int64_t cb = w / args.ptiles, cpt = w - cb * args.ptiles;
     const int64_t gb = gridDim.x / args.ptiles, gr = gridDim.x - gb * args.ptiles;
@@ -89,14 +95,14 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         for (int i = 0; i < K::WPT; ++i) {
             C2 u[K::RL];
             K::last_dft(c, tid, i, u);
-            K::last_emit(c, tid, i, u, nullptr);
+            K::template last_emit_v<ONES, SPEC>(c, tid, i, u, nullptr);
         }
         cb = nb;
         cpt = npt;
     }
 }
 
-template <int LOGMC, int TF, int NSUB>
+template <int LOGMC, int TF, int NSUB, bool ONES>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
               const int64_t total, const int work_bytes) {
@@ -132,7 +138,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         for (int i = 0; i < K::WPT; ++i) {
             Raw x[K::R1];
             Raw xn;
-            K::p1_load(c, tid, i, x, xn);
+            K::template p1_load_v<ONES>(c, tid, i, x, xn);
             K::p1_rest(c, tid, i, x, xn, nullptr);
         }
         __syncthreads();
@@ -148,6 +154,17 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         K::gather(c, tid);
         __syncthreads();
     }
+}
+
+int pk_env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+int pk_num_sms();
+int pk_cta_cap(int per_sm) {
+    const char *e = getenv("VEILS_PK_CTAS_PER_SM");
+    if (e && atoi(e) > 0 && atoi(e) < per_sm) return atoi(e);
+    return per_sm;
 }
 
 int pk_num_sms() {
@@ -168,7 +185,10 @@ struct PkFwdLaunch {
         FwdArgs<float> a = make_fwd_args<float>(x, out, p, nullptr, tw, TF);
         const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
         const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
-        auto kern = pk_fwd_kernel<LOGMC, TF, NSUB>;
+        using KernT = void (*)(const FwdArgs<float>, const PTab *, const int64_t, const int, const int, const int, const int);
+        const bool ones = p.mode >= 2, spec = p.spectrogram != 0;
+        KernT kern = ones ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false>)
+                          : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -176,9 +196,9 @@ struct PkFwdLaunch {
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ptiles * p.batch;
-        const int64_t cap = (int64_t)per_sm * pk_num_sms();
+        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(
-            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF));
+            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms());
         ++g_launch_count;
         return cudaGetLastError();
     }
@@ -191,10 +211,12 @@ struct PkInvLaunch {
         const InvParams &p = *prm;
         if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
         InvArgs<float> a = make_inv_args<float>(S, xo, p, nullptr, tw, TF);
-        a.ostride = pk_ostride(p.N);
+        a.ostride = pk_ostride(p.N, p.ps);
+        a.pair = pk_pair(p.N, p.ps) ? 1 : 0;
         const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
         const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
-        auto kern = pk_inv_kernel<LOGMC, TF, NSUB>;
+        using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int);
+        KernT kern = p.mode >= 2 ? (KernT)pk_inv_kernel<LOGMC, TF, NSUB, true> : (KernT)pk_inv_kernel<LOGMC, TF, NSUB, false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -202,7 +224,7 @@ struct PkInvLaunch {
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ntiles * p.batch;
-        const int64_t cap = (int64_t)per_sm * pk_num_sms();
+        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes);
         ++g_launch_count;
         return cudaGetLastError();
@@ -223,7 +245,7 @@ void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double
     if (!p2::pk_cfg_for(M, &c)) return;
     p2::pk_ptab_fill(M, N, H, ps, win, c.tf, (p2::PTab *)out16);
 }
-void pk_twiddle_fill(int64_t M, double *t) { p2::pk_twiddle_fill(M, t); }
+void pk_twiddle_fill(int64_t M, bool inverse, double *t) { p2::pk_twiddle_fill(M, inverse, t); }
 
 cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st) {
     if (prm.P <= 0 || prm.batch <= 0) return cudaSuccess;
@@ -237,7 +259,7 @@ cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const 
     if (prm.batch <= 0 || prm.k1 <= prm.k0) return cudaSuccess;
     p2::Cfg c;
     if (!p2::pk_cfg_for(prm.M, &c)) return cudaErrorNotSupported;
-    PkInvLaunch l{S, x_out, &prm, (const ITab *)tb.itab_pk, tb.tw_pk, st};
+    PkInvLaunch l{S, x_out, &prm, (const ITab *)tb.itab_pk, tb.tw_pk_inv, st};
     return p2::pk_dispatch(c.logmc, l);
 }
 

@@ -23,32 +23,48 @@ inline int64_t pk_twiddle_count(int64_t M) {          // floats
     int np, r1, r2, r3;
     fac_of(c.logmc, &np, &r1, &r2, &r3);
     const int64_t mc = M / 2, l1 = mc / r1;
-    return 4 * (2 * mc + l1 + 1);
+    return 4 * (3 * mc + 2 * l1 + 1);
 }
-// entries (wr, wi, -wr, -wi): [tw1: W_Mc^(j c) at j*R1+c][tw2: W_L1^(j2 c2)][twp: W_M^k, k <= Mc]
-inline void pk_twiddle_fill(int64_t M, double *t) {
+// entries (wr, wi, -wr, -wi), w = product of unit roots exp(-2 pi i m / n):
+//   [tw1: MC  at j*R1+c ][tw2: L1 at j2*R2+c2][twp: W_M^k, k <= Mc][tw1x: MC][tw2x: L1]
+// forward table:  tw1[j][c] = W_Mc^(j c), times W_L1^(-j) for the reversed groups c > R1/2 of 2-pass
+//                 plans (PkGeo::rev_group); tw1x / tw2x unused (zero).
+// inverse table:  tw1[j][c] = W_Mc^(j c);  tw1x[j][k] = W_R1^k W_Mc^(j ((R1-k) mod R1)) for the
+//                 half-1 groups that run the IDFT on a reversed array (pow2_pk_impl.cuh p1_rest).
+inline void pk_twiddle_fill(int64_t M, bool inverse, double *t) {
     Cfg c;
     if (!pk_cfg_for(M, &c)) return;
     int np, r1, r2, r3;
     fac_of(c.logmc, &np, &r1, &r2, &r3);
     const int64_t mc = M / 2, l1 = mc / r1;
     double *p = t;
-    auto put = [&](int64_t m, int64_t n) {
-        double re, im;
-        tw_exact(m, n, &re, &im);
+    auto put2 = [&](int64_t m1, int64_t n1, int64_t m2, int64_t n2) {   // W_n1^m1 * W_n2^m2
+        double a, b, cr, ci;
+        tw_exact(m1, n1, &a, &b);
+        tw_exact(m2, n2, &cr, &ci);
+        const double re = a * cr - b * ci, im = a * ci + b * cr;
         p[0] = re; p[1] = im; p[2] = -re; p[3] = -im;
         p += 4;
     };
     for (int64_t j = 0; j < l1; ++j)
-        for (int64_t cc = 0; cc < r1; ++cc) put(j * cc, mc);
+        for (int64_t cc = 0; cc < r1; ++cc) {
+            const bool rev = !inverse && np == 2 && cc > r1 / 2;
+            put2(j * cc, mc, rev ? -j : 0, l1);
+        }
     if (np == 3) {
         const int64_t l2 = l1 / r2;
         for (int64_t j2 = 0; j2 < l2; ++j2)
-            for (int64_t cc = 0; cc < r2; ++cc) put(j2 * cc, l1);
+            for (int64_t cc = 0; cc < r2; ++cc) put2(j2 * cc, l1, 0, 1);
     } else {
-        for (int64_t i = 0; i < l1; ++i) put(0, 1);
+        for (int64_t i = 0; i < l1; ++i) put2(0, 1, 0, 1);
     }
-    for (int64_t k = 0; k <= mc; ++k) put(k, M);
+    for (int64_t k = 0; k <= mc; ++k) put2(k, M, 0, 1);
+    for (int64_t j = 0; j < l1; ++j)
+        for (int64_t k = 0; k < r1; ++k) {
+            if (inverse) put2(k, r1, j * ((r1 - k) % r1), mc);
+            else put2(0, 1, 0, 1);
+        }
+    for (int64_t i = 0; i < l1; ++i) put2(0, 1, 0, 1);
 }
 
 template <int LOGMC, int TF>
@@ -95,7 +111,13 @@ inline void pk_itab_fill(int64_t M, int64_t N, int64_t ps, const double *dual_sc
         t[m] = e;
     }
 }
-inline int pk_ostride(int64_t N) { return (int)((N + 1) | 1); }     // odd, > m_num (dump slot)
+// overlap-row stride: > m_num (dump slot); pairs: = 2 (mod 4) so the 8-byte stores of the 16 lanes
+// of a half-warp hit 32 distinct banks; otherwise odd (4-byte stores).
+inline bool pk_pair(int64_t N, int64_t ps) { return ps % 2 == 0 && N % 2 == 0; }
+inline int pk_ostride(int64_t N, int64_t ps) {
+    if (pk_pair(N, ps)) { int64_t s = N + 2; while (s % 4 != 2) ++s; return (int)s; }
+    return (int)((N + 1) | 1);
+}
 inline int pk_zero_off(int64_t N, int64_t H, int tf) {
     const TileLayout lay = tile_layout(H, true);
     const int64_t span = (int64_t)(tf - 1) * H + N;
@@ -106,7 +128,7 @@ template <int LOGMC, int TF>
 inline size_t pk_inv_work_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
     size_t work = 4 * (size_t)G::MC * 2 * TF;
-    const size_t ola = 4 * (size_t)TF * (size_t)pk_ostride(N);
+    const size_t ola = 4 * (size_t)TF * (size_t)(N + 6);
     if (ola > work) work = ola;
     return (work + 15) & ~(size_t)15;
 }

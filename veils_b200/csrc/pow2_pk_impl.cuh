@@ -40,8 +40,17 @@ struct PkGeo {
     static constexpr int L1 = MC / R1;
     static constexpr int L2 = (NP == 3) ? L1 / R2 : 1;
     static constexpr int G = MC / RL;
-    // twiddle table: entries of 4 floats (wr, wi, -wr, -wi): [tw1: MC][tw2: L1][twp: MC + 1]
-    static constexpr int TW1 = 0, TW2 = 4 * MC, TWP = 4 * (MC + L1), TWN = 4 * (2 * MC + L1 + 1);
+    // twiddle table: entries of 4 floats (wr, wi, -wr, -wi):
+    //   [tw1: MC][tw2: L1][twp: MC + 1][tw1x: MC][tw2x: L1]   (pow2_pk_cfg.hpp: separate forward and
+    //   inverse tables; the x-tables serve the "reversed" groups of the second warp halves)
+    static constexpr int TW1 = 0, TW2 = 4 * MC, TWP = 4 * (MC + L1), TW1X = 4 * (2 * MC + L1 + 1),
+                         TW2X = 4 * (3 * MC + L1 + 1), TWN = 4 * (3 * MC + 2 * L1 + 1);
+    // last-pass groups > G/2 are handled by the second halves (h = 1) of the warp row pairs: they
+    // need their DFT outputs in REVERSED order (their partner's u[d] mirrors their u[RL-1-d]).
+    // DFT(y)[e] = X[RL-1-e] for y[n] = x[(-n) mod RL] W_RL^n, so the producer pass stores such a
+    // group reversed and folds W_RL^(-j) into its twiddle: free at run time.
+    static constexpr bool REVG = (NP == 2);           // 2-pass plans: pass 1 reads the tile, no hazard
+    VHD static bool rev_group(int g) { return REVG && g > G / 2; }
     VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
     static constexpr bool STAB = LOGMC <= 8;          // plan tables in shared memory
     static constexpr bool DBUF = LOGMC <= 7;          // double-buffered signal tile
@@ -77,6 +86,15 @@ struct PkGeo {
     }
 };
 
+// Keeps a running pointer a running pointer: without it the compiler materialises all 16
+// addresses of an unrolled `p += step` chain up front and spills them.
+template <typename P> VHD void keep(P *&p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(p));
+#else
+    (void)p;
+#endif
+}
 using C2 = cx<f2>;
 VHD C2 c2zero() { C2 r; r.x = bc(0.f); r.y = bc(0.f); return r; }
 VHD C2 wload(const float *w, int TF) {
@@ -160,6 +178,19 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         const float *xb = p.x + c.b * p.x_pitch;
         if ((((c.b * p.x_pitch + s0) & 1) == 0) && ((p.n & 1) == 0) && ((((size_t)p.x) & 7) == 0)) {
             const int np = span >> 1, hp = H >> 1;
+            if (s0 >= 0 && s0 + span <= p.n && hp <= NT && NT % hp == 0) {
+                // interior tile, thread grid (NT/hp rows) x (hp pairs): purely incremental addressing
+                const int c2 = tid % hp, r0 = tid / hp, rstep = NT / hp;
+                float *dst = c.xin + r0 * hs + 2 * c2;
+                const float *src = xb + s0 + (int64_t)r0 * H + 2 * c2;
+                int e = tid;
+                for (; e < np; e += NT) {
+                    cp_async_zfill<8>(dst, src, true);
+                    dst += rstep * hs;
+                    src += rstep * H;
+                }
+                return;
+            }
             for (int e = tid; e < np; e += NT) {
                 const int64_t s = s0 + 2 * (int64_t)e;
                 const bool ok = s >= 0 && s < p.n;
@@ -195,16 +226,22 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             }
             Dft<R1, false, f2>::run(v);
             float *wj = c.work + (j * 2) * TF + 2 * l;
+            // 2-pass plans: column cc IS last-pass group cc; reversed groups are stored at row
+            // (L1 - j) mod L1 (the extra W_L1^(-j) is already in the forward tw1 table)
+            float *wr = c.work + (((L1 - j) & (L1 - 1)) * 2) * TF + 2 * l;
             const float *twj = c.tw + GEO::TW1 + 4 * j * R1;
             wstore(wj, TF, v[0]);
 #pragma unroll
             for (int cc = 1; cc < R1; ++cc) {
                 const fl4 t = GEO::tw4(twj + 4 * cc);
-                wstore(wj + (L1 * cc * 2) * TF, TF, cmulw(v[cc], bc(t.x), bc(t.y), bc(t.w)));
+                float *dst = GEO::rev_group(cc) ? wr : wj;
+                wstore(dst + (L1 * cc * 2) * TF, TF, cmulw(v[cc], bc(t.x), bc(t.y), bc(t.w)));
             }
         }
     }
 
+    // middle pass (3-pass plans), in place.  (The reversed-group trick is NOT applied here: a
+    // reversed store would land in a row another thread of the block still has to read.)
     VHD static void pass_mid(const PkFwdCtx &c, int tid) {
         if (NP != 3) return;
         const int l = tid % LN, sub = tid / LN;
@@ -317,8 +354,9 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             const int tstep = 4 * kstep;
 #pragma unroll
             for (int d = 0; d < RL; ++d) {
-                const C2 mine = h == 0 ? u[d] : u[RL - 1 - d];
-                const C2 rcv = xchg<LN>(mine, pu ? pu + (h == 0 ? RL - 1 - d : d) : nullptr, mask);
+                // REVG: half 1 already holds its group reversed (u[d] mirrors the partner's u[d])
+                const C2 mine = (GEO::REVG || h == 0) ? u[d] : u[RL - 1 - d];
+                const C2 rcv = xchg<LN>(mine, pu ? pu + ((GEO::REVG || h != 0) ? d : RL - 1 - d) : nullptr, mask);
                 emit1<MODE, SPEC, false>(p, o, q, k, GEO::tw4(tq), mine, rcv);
                 k += kstep;
                 q += qstep;
@@ -335,22 +373,27 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
                 emit2<MODE, SPEC>(p, twp, o, G / 2 + G * d, u[d], u[RL - 1 - d], true);
         }
     }
+    // kernel variants: ONES = one-sided layouts (modes 2, 3), SPEC = |X|^2 output.  Keeping the
+    // two-sided address arithmetic out of the one-sided kernels matters: the compiler hoists it.
+    template <bool ONES, bool SPEC>
+    VHD static void last_emit_v(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
+        const int mode = c.a.mode;
+        if (ONES) {
+            if (mode == 3) last_emit_t<3, SPEC>(c, tid, it, u, pu);
+            else last_emit_t<2, SPEC>(c, tid, it, u, pu);
+        } else {
+            if (mode == 1) last_emit_t<1, SPEC>(c, tid, it, u, pu);
+            else last_emit_t<0, SPEC>(c, tid, it, u, pu);
+        }
+    }
     VHD static void last_emit(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
-        if (p.spectrogram) {
-            switch (p.mode) {
-                case 0: last_emit_t<0, true>(c, tid, it, u, pu); break;
-                case 1: last_emit_t<1, true>(c, tid, it, u, pu); break;
-                case 2: last_emit_t<2, true>(c, tid, it, u, pu); break;
-                default: last_emit_t<3, true>(c, tid, it, u, pu); break;
-            }
+        if (p.mode >= 2) {
+            if (p.spectrogram) last_emit_v<true, true>(c, tid, it, u, pu);
+            else last_emit_v<true, false>(c, tid, it, u, pu);
         } else {
-            switch (p.mode) {
-                case 0: last_emit_t<0, false>(c, tid, it, u, pu); break;
-                case 1: last_emit_t<1, false>(c, tid, it, u, pu); break;
-                case 2: last_emit_t<2, false>(c, tid, it, u, pu); break;
-                default: last_emit_t<3, false>(c, tid, it, u, pu); break;
-            }
+            if (p.spectrogram) last_emit_v<false, true>(c, tid, it, u, pu);
+            else last_emit_v<false, false>(c, tid, it, u, pu);
         }
     }
 };
@@ -429,6 +472,8 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         in.sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * 8;
         return in;
     }
+    // Half 1 (h = 1) loads its group BACKWARDS: x[a] = X[jp + L1 (R1-1-a)], so that x[a] of the two
+    // halves are each other's mirror bins and no register selects are needed.
     template <int MODE>
     VHD static void p1_load_t(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
         const int l = tid % LN, sub = tid / LN;
@@ -436,12 +481,17 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         if (w >= L1 / 2) return;
         const In in = make_in(c, l);
         const int j = group_of(w, h);
-        const char *q = in.sb + j * in.rb;
-        const int64_t qstep = L1 * in.rb;
+        const bool rev = h != 0 && w != 0;
+        int k = rev ? j + L1 * (R1 - 1) : j;
+        const int kstep = rev ? -L1 : L1;
+        const char *q = in.sb + k * in.rb;
+        const int64_t qstep = kstep * in.rb;
 #pragma unroll
         for (int a = 0; a < R1; ++a) {
-            x[a] = load_bin<MODE>(c.a, in, q, j + L1 * a);
+            x[a] = load_bin<MODE>(c.a, in, q, k);
             q += qstep;
+            keep(q);
+            k += kstep;
         }
         xn = x[0];
         if (w == 0 && h == 0) {                                           // DC pairs with Nyquist;
@@ -450,16 +500,27 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             xn.i0 = xn.i1 = 0.f;
         }
     }
-    VHD static void p1_load(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
-        switch (c.a.mode) {
-            case 0: p1_load_t<0>(c, tid, it, x, xn); break;
-            case 1: p1_load_t<1>(c, tid, it, x, xn); break;
-            case 2: p1_load_t<2>(c, tid, it, x, xn); break;
-            default: p1_load_t<3>(c, tid, it, x, xn); break;
+    template <bool ONES>
+    VHD static void p1_load_v(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
+        const int mode = c.a.mode;
+        if (ONES) {
+            if (mode == 3) p1_load_t<3>(c, tid, it, x, xn);
+            else p1_load_t<2>(c, tid, it, x, xn);
+        } else {
+            if (mode == 1) p1_load_t<1>(c, tid, it, x, xn);
+            else p1_load_t<0>(c, tid, it, x, xn);
         }
+    }
+    VHD static void p1_load(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
+        if (c.a.mode >= 2) p1_load_v<true>(c, tid, it, x, xn);
+        else p1_load_v<false>(c, tid, it, x, xn);
     }
     // ---- pass 1, part 2: exchange, real-IFFT merge, IDFT_R1, twiddle, store
     //      px = the partner thread's x[] (host emulation only)
+    // Half 1 runs the SAME IDFT on its reversed array v~[a] = z[R1-1-a]:
+    //   IDFT(v~)[k] = w^(-k) Y[(-k) mod R1],  w = exp(+2 pi i / R1),
+    // so its local output k is the true output k' = (R1-k) mod R1 times w^k; the factor is folded
+    // into the tw1x table and the store goes to row block k' (per-thread pointer stride).
     VHD static void p1_rest(const PkInvCtx &c, int tid, int it, const Raw (&x)[R1], const Raw &xn, const Raw *px) {
         const int l = tid % LN, sub = tid / LN;
         const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
@@ -467,18 +528,16 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         const float *twp = c.tw + GEO::TWP;
         const int j = group_of(w, h);
         const unsigned mask = pair_mask<LN>(tid);
+        const bool rev = h != 0 && w != 0;
         C2 v[R1];
         if (w != 0) {
-            const float *tj = twp + 4 * j;
+            const float *tq = twp + 4 * (rev ? j + L1 * (R1 - 1) : j);
+            const int tstep = rev ? -4 * L1 : 4 * L1;
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
-                // bin j + L1 a of half 0 mirrors bin jp + L1 (R1-1-a) of half 1
-                const int al = a, ar = R1 - 1 - a;
-                const Raw mine = h == 0 ? x[al] : x[ar];
-                const Raw rcv = xchg_raw<LN>(mine, px ? px + (h == 0 ? ar : al) : nullptr, mask);
-                const int am = h == 0 ? al : ar;
-                const C2 z = merge1(GEO::tw4(tj + 4 * L1 * am), mine, rcv);
-                if (h == 0) v[al] = z; else v[ar] = z;
+                const Raw rcv = xchg_raw<LN>(x[a], px ? px + a : nullptr, mask);
+                v[a] = merge1(GEO::tw4(tq), x[a], rcv);
+                tq += tstep;
             }
         } else if (h == 0) {                                          // group 0: mirrors inside
             v[0].x = mk2(x[0].r0 + xn.r0, x[0].r1 + xn.r1);
@@ -498,12 +557,15 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         }
         Dft<R1, true, f2>::run(v);
         float *wj = c.work + (j * 2) * TF + 2 * l;
-        const float *twj = c.tw + GEO::TW1 + 4 * j * R1;
+        const float *twj = c.tw + (rev ? GEO::TW1X : GEO::TW1) + 4 * j * R1;
         wstore(wj, TF, v[0]);
+        float *wq = rev ? wj + (L1 * R1 * 2) * TF : wj;
+        const int wstep = rev ? -(L1 * 2) * TF : (L1 * 2) * TF;
 #pragma unroll
         for (int cc = 1; cc < R1; ++cc) {
+            wq += wstep;
             const fl4 t = GEO::tw4(twj + 4 * cc);
-            wstore(wj + (L1 * cc * 2) * TF, TF, cmulwc(v[cc], bc(t.x), bc(t.y), bc(t.w)));
+            wstore(wq, TF, cmulwc(v[cc], bc(t.x), bc(t.y), bc(t.w)));
         }
     }
 
@@ -543,6 +605,11 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     // roll back (src/lib.rs:499-500), truncate to N, dual window -- all folded into the plan table
     // itab[m] = (ola offset of y[2m], of y[2m+1], dual/M of both); dropped samples go to a dump slot
     VHD static void last_store(const PkInvCtx &c, int tid, const C2 (&r)[GPT][RL]) {
+        if (c.a.pair) last_store_t<true>(c, tid, r);
+        else last_store_t<false>(c, tid, r);
+    }
+    template <bool PAIR>
+    VHD static void last_store_t(const PkInvCtx &c, int tid, const C2 (&r)[GPT][RL]) {
         const InvArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
         float *row0 = c.ola + (size_t)l * p.ostride, *row1 = row0 + (size_t)LN * p.ostride;
@@ -554,10 +621,18 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
 #pragma unroll
                 for (int d = 0; d < RL; ++d) {
                     const ITab e = GEO::it4(tg + G * d);                     // sample pair m = g + G d
-                    row0[e.o0] = lo(r[i][d].x) * e.d0;
-                    row1[e.o0] = hi(r[i][d].x) * e.d0;
-                    row0[e.o1] = lo(r[i][d].y) * e.d1;
-                    row1[e.o1] = hi(r[i][d].y) * e.d1;
+                    if (PAIR) {                                              // y[2m], y[2m+1] adjacent, 8-byte aligned
+                        fl2 a, b;
+                        a.x = lo(r[i][d].x) * e.d0; a.y = lo(r[i][d].y) * e.d1;
+                        b.x = hi(r[i][d].x) * e.d0; b.y = hi(r[i][d].y) * e.d1;
+                        *reinterpret_cast<fl2 *>(row0 + e.o0) = a;
+                        *reinterpret_cast<fl2 *>(row1 + e.o0) = b;
+                    } else {
+                        row0[e.o0] = lo(r[i][d].x) * e.d0;
+                        row1[e.o0] = hi(r[i][d].x) * e.d0;
+                        row0[e.o1] = lo(r[i][d].y) * e.d1;
+                        row1[e.o1] = hi(r[i][d].y) * e.d1;
+                    }
                 }
             }
         }
@@ -575,6 +650,28 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         float *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
         const int ua = (int)(ka - base), ub = (int)(kb - base);
         const int cnt = (TF - halo) * H, hH = halo * H, step = p.ostride - H;
+        if (halo == 3 && N == 4 * H && p.pair && (H & 1) == 0 && ((((size_t)xo) & 7) == 0)) {
+            // 75 % overlap, even geometry: two samples per thread, 8-byte loads and stores
+            const bool inner = ua <= hH && ub >= cnt + hH;
+            for (int e = 2 * tid; e < cnt; e += 2 * NT) {
+                const int u = e + hH;
+                const int r = (int)mulhi_u32((unsigned)e, p.magic_h);
+                const int idx = r * p.ostride + (e - r * H) + hH;
+                const fl2 a0 = *reinterpret_cast<const fl2 *>(c.ola + idx);
+                const fl2 a1 = *reinterpret_cast<const fl2 *>(c.ola + idx + step);
+                const fl2 a2 = *reinterpret_cast<const fl2 *>(c.ola + idx + 2 * step);
+                const fl2 a3 = *reinterpret_cast<const fl2 *>(c.ola + idx + 3 * step);
+                fl2 o;
+                o.x = ((a0.x + a1.x) + a2.x) + a3.x;
+                o.y = ((a0.y + a1.y) + a2.y) + a3.y;
+                if (inner || (u >= ua && u + 1 < ub)) *reinterpret_cast<fl2 *>(xo + u) = o;
+                else {
+                    if (u >= ua && u < ub) xo[u] = o.x;
+                    if (u + 1 >= ua && u + 1 < ub) xo[u + 1] = o.y;
+                }
+            }
+            return;
+        }
         if (halo == 3 && N == 4 * H) {                       // 75 % overlap: fully unrolled
             for (int e = tid; e < cnt; e += NT) {
                 const int u = e + hH;

@@ -481,7 +481,8 @@ struct InvArgs {
     T rfac2x;                // 1 / fac2x for onesided2X, 1 otherwise
     unsigned magic_h;        // ceil(2^32 / H)
     int halo;                // ceil(N/H) - 1 leading slices recomputed for the overlap
-    int ostride;             // row stride of the overlap buffer (odd)
+    int ostride;             // row stride of the overlap buffer
+    int pair;                // packed family: rolled-back sample pairs are adjacent (ps, N even)
 };
 
 template <typename T>
