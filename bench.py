@@ -85,7 +85,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -204,7 +204,7 @@ def workload_config(cfg, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
@@ -371,10 +371,11 @@ def main():
         rows = max(threads, 8)
         _, _, _, t1, _ = cpu_reference_run(cfg, rows, threads, reps=2)
         rows = int(max(rows, min(B, rows * 12.0 / max(t1, 1e-3))))
-        xs, Sref, yref, dt, threads = cpu_reference_run(cfg, rows, threads, seed=77)
+        reps = int(max(1, min(10, round(10.0 / max(t1 * rows / max(threads, 8), 1e-3)))))
+        xs, Sref, yref, dt, threads = cpu_reference_run(cfg, rows, threads, seed=77, reps=reps)
         cpu = {"value": rows * n / dt / 1e6, "unit": "Msamples/s", "cores": threads, "kind": "port",
                "sample": f"{rows} of {B} rows, stft+istft in f64, C restatement of src/lib.rs "
-                         f"(oracle/stft_ref.c, OpenMP over rows)", "seconds": dt,
+                         f"(oracle/stft_ref.c, OpenMP over rows), best of {reps}", "seconds": dt,
                "host": {"nproc": os.cpu_count(), "cpu": cpu_model()}}
         # parity of the CUDA path on the same rows (first 8) against that CPU result
         r8 = min(8, rows)
