@@ -38,6 +38,7 @@ def build(force=False, verbose=False):
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("VEILS_EXTRA_NVCC_FLAGS", "").split()
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src + ".o")
         cmd = [_nvcc(), *flags, "-Xptxas", "-v", "-c", os.path.join(CSRC, src), "-o", obj]

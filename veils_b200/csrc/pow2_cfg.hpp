@@ -152,6 +152,7 @@ inline FwdArgs<T> make_fwd_args(const T *x, void *out, const FwdParams &p, const
     a.mode = p.mode;
     a.shift = p.mode == 1 ? (int)(p.M / 2) : 0;
     a.spectrogram = p.spectrogram;
+    a.dbg = 0;
     a.fac2x = p.mode == 3 ? (T)p.fac2x : (T)1;
     return a;
 }

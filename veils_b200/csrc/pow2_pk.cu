@@ -78,7 +78,11 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         c.b = cb;
         c.pt = cpt;
         c.xin = cur;
+#ifdef VEILS_ABLATE
+        if (!(args.dbg & 4)) K::pass1(c, tid);
+#else
         K::pass1(c, tid);
+#endif
         __syncthreads();
         if (!K::DBUF && wn < total) {
             PkFwdCtx cn = c;
@@ -94,6 +98,9 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
 #pragma unroll 1
         for (int i = 0; i < K::WPT; ++i) {
             C2 u[K::RL];
+#ifdef VEILS_ABLATE
+            if (args.dbg & 8) continue;
+#endif
             K::last_dft(c, tid, i, u);
             K::template last_emit_v<ONES, SPEC>(c, tid, i, u, nullptr);
         }
@@ -183,6 +190,7 @@ struct PkFwdLaunch {
     cudaError_t run() {
         const FwdParams &p = *prm;
         FwdArgs<float> a = make_fwd_args<float>(x, out, p, nullptr, tw, TF);
+        a.dbg = pk_env_int("VEILS_PK_DBG", 0);
         const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
         const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
         using KernT = void (*)(const FwdArgs<float>, const PTab *, const int64_t, const int, const int, const int, const int);

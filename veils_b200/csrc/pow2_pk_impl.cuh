@@ -266,9 +266,13 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         char *ob;            // byte pointer of (row 0, column of slice l)
         int64_t rb;          // row pitch in bytes
         bool live0, live1;   // slice l / l + LN inside [0, P)
+        int dbg;
     };
     template <bool SPEC>
     VHD static void put_at(const Out &o, char *q, float r0, float i0, float r1, float i1) {
+#ifdef VEILS_ABLATE
+        if ((o.dbg & 1) && r0 != 12345.678f) return;      // ablation: no global stores
+#endif
         if (SPEC) {
             if (o.live0) *reinterpret_cast<float *>(q) = r0 * r0 + i0 * i0;
             if (o.live1) *reinterpret_cast<float *>(q + 4 * LN) = r1 * r1 + i1 * i1;
@@ -340,6 +344,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         o.live1 = pl + LN < p.P;
         o.rb = p.ldp * esz;
         o.ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+        o.dbg = p.dbg;
         const float *twp = c.tw + GEO::TWP;
         const int g = group_of(w, h);
         const unsigned mask = pair_mask<LN>(tid);
@@ -356,21 +361,29 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             for (int d = 0; d < RL; ++d) {
                 // REVG: half 1 already holds its group reversed (u[d] mirrors the partner's u[d])
                 const C2 mine = (GEO::REVG || h == 0) ? u[d] : u[RL - 1 - d];
+#ifdef VEILS_ABLATE
+                const C2 rcv = (p.dbg & 2) ? mine : xchg<LN>(mine, nullptr, mask);   // ablation: no shuffles
+#else
                 const C2 rcv = xchg<LN>(mine, pu ? pu + ((GEO::REVG || h != 0) ? d : RL - 1 - d) : nullptr, mask);
+#endif
                 emit1<MODE, SPEC, false>(p, o, q, k, GEO::tw4(tq), mine, rcv);
                 k += kstep;
                 q += qstep;
                 tq += tstep;
             }
-        } else if (h == 0) {                                         // group 0: mirrors inside
-            emit2<MODE, SPEC>(p, twp, o, 0, u[0], u[0], true);      // X[0], X[Mc]
+        } else {
+            // self-mirrored groups: half 0 holds group 0 (u[d] <-> u[(RL-d) mod RL]), half 1 group G/2
+            // (u[d] <-> u[RL-1-d]).  One instruction stream for both halves (the mirror operand is a
+            // register select), two outputs per pair -- same amount of work as the other warps, which
+            // would otherwise wait at the next barrier for a warp running two code paths in turn.
 #pragma unroll
-            for (int d = 1; d < RL / 2; ++d) emit2<MODE, SPEC>(p, twp, o, G * d, u[d], u[RL - d], true);
-            emit2<MODE, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
-        } else {                                                     // group G/2: mirrors inside
-#pragma unroll
-            for (int d = 0; d < RL / 2; ++d)
-                emit2<MODE, SPEC>(p, twp, o, G / 2 + G * d, u[d], u[RL - 1 - d], true);
+            for (int t = 0; t < RL / 2; ++t) {
+                const C2 a = u[t];
+                const C2 bm = h == 0 ? u[(RL - t) & (RL - 1)] : u[RL - 1 - t];
+                const int k = h == 0 ? G * t : G / 2 + G * t;
+                emit2<MODE, SPEC>(p, twp, o, k, a, bm, true);      // t = 0, h = 0: X[0] and X[Mc]
+            }
+            if (h == 0) emit2<MODE, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
         }
     }
     // kernel variants: ONES = one-sided layouts (modes 2, 3), SPEC = |X|^2 output.  Keeping the

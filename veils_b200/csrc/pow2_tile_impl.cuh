@@ -265,6 +265,7 @@ struct FwdArgs {
     int mode;                // Mode
     int shift;               // centered: Mc (fftshift), else 0
     int spectrogram;         // 1: |X|^2 real output
+    int dbg;                 // ablation mask (VEILS_ABLATE builds only)
     T fac2x;                 // onesided2X factor, 1 otherwise
 };
 
