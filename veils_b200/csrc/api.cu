@@ -181,7 +181,10 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         pl.pow2_fwd = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, false);
         pl.pow2_inv = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, true);
         const bool no_pk = getenv("VEILS_NO_PACKED") != nullptr;
-        pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
+        // measured on B200 (profiles/r1_config_sweep.txt): the packed forward wins for 2-pass plans
+        // (mfft <= 512); for the 3-pass plans its 255-register build loses to the scalar family
+        pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && (pl.M <= 512 || !pl.pow2_fwd) &&
+                    pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
         pl.pk_inv = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, true);
     }
     *out = p;
