@@ -206,7 +206,8 @@ def workload_config(cfg, name):
     return {"workload": f"{name}: batch {cfg['batch']} x {cfg['n']} samples @ {cfg['fs']:.0f} Hz, "
                         f"{cfg['win']} {cfg['m']} / hop {cfg['hop']}, {cfg['mode']}, {cfg['prec']}, stft+istft",
             "batch": cfg["batch"], "n": cfg["n"], "m_num": cfg["m"], "hop": cfg["hop"],
-            "fft_mode": cfg["mode"], "l2_policy": "working set (input + S) >> 126 MB L2, no flush needed"}
+            "fft_mode": cfg["mode"], "l2_policy": "working set (input + S) >> 126 MB L2, no flush needed",
+            "s_row_pitch": "rows padded to 32-byte sectors (ldp = ceil(P/4)*4 for f32); --dense-pitch for ldp = P"}
 
 
 def main():
@@ -219,6 +220,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the batch size (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--dense-pitch", action="store_true", help="S row pitch ldp = P (reference-dense)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -255,17 +257,21 @@ def main():
     k0, k1 = st.istft_range(P)
     n_out = k1 - k0
     cdt = torch.complex64 if cfg["prec"] == "f32" else torch.complex128
-    S = torch.empty((B, F, P), dtype=cdt, device=dev)
+    # row pitch of S: sector-aligned rows (what StandaloneSTFT.stft allocates for device tensors);
+    # --dense-pitch times the reference-dense layout ldp = P instead
+    ldp = P if args.dense_pitch else -(-P // st.pitch_align) * st.pitch_align
+    S = torch.empty((B, F, ldp), dtype=cdt, device=dev)
     y = torch.empty((B, n_out), dtype=x.dtype, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
-    import ctypes as C
 
-    def fwd():
-        rc = L.veils_stft_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), P, stream)
+    def fwd(Sbuf=None, pitch=None):
+        Sb, lp = (S, ldp) if Sbuf is None else (Sbuf, pitch)
+        rc = L.veils_stft_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, Sb.data_ptr(), lp, stream)
         assert rc == 0, L.veils_last_error()
 
-    def inv():
-        rc = L.veils_istft_dev(st._h, S.data_ptr(), P, B, P, None, None, y.data_ptr(), n_out, stream)
+    def inv(Sbuf=None, pitch=None):
+        Sb, lp = (S, ldp) if Sbuf is None else (Sbuf, pitch)
+        rc = L.veils_istft_dev(st._h, Sb.data_ptr(), P, B, lp, None, None, y.data_ptr(), n_out, stream)
         assert rc == 0, L.veils_last_error()
 
     def step():
@@ -327,7 +333,14 @@ def main():
             "peak_source": peak_src, "bytes_per_launch": dom[2], "ms_per_launch": dom[1],
             "stft": {"ms": ms_f, "GBps": bytes_f / (ms_f * 1e-3) / 1e9, "frac": bytes_f / (ms_f * 1e-3) / 1e9 / peak},
             "istft": {"ms": ms_i, "GBps": bytes_i / (ms_i * 1e-3) / 1e9, "frac": bytes_i / (ms_i * 1e-3) / 1e9 / peak},
-            "roundtrip_frac": (bytes_f + bytes_i) / (ms_step * 1e-3) / 1e9 / peak}
+            "roundtrip_frac": (bytes_f + bytes_i) / (ms_step * 1e-3) / 1e9 / peak, "ldp": ldp}
+    if ldp != P:                                   # the same kernels on the dense layout, for the record
+        Sd = torch.empty((B, F, P), dtype=cdt, device=dev)
+        ms_fd, ms_id = time_kernel(lambda: fwd(Sd, P), reps), time_kernel(lambda: inv(Sd, P), reps)
+        roof["dense_pitch"] = {"ldp": P, "stft_ms": ms_fd, "istft_ms": ms_id,
+                               "stft_frac": bytes_f / (ms_fd * 1e-3) / 1e9 / peak,
+                               "istft_frac": bytes_i / (ms_id * 1e-3) / 1e9 / peak}
+        del Sd
 
     # ---- e2e: host (pinned) -> device -> stft -> istft -> host (pinned), public tensor API ----
     e2e = None

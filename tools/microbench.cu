@@ -120,6 +120,29 @@ __global__ void tile_store(float *S, int F, int P, int ldp, int ptiles) {
         }
     }
 }
+// the packed kernels' store shapes for a tile of 32 slices: half-warp (16 lanes) per row, 2 rows per
+// instruction.  PAIR = 0: lane l holds slices (l, l+16): two 8-byte stores, 128-byte runs each;
+// PAIR = 1: lane l holds slices (2l, 2l+1): one 16-byte store (two 8-byte ones if misaligned), 256-byte runs.
+template <int PAIR>
+__global__ void tile_store_hw(float *S, int F, int P, int ldp, int ptiles) {
+    const int b = blockIdx.x / ptiles, pt = blockIdx.x % ptiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int l = lane & 15, sub = lane >> 4;
+    float val = (float)(threadIdx.x + blockIdx.x);
+    for (int k = warp * 2 + sub; k < F; k += nw * 2) {
+        float *row = S + (((size_t)b * F + k) * ldp + pt * 32) * 2;
+        if (PAIR == 0) {
+            if (pt * 32 + l < P) *(float2 *)(row + 2 * l) = make_float2(val, val + k);
+            if (pt * 32 + l + 16 < P) *(float2 *)(row + 2 * (l + 16)) = make_float2(val, val - k);
+        } else {
+            float *dst = row + 4 * l;
+            if (pt * 32 + 2 * l + 1 < P) {
+                if ((((size_t)dst) & 15) == 0) *(float4 *)dst = make_float4(val, val + k, val, val - k);
+                else { *(float2 *)dst = make_float2(val, val + k); *(float2 *)(dst + 2) = make_float2(val, val - k); }
+            } else if (pt * 32 + 2 * l < P) *(float2 *)dst = make_float2(val, val + k);
+        }
+    }
+}
 template <int T>
 __global__ void tile_load(const float *S, float *sink, int F, int P, int ldp, int ptiles) {
     constexpr int LPR = T;
@@ -230,6 +253,13 @@ int main() {
             run_store<16, 2>("tile_store", S, B, F, P, ldp);
             run_store<32, 2>("tile_store", S, B, F, P, ldp);
             run_store<64, 4>("tile_store", S, B, F, P, ldp);
+        }
+        for (int ldp : {1253, 1254, 1256}) {
+            const int ptiles = (P + 31) / 32;
+            float ms = time_ms([&] { tile_store_hw<0><<<B * ptiles, 256>>>(S, F, P, ldp, ptiles); });
+            printf("tile_store_hw pair(l,l+16) 2x8B ldp=%d  %.1f GB/s\n", ldp, (double)B * F * P * 8 / ms / 1e6);
+            ms = time_ms([&] { tile_store_hw<1><<<B * ptiles, 256>>>(S, F, P, ldp, ptiles); });
+            printf("tile_store_hw pair(2l,2l+1) 16B ldp=%d  %.1f GB/s\n", ldp, (double)B * F * P * 8 / ms / 1e6);
         }
         for (int ldp : {1253, 1256}) {
             run_load<8>("tile_load", S, out, B, F, P, ldp);
