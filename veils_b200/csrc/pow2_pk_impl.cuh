@@ -435,8 +435,15 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         int64_t rb;
         bool live0, live1;
     };
+    template <bool FULL>
     VHD static Raw get_at(const In &in, const char *q) {
         Raw r;
+        if (FULL) {                                  // both slices inside [q0, q1): no predication
+            const fl2 a = *reinterpret_cast<const fl2 *>(q);
+            const fl2 b = *reinterpret_cast<const fl2 *>(q + 8 * LN);
+            r.r0 = a.x; r.i0 = a.y; r.r1 = b.x; r.i1 = b.y;
+            return r;
+        }
         r.r0 = r.i0 = r.r1 = r.i1 = 0.f;
         if (in.live0) { const fl2 v = *reinterpret_cast<const fl2 *>(q); r.r0 = v.x; r.i0 = v.y; }
         if (in.live1) { const fl2 v = *reinterpret_cast<const fl2 *>(q + 8 * LN); r.r1 = v.x; r.i1 = v.y; }
@@ -444,18 +451,18 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     }
     // Hermitian one-sided bin k (src/lib.rs:414-487); two-sided layouts: S[k] + conj(S[M-k]).
     // q: byte pointer of row k (one-sided layouts).  Im(DC), Im(Nyquist) are cleared by the caller.
-    template <int MODE>
+    template <int MODE, bool FULL>
     VHD static Raw load_bin(const InvArgs<float> &p, const In &in, const char *q, int k) {
         Raw v;
         if (MODE >= 2) {
-            v = get_at(in, q);
+            v = get_at<FULL>(in, q);
             if (MODE == 3 && k >= 1 && k <= MC - 1) {
                 v.r0 *= p.rfac2x; v.i0 *= p.rfac2x; v.r1 *= p.rfac2x; v.i1 *= p.rfac2x;
             }
         } else {
             const int sh = MODE == 1 ? MC : 0;                                // ifftshift :516-521
-            const Raw a = get_at(in, in.sb + ((k + sh) & (M - 1)) * in.rb);
-            const Raw bq = get_at(in, in.sb + ((M - k + sh) & (M - 1)) * in.rb);
+            const Raw a = get_at<FULL>(in, in.sb + ((k + sh) & (M - 1)) * in.rb);
+            const Raw bq = get_at<FULL>(in, in.sb + ((M - k + sh) & (M - 1)) * in.rb);
             v.r0 = a.r0 + bq.r0; v.i0 = a.i0 - bq.i0; v.r1 = a.r1 + bq.r1; v.i1 = a.i1 - bq.i1;
         }
         return v;
@@ -490,9 +497,16 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     template <int MODE>
     VHD static void p1_load_t(const PkInvCtx &c, int tid, int it, Raw (&x)[R1], Raw &xn) {
         const int l = tid % LN, sub = tid / LN;
-        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
+        const int w = (sub >> 1) + it * (NSUB / 2);
         if (w >= L1 / 2) return;
         const In in = make_in(c, l);
+        if (in.live0 && in.live1) p1_load_f<MODE, true>(c, tid, it, in, x, xn);
+        else p1_load_f<MODE, false>(c, tid, it, in, x, xn);
+    }
+    template <int MODE, bool FULL>
+    VHD static void p1_load_f(const PkInvCtx &c, int tid, int it, const In &in, Raw (&x)[R1], Raw &xn) {
+        const int sub = tid / LN;
+        const int w = (sub >> 1) + it * (NSUB / 2), h = sub & 1;
         const int j = group_of(w, h);
         const bool rev = h != 0 && w != 0;
         int k = rev ? j + L1 * (R1 - 1) : j;
@@ -501,14 +515,14 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         const int64_t qstep = kstep * in.rb;
 #pragma unroll
         for (int a = 0; a < R1; ++a) {
-            x[a] = load_bin<MODE>(c.a, in, q, k);
+            x[a] = load_bin<MODE, FULL>(c.a, in, q, k);
             q += qstep;
             keep(q);
             k += kstep;
         }
         xn = x[0];
         if (w == 0 && h == 0) {                                           // DC pairs with Nyquist;
-            xn = load_bin<MODE>(c.a, in, in.sb + MC * in.rb, MC);         // irfft ignores their Im
+            xn = load_bin<MODE, FULL>(c.a, in, in.sb + MC * in.rb, MC);   // irfft ignores their Im
             x[0].i0 = x[0].i1 = 0.f;
             xn.i0 = xn.i1 = 0.f;
         }
@@ -552,21 +566,31 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
                 v[a] = merge1(GEO::tw4(tq), x[a], rcv);
                 tq += tstep;
             }
-        } else if (h == 0) {                                          // group 0: mirrors inside
-            v[0].x = mk2(x[0].r0 + xn.r0, x[0].r1 + xn.r1);
-            v[0].y = mk2(x[0].r0 - xn.r0, x[0].r1 - xn.r1);
+        } else {
+            // self-mirrored groups: half 0 holds group 0 (x[a] <-> x[(R1-a) mod R1], DC <-> Nyquist), half 1
+            // group L1/2 (x[a] <-> x[R1-1-a]).  One instruction stream: the mirror operand and the slot of
+            // the mirrored result are register selects (cheaper than running the two paths in turn while
+            // the seven other warps wait at the barrier).
+            C2 m[R1 / 2];
 #pragma unroll
-            for (int a = 1; a < R1 / 2; ++a) {
-                v[a] = merge1(GEO::tw4(twp + 4 * L1 * a), x[a], x[R1 - a]);
-                v[R1 - a] = merge1(GEO::tw4(twp + 4 * L1 * (R1 - a)), x[R1 - a], x[a]);
+            for (int t = 0; t < R1 / 2; ++t) {
+                const Raw b = h == 0 ? (t == 0 ? xn : x[R1 - t]) : x[R1 - 1 - t];
+                const int k = h == 0 ? L1 * t : j + L1 * t;
+                v[t] = merge1(GEO::tw4(twp + 4 * k), x[t], b);
+                m[t] = merge1(GEO::tw4(twp + 4 * (MC - k)), b, x[t]);             // Z'[Mc - k]
             }
-            v[R1 / 2] = merge1(GEO::tw4(twp + 4 * (MC / 2)), x[R1 / 2], x[R1 / 2]);
-        } else {                                                      // group L1/2
+            if (h == 0) {
+                // k = 0: Z'[0] = (X0 + XN) + i (X0 - XN) with real X0, XN (imag parts cleared on load)
+                v[0].x = mk2(x[0].r0 + xn.r0, x[0].r1 + xn.r1);
+                v[0].y = mk2(x[0].r0 - xn.r0, x[0].r1 - xn.r1);
+                v[R1 / 2] = merge1(GEO::tw4(twp + 4 * (MC / 2)), x[R1 / 2], x[R1 / 2]);
+            }
 #pragma unroll
-            for (int a = 0; a < R1 / 2; ++a) {
-                v[a] = merge1(GEO::tw4(twp + 4 * (j + L1 * a)), x[a], x[R1 - 1 - a]);
-                v[R1 - 1 - a] = merge1(GEO::tw4(twp + 4 * (j + L1 * (R1 - 1 - a))), x[R1 - 1 - a], x[a]);
+            for (int t = 0; t < R1 / 2; ++t) {
+                // half 0: mirror of bin L1 t is element R1 - t (t >= 1); half 1: element R1 - 1 - t
+                if (t >= 1) v[R1 - t] = h == 0 ? m[t] : (t == 1 ? m[0] : m[t - 1]);
             }
+            if (h != 0) v[R1 / 2] = m[R1 / 2 - 1];
         }
         Dft<R1, true, f2>::run(v);
         float *wj = c.work + (j * 2) * TF + 2 * l;
