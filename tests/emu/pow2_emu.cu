@@ -18,6 +18,7 @@ using namespace veils::p2;
 namespace veils { std::atomic<unsigned long long> g_launch_count{0}; }
 
 static thread_local std::string e_err;
+static int64_t emu_grid_hint = 2;   // small -> several tiles per chunk even for short test signals
 
 template <typename T>
 static std::vector<T> conv(const std::vector<double> &s, double scale = 1.0) {
@@ -151,38 +152,53 @@ struct EmuPkInv {
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<fl4> buf(elems / 4 + 4);
         c.work = (float *)buf.data(); c.ola = (float *)buf.data(); c.tw = tw.data(); c.itab = itab.data();
-        const int own = TF - c.a.halo;
         std::vector<C2> regs((size_t)K::NT * K::GPT * K::RL);
         std::vector<Raw> raws((size_t)K::NT * (K::R1 + 1));
-        for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
-            c.b = blk / c.a.ntiles; c.qa = c.a.qa0 + (blk % c.a.ntiles) * own;
-            for (int i = 0; i < K::WPT; ++i) {
-                for (int t = 0; t < K::NT; ++t) {
-                    Raw xr[K::R1]; Raw xn;
-                    std::memset(xr, 0, sizeof(xr)); std::memset(&xn, 0, sizeof(xn));
-                    K::p1_load(c, t, i, xr, xn);
-                    std::memcpy(&raws[(size_t)t * (K::R1 + 1)], xr, sizeof(xr));
-                    raws[(size_t)t * (K::R1 + 1) + K::R1] = xn;
+        std::vector<float> carry0((size_t)prm.N + 4), carry1((size_t)prm.N + 4);
+        pk_inv_chunks(c.a, prm, TF, prm.batch, emu_grid_hint);
+        const int64_t lc = (int64_t)TF * c.a.chunk_tiles - c.a.halo;
+        for (int64_t ch = 0; ch < c.a.cps * prm.batch; ++ch) {
+            c.b = ch / c.a.cps;
+            const int64_t a0 = c.a.qh0 + (ch - c.b * c.a.cps) * lc;
+            int flip = 0;
+            // poison the carries: a chunk must never read what another chunk left behind
+            for (auto &v : carry0) v = std::nanf("");
+            for (auto &v : carry1) v = std::nanf("");
+            for (int t = 0; t < c.a.chunk_tiles; ++t) {
+                c.qa = a0 - c.a.halo + (int64_t)t * TF;
+                if (c.qa > c.a.qh1) break;
+                c.first = t == 0;
+                c.carry_in = flip ? carry1.data() : carry0.data();
+                c.carry_out = flip ? carry0.data() : carry1.data();
+                flip ^= 1;
+                for (int i = 0; i < K::WPT; ++i) {
+                    for (int tt = 0; tt < K::NT; ++tt) {
+                        Raw xr[K::R1]; Raw xn;
+                        std::memset(xr, 0, sizeof(xr)); std::memset(&xn, 0, sizeof(xn));
+                        K::p1_load(c, tt, i, xr, xn);
+                        std::memcpy(&raws[(size_t)tt * (K::R1 + 1)], xr, sizeof(xr));
+                        raws[(size_t)tt * (K::R1 + 1) + K::R1] = xn;
+                    }
+                    for (int tt = 0; tt < K::NT; ++tt) {
+                        Raw xr[K::R1];
+                        std::memcpy(xr, &raws[(size_t)tt * (K::R1 + 1)], sizeof(xr));
+                        K::p1_rest(c, tt, i, xr, raws[(size_t)tt * (K::R1 + 1) + K::R1],
+                                   &raws[(size_t)(tt ^ K::LN) * (K::R1 + 1)]);
+                    }
                 }
-                for (int t = 0; t < K::NT; ++t) {
-                    Raw xr[K::R1];
-                    std::memcpy(xr, &raws[(size_t)t * (K::R1 + 1)], sizeof(xr));
-                    K::p1_rest(c, t, i, xr, raws[(size_t)t * (K::R1 + 1) + K::R1],
-                               &raws[(size_t)(t ^ K::LN) * (K::R1 + 1)]);
+                for (int tt = 0; tt < K::NT; ++tt) K::pass_mid(c, tt);
+                for (int tt = 0; tt < K::NT; ++tt) {
+                    C2 r[K::GPT][K::RL];
+                    K::last_load(c, tt, r);
+                    std::memcpy(&regs[(size_t)tt * K::GPT * K::RL], r, sizeof(r));
                 }
+                for (int tt = 0; tt < K::NT; ++tt) {
+                    C2 r[K::GPT][K::RL];
+                    std::memcpy(r, &regs[(size_t)tt * K::GPT * K::RL], sizeof(r));
+                    K::last_store(c, tt, r);
+                }
+                for (int tt = 0; tt < K::NT; ++tt) K::gather(c, tt);
             }
-            for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
-            for (int t = 0; t < K::NT; ++t) {
-                C2 r[K::GPT][K::RL];
-                K::last_load(c, t, r);
-                std::memcpy(&regs[(size_t)t * K::GPT * K::RL], r, sizeof(r));
-            }
-            for (int t = 0; t < K::NT; ++t) {
-                C2 r[K::GPT][K::RL];
-                std::memcpy(r, &regs[(size_t)t * K::GPT * K::RL], sizeof(r));
-                K::last_store(c, t, r);
-            }
-            for (int t = 0; t < K::NT; ++t) K::gather(c, t);
         }
         return 0;
     }

@@ -143,3 +143,23 @@ def test_emulated_packed_kernels_match_oracle(emu, case):
         k0, k1 = H + 3, 2 * N + 5
         y2 = emu_istft(emu, o, 0, Sref, k0, k1, family=1)
         assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= 1e-5
+
+
+@pytest.mark.parametrize("M,N,H,n", [(64, 64, 16, 5000), (512, 512, 128, 30000), (256, 200, 50, 9000),
+                                     (128, 128, 64, 6000), (64, 64, 64, 3000), (1024, 1024, 256, 40000)])
+def test_emulated_packed_inverse_streaming_overlap_add(emu, M, N, H, n):
+    """Long signals: several chunks of several tiles each -> the carried overlap tails, the chunk
+    starts (halo re-computation) and clipped (k0, k1) ranges of the packed inverse."""
+    rng = np.random.default_rng(M + H)
+    win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(N) / N)) + 0.02
+    o = mk(win, H, fft_mode="onesided", mfft=M)
+    x = rng.uniform(-1, 1, (2, n)).astype(np.float32).astype(np.float64)
+    Sref = np.stack([o.stft(r) for r in x])
+    y = emu_istft(emu, o, 0, Sref, family=1)
+    assert y is not None and not np.isnan(y).any()
+    assert rel_err(y, np.stack([o.istft(s) for s in Sref])) <= 1e-5
+    assert np.max(np.abs(y[:, :n] - x)) <= 2e-5
+    k0, k1 = 3 * H + 5, n - 2 * H - 7
+    y2 = emu_istft(emu, o, 0, Sref, k0, k1, family=1)
+    assert not np.isnan(y2).any()
+    assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= 1e-5

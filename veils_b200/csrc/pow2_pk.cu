@@ -120,8 +120,11 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
     c.ola = reinterpret_cast<float *>(smem);
+    float *carry0 = reinterpret_cast<float *>(smem + work_bytes);
+    const int carry_elems = (args.N + 3) & ~3;
+    float *carry1 = carry0 + carry_elems;
     if (K::STAB) {
-        float *stw = reinterpret_cast<float *>(smem + work_bytes);
+        float *stw = carry1 + carry_elems;
         ITab *sitab = reinterpret_cast<ITab *>(stw + K::TWN);
         copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
         copy_table_f(reinterpret_cast<float *>(sitab), reinterpret_cast<const float *>(itab_g), 4 * K::MC, tid, K::NT);
@@ -132,34 +135,43 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         c.itab = itab_g;
     }
     __syncthreads();
-    const int own = TF - args.halo;
-    int64_t cb = blockIdx.x / args.ntiles, ct = blockIdx.x - cb * args.ntiles;
-    const int64_t gb = gridDim.x / args.ntiles, gr = gridDim.x - gb * args.ntiles;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        c.b = cb;
-        c.qa = args.qa0 + ct * own;
-        cb += gb;
-        ct += gr;
-        if (ct >= args.ntiles) { ct -= args.ntiles; ++cb; }
+    // A CTA walks the tiles of one chunk of one signal in order (streaming overlap-add): only the
+    // first tile of a chunk re-computes the halo slices, every other tile owns all TF slices.
+    const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
+    for (int64_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        c.b = ch / args.cps;
+        const int64_t a0 = args.qh0 + (ch - c.b * args.cps) * lc;      // first owned slice
+        int flip = 0;
 #pragma unroll 1
-        for (int i = 0; i < K::WPT; ++i) {
-            Raw x[K::R1];
-            Raw xn;
-            K::template p1_load_v<ONES>(c, tid, i, x, xn);
-            K::p1_rest(c, tid, i, x, xn, nullptr);
-        }
-        __syncthreads();
-        if (K::NP == 3) {
-            K::pass_mid(c, tid);
+        for (int t = 0; t < args.chunk_tiles; ++t) {
+            c.qa = a0 - args.halo + (int64_t)t * TF;
+            if (c.qa > args.qh1) break;
+            c.first = t == 0;
+            c.carry_in = flip ? carry1 : carry0;
+            c.carry_out = flip ? carry0 : carry1;
+            flip ^= 1;
+#pragma unroll 1
+            for (int i = 0; i < K::WPT; ++i) {
+                Raw x[K::R1];
+                Raw xn;
+                K::template p1_load_v<ONES>(c, tid, i, x, xn);
+                K::p1_rest(c, tid, i, x, xn, nullptr);
+            }
             __syncthreads();
+            if (K::NP == 3) {
+                K::pass_mid(c, tid);
+                __syncthreads();
+            }
+            {
+                C2 r[K::GPT][K::RL];
+                K::last_load(c, tid, r);
+                __syncthreads();               // all reads of `work` done before it becomes `ola`
+                K::last_store(c, tid, r);
+            }
+            __syncthreads();
+            K::gather(c, tid);
+            __syncthreads();                   // `ola` consumed before the next tile overwrites `work`
         }
-        C2 r[K::GPT][K::RL];
-        K::last_load(c, tid, r);
-        __syncthreads();
-        K::last_store(c, tid, r);
-        __syncthreads();
-        K::gather(c, tid);
-        __syncthreads();
     }
 }
 
@@ -231,8 +243,9 @@ struct PkInvLaunch {
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
-        const int64_t total = a.ntiles * p.batch;
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
+        pk_inv_chunks(a, p, TF, p.batch, cap);
+        const int64_t total = a.cps * p.batch;
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes);
         ++g_launch_count;
         return cudaGetLastError();

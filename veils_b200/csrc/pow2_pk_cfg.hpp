@@ -81,7 +81,6 @@ inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
 inline void pk_ptab_fill(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, int tf, PTab *t) {
     const TileLayout lay = tile_layout(H, true);
     const int64_t span = (int64_t)(tf - 1) * H + N;
-    const int zero_off = (int)(lay.addr((int)(span - 1)) + 1 + ((lay.addr((int)(span - 1)) + 1) & 1));
     for (int64_t m = 0; m < M / 2; ++m) {
         const int64_t j0 = (2 * m + ps) & (M - 1);
         PTab e;
@@ -91,7 +90,8 @@ inline void pk_ptab_fill(int64_t M, int64_t N, int64_t H, int64_t ps, const doub
             e.w0 = (float)(win[j0] * 0.5);
             e.w1 = (float)(win[j0 + 1] * 0.5);
         } else {
-            e.aoff = zero_off;
+            e.aoff = 0;
+            e.pad = 1;                                 // zero-padded pair (mfft > m_num): no tile read
             e.w0 = e.w1 = 0.f;
         }
         t[m] = e;
@@ -132,10 +132,23 @@ inline size_t pk_inv_work_bytes(int64_t N) {
     if (ola > work) work = ola;
     return (work + 15) & ~(size_t)15;
 }
+// streaming overlap-add: chunk geometry for a launch (owned slices qh0..qh1 per signal)
+inline void pk_inv_chunks(InvArgs<float> &a, const InvParams &p, int tf, int64_t batch, int64_t grid_hint) {
+    a.qh0 = fdiv64(p.k0 + p.mid, p.H);
+    a.qh1 = fdiv64(p.k1 - 1 + p.mid, p.H);
+    const int64_t Q = a.qh1 - a.qh0 + 1;
+    int ct = (50 * a.halo + tf - 1) / tf;              // halo re-computation <= ~2 % of a chunk
+    if (ct < 2) ct = 2;
+    if (ct > 64) ct = 64;
+    auto cps = [&](int c) { const int64_t lc = (int64_t)tf * c - a.halo; return (Q + lc - 1) / lc; };
+    while (ct > 2 && batch * cps(ct) < 4 * grid_hint) --ct;   // enough chunks to balance the CTAs
+    a.chunk_tiles = ct;
+    a.cps = cps(ct);
+}
 template <int LOGMC, int TF>
 inline size_t pk_inv_smem_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
-    size_t b = pk_inv_work_bytes<LOGMC, TF>(N);
+    size_t b = pk_inv_work_bytes<LOGMC, TF>(N) + 2 * 4 * (size_t)((N + 3) & ~3LL);   // + 2 carry buffers
     if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(ITab) * (size_t)G::MC;
     return b;
 }

@@ -209,6 +209,11 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
 
     // ---- pass 1: one group per thread and iteration
     VHD static void pass1(const PkFwdCtx &c, int tid) {
+        if (c.a.padded) pass1_t<true>(c, tid);
+        else pass1_t<false>(c, tid);
+    }
+    template <bool PADDED>
+    VHD static void pass1_t(const PkFwdCtx &c, int tid) {
         const FwdArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
         const int hs = p.H + p.lay.padw;
@@ -219,6 +224,10 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
                 const PTab e = GEO::pt4(pj + L1 * a);
+                if (PADDED && e.pad) {                         // sample pair beyond m_num: exact zeros
+                    v[a] = c2zero();
+                    continue;
+                }
                 const fl2 x0 = *reinterpret_cast<const fl2 *>(xf0 + e.aoff);
                 const fl2 x1 = *reinterpret_cast<const fl2 *>(xf1 + e.aoff);
                 v[a].x = mk2(x0.x * e.w0, x1.x * e.w0);        // scalar multiplies transpose for free
@@ -418,6 +427,9 @@ struct PkInvCtx {
     const ITab *itab;        // [MC] ola offsets + dual/M of sample pair m
     float *work;             // planar [MC][2][TF]
     float *ola;              // [TF][ostride] -- ALIASES work
+    const float *carry_in;   // [N - H] partial overlap sums of the samples this tile completes
+    float *carry_out;        // [N - H] ... and of the samples the next tile completes
+    int first;               // first tile of a chunk: no carry-in, its first `halo` slices are a re-computed halo
     int64_t b, qa;
 };
 
@@ -675,22 +687,41 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         }
     }
 
-    // overlap-add gather over the samples this tile owns, increasing q (src/lib.rs:853)
+    // Streaming overlap-add (src/lib.rs:853-911), increasing q:  local sample u = k + mid - qa*H.
+    //   u in [0, TF*H)           : completed by this tile -> global memory.  Contributions of earlier
+    //                              slices arrive in carry_in (u < N - H); the first tile of a chunk has
+    //                              no carry and only completes u >= halo*H.
+    //   u in [TF*H, TF*H + N - H): partial sums over this tile's slices -> carry_out.
+    // The summation order (earlier tiles' slices first, then this tile's in increasing q) is the
+    // reference's; everything is owned by this CTA: deterministic, no atomics.
+    VHD static float ola_sum(const PkInvCtx &c, int u, float acc) {
+        const InvArgs<float> &p = c.a;
+        const int H = p.H, N = p.N, halo = p.halo;
+        const int rq = (int)mulhi_u32((unsigned)u, p.magic_h);          // u / H: latest slice
+        int r = rq - halo;
+        int jj = u - r * H;
+        for (int h = 0; h <= halo; ++h, ++r, jj -= H)
+            if (r >= 0 && r < TF && jj < N) acc += c.ola[r * p.ostride + jj];
+        return acc;
+    }
     VHD static void gather(const PkInvCtx &c, int tid) {
         const InvArgs<float> &p = c.a;
         const int H = p.H, N = p.N, halo = p.halo;
-        const int64_t qo = c.qa + halo;
-        int64_t ka = qo * H - p.mid, kb = (c.qa + TF) * (int64_t)H - p.mid;
+        const int TFH = TF * H, NH = N - H, hH = halo * H;
+        const int64_t base = c.qa * (int64_t)H - p.mid;                 // k = base + u
+        float *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
+        // output range of this tile, clipped to [k0, k1)
+        int64_t ka = base + (c.first ? hH : 0), kb = base + TFH;
         if (ka < p.k0) ka = p.k0;
         if (kb > p.k1) kb = p.k1;
-        const int64_t base = c.qa * (int64_t)H - p.mid;
-        float *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
         const int ua = (int)(ka - base), ub = (int)(kb - base);
-        const int cnt = (TF - halo) * H, hH = halo * H, step = p.ostride - H;
+        const int u_hot = hH > NH ? hH : NH;                            // from here on: no carry, all slices local
+        // (1) the bulk: u in [u_hot, TF*H)
         if (halo == 3 && N == 4 * H && p.pair && (H & 1) == 0 && ((((size_t)xo) & 7) == 0)) {
-            // 75 % overlap, even geometry: two samples per thread, 8-byte loads and stores
-            const bool inner = ua <= hH && ub >= cnt + hH;
-            for (int e = 2 * tid; e < cnt; e += 2 * NT) {
+            const int step = p.ostride - H;
+            const bool inner = ua <= u_hot && ub >= TFH;
+            const int cnt = TFH - hH;
+            for (int e = 2 * tid; e < cnt; e += 2 * NT) {               // two samples per thread
                 const int u = e + hH;
                 const int r = (int)mulhi_u32((unsigned)e, p.magic_h);
                 const int idx = r * p.ostride + (e - r * H) + hH;
@@ -707,36 +738,54 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
                     if (u + 1 >= ua && u + 1 < ub) xo[u + 1] = o.y;
                 }
             }
-            return;
+        } else {
+            for (int u = u_hot + tid; u < TFH; u += NT)
+                if (u >= ua && u < ub) xo[u] = ola_sum(c, u, 0.f);
         }
-        if (halo == 3 && N == 4 * H) {                       // 75 % overlap: fully unrolled
-            for (int e = tid; e < cnt; e += NT) {
-                const int u = e + hH;
-                if (u < ua || u >= ub) continue;
-                const int r = (int)mulhi_u32((unsigned)e, p.magic_h);
-                const int idx = r * p.ostride + (e - r * H) + hH;
-                float acc = c.ola[idx];
-                acc += c.ola[idx + step];
-                acc += c.ola[idx + 2 * step];
-                acc += c.ola[idx + 3 * step];
-                xo[u] = acc;
+        if (halo == 3 && N == 4 * H && p.pair && (H & 1) == 0 && ((((size_t)xo) & 7) == 0)) {
+            // (2) head, (3) tail for the 75 % overlap case: block b of H samples sums b+1 (head) or 3-b
+            // (tail) local slices; two samples per thread, the same 8-byte accesses as the bulk
+            const int step = p.ostride - H, hp = H >> 1;
+            for (int e = tid; e < 3 * hp; e += NT) {
+                const int b = e >= 2 * hp ? 2 : (e >= hp ? 1 : 0);
+                const int c0 = 2 * (e - b * hp);
+                if (!c.first) {                                      // head: u = b H + c0
+                    const int u = b * H + c0;
+                    fl2 o = *reinterpret_cast<const fl2 *>(c.carry_in + u);
+                    int idx = u;                                     // row 0, offset u; next row: + step
+                    for (int i = 0; i <= b; ++i, idx += step) {
+                        const fl2 a = *reinterpret_cast<const fl2 *>(c.ola + idx);
+                        o.x += a.x;
+                        o.y += a.y;
+                    }
+                    if (u >= ua && u + 1 < ub) *reinterpret_cast<fl2 *>(xo + u) = o;
+                    else {
+                        if (u >= ua && u < ub) xo[u] = o.x;
+                        if (u + 1 >= ua && u + 1 < ub) xo[u + 1] = o.y;
+                    }
+                }
+                {                                                    // tail: v = b H + c0, rows TF-3+b .. TF-1
+                    const int v = b * H + c0;
+                    int idx = (TF - 3 + b) * p.ostride + 3 * H + c0;       // earliest slice: its last quarter
+                    fl2 o = *reinterpret_cast<const fl2 *>(c.ola + idx);
+                    idx += step;
+                    for (int i = 1; i < 3 - b; ++i, idx += step) {
+                        const fl2 a = *reinterpret_cast<const fl2 *>(c.ola + idx);
+                        o.x += a.x;
+                        o.y += a.y;
+                    }
+                    *reinterpret_cast<fl2 *>(c.carry_out + v) = o;
+                }
             }
             return;
         }
-        for (int e = tid; e < cnt; e += NT) {
-            const int u = e + hH;
-            if (u < ua || u >= ub) continue;
-            const int r = (int)mulhi_u32((unsigned)e, p.magic_h);
-            int jj = e - r * H + hH;
-            int idx = r * p.ostride + jj;
-            float acc = 0.f;
-            for (int h = 0; h <= halo; ++h) {
-                if (jj < N) acc += c.ola[idx];
-                jj -= H;
-                idx += step;
-            }
-            xo[u] = acc;
+        // (2) the head completed with the carry of the previous tile: u in [0, u_hot)
+        if (!c.first) {
+            for (int u = tid; u < u_hot; u += NT)
+                if (u >= ua && u < ub) xo[u] = ola_sum(c, u, u < NH ? c.carry_in[u] : 0.f);
         }
+        // (3) the tail handed to the next tile
+        for (int v = tid; v < NH; v += NT) c.carry_out[v] = ola_sum(c, TFH + v, 0.f);
     }
 };
 

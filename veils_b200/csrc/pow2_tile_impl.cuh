@@ -484,6 +484,10 @@ struct InvArgs {
     int halo;                // ceil(N/H) - 1 leading slices recomputed for the overlap
     int ostride;             // row stride of the overlap buffer
     int pair;                // packed family: rolled-back sample pairs are adjacent (ps, N even)
+    // packed family, streaming overlap-add: a signal's owned slices [qh0, qh1] are cut into chunks of
+    // chunk_tiles consecutive tiles that one CTA walks in order, carrying the overlap tail
+    int64_t qh0, qh1, cps;   // first / last owned (latest contributing) slice, chunks per signal
+    int chunk_tiles;
 };
 
 template <typename T>
