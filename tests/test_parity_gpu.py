@@ -109,3 +109,45 @@ def test_torch_device_pointer_path():
     assert np.max(np.abs(y.cpu().numpy()[:, :4000] - x)) <= 1e-4
     sp = s.spectrogram(xt)
     assert rel_err(sp.cpu().numpy(), np.abs(Sref) ** 2) <= 1e-5
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_randomized_pow2_geometry_against_oracle(precision):
+    """Randomized geometry for the power-of-two kernel families (packed f32, scalar f32/f64):
+    window length <= mfft, arbitrary hop, roll, k_offset, slice sub-ranges, all four layouts,
+    long enough for several tiles / chunks of the streaming overlap-add."""
+    rng = np.random.default_rng(2026)
+    tol = TOL[precision]
+    seen = set()
+    for it in range(40):
+        M = int(2 ** rng.integers(5, 12))
+        N = int(M if rng.random() < 0.6 else rng.integers(M // 2 + 1, M + 1))
+        H = int(rng.choice([N // 4, N // 2, max(2, N // 3), max(2, N // 8), int(rng.integers(2, N + 1))]))
+        H = max(2, min(H, N))
+        mode = str(rng.choice(["onesided", "twosided", "centered", "onesided2X"]))
+        ps = int(rng.integers(-M + 1, M)) if rng.random() < 0.3 else 0
+        scale = rng.choice([None, None, "magnitude", "psd"])
+        win = rng.uniform(0.2, 1.0, N)
+        n = int(rng.integers(6 * N, 6 * N + 40 * H + 100))
+        x = rng.uniform(-1, 1, (3, n))
+        if precision == "f32":
+            x = x.astype(np.float32).astype(np.float64)
+        o = OracleSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale)
+        s = StandaloneSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale,
+                           precision=precision)
+        seen.add((s.kernel_name(), s.kernel_name(True)))
+        koff = int(rng.integers(-3, 4))
+        Sref = np.stack([o.stft(r, k_offset=koff) for r in x])
+        S = s.stft(x, k_offset=koff)
+        assert rel_err(S, Sref) <= tol, (M, N, H, mode, ps, s.kernel_name())
+        sp = s.spectrogram(x, k_offset=koff)
+        assert rel_err(sp, np.abs(Sref) ** 2) <= 4 * tol
+        if o.invertible:
+            S0 = np.stack([o.stft(r) for r in x])
+            yref = np.stack([o.istft(q) for q in S0])
+            y = s.istft(S0)
+            assert rel_err(y, yref) <= tol, (M, N, H, mode, ps, s.kernel_name(True))
+            k0 = int(rng.integers(0, n // 3))
+            k1 = int(rng.integers(k0 + N, n))
+            assert rel_err(s.istft(S0, k0, k1), np.stack([o.istft(q, k0, k1) for q in S0])) <= tol
+    assert len(seen) >= 2
