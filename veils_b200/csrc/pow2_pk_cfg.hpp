@@ -160,8 +160,8 @@ template <typename FN>
 inline auto pk_dispatch(int logmc, FN &fn) -> decltype(fn.template run<4, 32, 4>()) {
     switch (logmc) {
         VEILS_PK_CASE(4, 32, 4) VEILS_PK_CASE(5, 32, 8) VEILS_PK_CASE(6, 32, 8) VEILS_PK_CASE(7, 32, 16)
-        VEILS_PK_CASE(8, 32, 16) VEILS_PK_CASE(9, 32, 16) VEILS_PK_CASE(10, 16, 32)
-        VEILS_PK_CASE(11, 8, 64) VEILS_PK_CASE(12, 4, 128)
+        VEILS_PK_CASE(8, 32, 16) VEILS_PK_CASE(9, 32, 32) VEILS_PK_CASE(10, 16, 64)
+        VEILS_PK_CASE(11, 8, 128) VEILS_PK_CASE(12, 4, 256)          // 3-pass plans: 512 threads, 1 CTA/SM
     }
     return decltype(fn.template run<4, 32, 4>())(-1);
 }
