@@ -3,8 +3,10 @@
 // list; plan tables live in shared memory and the signal tile is double-buffered with cp.async
 // for mfft <= 512.
 #include <cstdlib>
+#include <cstring>
 
 #include "pow2_pk_cfg.hpp"
+#include "tma.cuh"
 
 namespace veils {
 
@@ -19,18 +21,22 @@ __device__ __forceinline__ void copy_table_f(float *dst, const float *src, int n
 template <int LOGMC, int TF>
 constexpr int pk_min_ctas() { return 8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
 
-template <int LOGMC, int TF, int NSUB, bool ONES, bool SPEC>
+// STAGE (one-sided layouts): the last pass overwrites its own work rows with the finished bins
+// -- every thread writes exactly the bytes it has read, so no barrier is needed -- and each
+// half-warp hands its group's dense [RL rows][TF slices] box to the TMA engine (tma.cuh): the
+// global stores cost the compute warps one instruction per group and drain asynchronously.
+template <int LOGMC, int TF, int NSUB, bool ONES, bool SPEC, bool STAGE>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
 pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restrict__ ptab_g,
               const int64_t total, const int xin_elems, const int zero_off, const int stagger_ns,
-              const int num_sms) {
-    extern __shared__ __align__(16) unsigned char smem[];
+              const int num_sms, const __grid_constant__ CUtensorMap smap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     using K = PkFwd<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
     PkFwdCtx c;
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
-    float *xin0 = c.work + (size_t)K::MC * 2 * TF;
+    float *xin0 = c.work + (size_t)K::MC * 2 * TF + PK_NYQ_ROW;     // + staged Nyquist row
     float *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
     if (K::STAB) {
         float *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;     // xin_elems is a multiple of 4
@@ -63,6 +69,7 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
     }
     for (int it = 0; w < total; w += gridDim.x, ++it) {
         cp_async_wait_all();
+        if (STAGE) tma::wait_read_all();       // the previous tile's boxes have left the work buffer
         __syncthreads();
         float *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
         const int64_t wn = w + gridDim.x;
@@ -102,18 +109,35 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
             if (args.dbg & 8) continue;
 #endif
             K::last_dft(c, tid, i, u);
-            K::template last_emit_v<ONES, SPEC>(c, tid, i, u, nullptr);
+            if (STAGE && SPEC) __syncwarp();   // |X|^2 rows are half as wide: lanes overwrite each other's inputs
+            K::template last_emit_v<ONES, SPEC, STAGE>(c, tid, i, u, nullptr);
+            if (STAGE) {
+                tma::fence_async_smem();
+                __syncwarp();
+                const int l = tid % K::LN, sub = tid / K::LN;
+                const int wg = (sub >> 1) + i * (NSUB / 2), h = sub & 1;
+                if (l == 0 && wg < K::G / 2) {
+                    const int g = K::group_of(wg, h);
+                    const unsigned wbase = tma::smem_u32(c.work);
+                    const int p0 = (int)(cpt * TF);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * (TF * 8), p0, g, 0, (int)cb);
+                    if (wg == 0 && h == 0)      // Nyquist row: rows past d = RL are clipped by the map
+                        tma::store_4d(&smap, wbase + K::MC * (TF * 8), p0, 0, K::RL, (int)cb);
+                    tma::commit_group();
+                }
+            }
         }
         cb = nb;
         cpt = npt;
     }
+    if (STAGE) tma::wait_all();
 }
 
 template <int LOGMC, int TF, int NSUB, bool ONES>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
               const int64_t total, const int work_bytes) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     using K = PkInv<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
     PkInvCtx c;
@@ -205,10 +229,19 @@ struct PkFwdLaunch {
         a.dbg = pk_env_int("VEILS_PK_DBG", 0);
         const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
         const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
-        using KernT = void (*)(const FwdArgs<float>, const PTab *, const int64_t, const int, const int, const int, const int);
+        using KernT = void (*)(const FwdArgs<float>, const PTab *, const int64_t, const int, const int, const int, const int,
+                               const CUtensorMap);
         const bool ones = p.mode >= 2, spec = p.spectrogram != 0;
-        KernT kern = ones ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false>)
-                          : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false>);
+        using K = PkFwd<LOGMC, TF, NSUB>;
+        // one-sided layouts leave through the TMA engine when S can be described by a tensor map
+        // (16-byte aligned base and row pitch); VEILS_PK_NO_TMA=1 forces the plain-store kernels
+        CUtensorMap smap;
+        memset(&smap, 0, sizeof(smap));
+        const bool stage = ones && p.batch < (1LL << 31) && !pk_env_int("VEILS_PK_NO_TMA", 0) &&
+                           tma::make_s_map(&smap, out, spec ? 4 : 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL);
+        KernT kern = stage ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, true>)
+                   : ones  ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, false>)
+                           : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false, false>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -218,7 +251,7 @@ struct PkFwdLaunch {
         const int64_t total = a.ptiles * p.batch;
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(
-            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms());
+            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms(), smap);
         ++g_launch_count;
         return cudaGetLastError();
     }

@@ -67,11 +67,12 @@ inline void pk_twiddle_fill(int64_t M, bool inverse, double *t) {
     for (int64_t i = 0; i < l1; ++i) put2(0, 1, 0, 1);
 }
 
+constexpr int PK_NYQ_ROW = 64;    // floats kept behind the work buffer: the staged Nyquist row (TMA stores)
 template <int LOGMC, int TF>
 inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
     using G = PkGeo<LOGMC, TF, 2>;
     (void)N;
-    size_t b = 4 * ((size_t)G::MC * 2 * TF + (size_t)((xin_elems + 3) & ~3LL) * (G::DBUF ? 2 : 1));
+    size_t b = 4 * ((size_t)G::MC * 2 * TF + PK_NYQ_ROW + (size_t)((xin_elems + 3) & ~3LL) * (G::DBUF ? 2 : 1));
     if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(PTab) * (size_t)G::MC;
     return b;
 }

@@ -277,11 +277,23 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         bool live0, live1;   // slice l / l + LN inside [0, P)
         int dbg;
     };
-    template <bool SPEC>
+    // STAGE: the tile is staged in shared memory (in place, over the rows this thread has read) and
+    // leaves through the TMA engine (pk_fwd_kernel); q then points into the work buffer.
+    template <bool SPEC, bool STAGE>
     VHD static void put_at(const Out &o, char *q, float r0, float i0, float r1, float i1) {
 #ifdef VEILS_ABLATE
         if ((o.dbg & 1) && r0 != 12345.678f) return;      // ablation: no global stores
 #endif
+        if (STAGE) {
+            if (SPEC) {
+                *reinterpret_cast<float *>(q) = r0 * r0 + i0 * i0;
+                *reinterpret_cast<float *>(q + 4 * LN) = r1 * r1 + i1 * i1;
+            } else {
+                fl2 v; v.x = r0; v.y = i0; *reinterpret_cast<fl2 *>(q) = v;
+                fl2 u; u.x = r1; u.y = i1; *reinterpret_cast<fl2 *>(q + 8 * LN) = u;
+            }
+            return;
+        }
         if (SPEC) {
             if (o.live0) *reinterpret_cast<float *>(q) = r0 * r0 + i0 * i0;
             if (o.live1) *reinterpret_cast<float *>(q + 4 * LN) = r1 * r1 + i1 * i1;
@@ -293,23 +305,34 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     // mode epilogue of one-sided bin k (src/lib.rs:367-408) and the store(s).
     // MODE: 0 twosided, 1 centered, 2 onesided, 3 onesided2X.  EDGE: k may be 0 or Mc.
     // q: byte pointer of row k (one-sided layouts only).
-    template <int MODE, bool SPEC, bool EDGE>
+    // byte offset of one-sided bin k in the staged tile: the RL rows of last-pass group g = k mod G
+    // are contiguous at the group's own work rows (row pitch TF * esz); bin Mc has an extra row.
+    template <bool SPEC>
+    VHD static int srow(int k) {
+        if (k >= MC) return MC * TF * 8;
+        return GEO::goff(k & (G - 1)) * (TF * 8) + (k / G) * (TF * (SPEC ? 4 : 8));
+    }
+    template <bool SPEC, bool STAGE>
+    VHD static char *rowptr(const Out &o, int k) {
+        return STAGE ? o.ob + srow<SPEC>(k) : o.ob + k * o.rb;
+    }
+    template <int MODE, bool SPEC, bool EDGE, bool STAGE>
     VHD static void store_bin(const FwdArgs<float> &p, const Out &o, char *q, int k, float r0, float i0, float r1, float i1) {
         const bool edge = EDGE && (k == 0 || k == MC);
         if (edge) { i0 = 0.f; i1 = 0.f; }
         if (MODE >= 2) {
             if (MODE == 3 && !edge) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }
-            put_at<SPEC>(o, q, r0, i0, r1, i1);
+            put_at<SPEC, STAGE>(o, q, r0, i0, r1, i1);
             return;
         }
         const int sh = MODE == 1 ? MC : 0;                                    // fftshift for centered
-        put_at<SPEC>(o, o.ob + ((k + sh) & (M - 1)) * o.rb, r0, i0, r1, i1);
-        if (!edge) put_at<SPEC>(o, o.ob + ((M - k + sh) & (M - 1)) * o.rb, r0, -i0, r1, -i1);
+        put_at<SPEC, false>(o, o.ob + ((k + sh) & (M - 1)) * o.rb, r0, i0, r1, i1);
+        if (!edge) put_at<SPEC, false>(o, o.ob + ((M - k + sh) & (M - 1)) * o.rb, r0, -i0, r1, -i1);
     }
 
     // own = Z[k_own]/2 of this thread's group, rcv = Z[Mc - k_own]/2 (partner half or own
     // registers); t = table entry of k_own (= (-wr, wi) of the mirrored bin).  Produces X[k_own].
-    template <int MODE, bool SPEC, bool EDGE>
+    template <int MODE, bool SPEC, bool EDGE, bool STAGE>
     VHD static void emit1(const FwdArgs<float> &p, const Out &o, char *q, int k, fl4 t, C2 own, C2 rcv) {
         const f2 Ex = own.x + rcv.x, Oy = own.y + rcv.y, ey = own.y - rcv.y, ox = own.x - rcv.x;
         const f2 ax = vfma(bc(t.y), ox, Ex);                 // + wi * ox
@@ -317,13 +340,14 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         // last fma scalar: moves (re,re)(im,im) into {re,im} per slice for free
         const float r0 = t.x * lo(Oy) + lo(ax), r1 = t.x * hi(Oy) + hi(ax);
         const float i0 = t.z * lo(ox) + lo(ay), i1 = t.z * hi(ox) + hi(ay);
-        store_bin<MODE, SPEC, EDGE>(p, o, q, k, r0, i0, r1, i1);
+        store_bin<MODE, SPEC, EDGE, STAGE>(p, o, q, k, r0, i0, r1, i1);
     }
     // both outputs from values held by one thread (self-mirrored groups 0 and G/2)
-    template <int MODE, bool SPEC>
+    template <int MODE, bool SPEC, bool STAGE>
     VHD static void emit2(const FwdArgs<float> &p, const float *twp, const Out &o, int k, C2 A, C2 Zp, bool both) {
-        emit1<MODE, SPEC, true>(p, o, o.ob + k * o.rb, k, GEO::tw4(twp + 4 * k), A, Zp);
-        if (both) emit1<MODE, SPEC, true>(p, o, o.ob + (MC - k) * o.rb, MC - k, GEO::tw4(twp + 4 * (MC - k)), Zp, A);
+        emit1<MODE, SPEC, true, STAGE>(p, o, rowptr<SPEC, STAGE>(o, k), k, GEO::tw4(twp + 4 * k), A, Zp);
+        if (both)
+            emit1<MODE, SPEC, true, STAGE>(p, o, rowptr<SPEC, STAGE>(o, MC - k), MC - k, GEO::tw4(twp + 4 * (MC - k)), Zp, A);
     }
 
     // ---- last pass, part 1: this thread's group -> registers
@@ -340,7 +364,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     }
     // ---- last pass, part 2: exchange with the partner half, split, epilogue, store.
     //      pu = the partner thread's u[] (host emulation only)
-    template <int MODE, bool SPEC>
+    template <int MODE, bool SPEC, bool STAGE = false>
     VHD static void last_emit_t(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const FwdArgs<float> &p = c.a;
         const int l = tid % LN, sub = tid / LN;
@@ -349,10 +373,16 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         const int64_t pl = c.pt * TF + l;
         const int64_t esz = SPEC ? 4 : 8;
         Out o;
-        o.live0 = pl < p.P;
-        o.live1 = pl + LN < p.P;
-        o.rb = p.ldp * esz;
-        o.ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+        if (STAGE) {
+            o.live0 = o.live1 = true;                      // the TMA store clips at P
+            o.rb = TF * esz;
+            o.ob = reinterpret_cast<char *>(c.work) + l * esz;
+        } else {
+            o.live0 = pl < p.P;
+            o.live1 = pl + LN < p.P;
+            o.rb = p.ldp * esz;
+            o.ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+        }
         o.dbg = p.dbg;
         const float *twp = c.tw + GEO::TWP;
         const int g = group_of(w, h);
@@ -362,8 +392,8 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             // its bins backwards, so row pointer, table pointer and k advance by a per-thread stride.
             int k = g + (h == 0 ? 0 : G * (RL - 1));
             const int kstep = h == 0 ? G : -G;
-            char *q = o.ob + k * o.rb;
-            const int64_t qstep = kstep * o.rb;
+            char *q = rowptr<SPEC, STAGE>(o, k);
+            const int64_t qstep = STAGE ? (h == 0 ? TF * esz : -TF * esz) : kstep * o.rb;
             const float *tq = twp + 4 * k;
             const int tstep = 4 * kstep;
 #pragma unroll
@@ -375,7 +405,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
 #else
                 const C2 rcv = xchg<LN>(mine, pu ? pu + ((GEO::REVG || h != 0) ? d : RL - 1 - d) : nullptr, mask);
 #endif
-                emit1<MODE, SPEC, false>(p, o, q, k, GEO::tw4(tq), mine, rcv);
+                emit1<MODE, SPEC, false, STAGE>(p, o, q, k, GEO::tw4(tq), mine, rcv);
                 k += kstep;
                 q += qstep;
                 tq += tstep;
@@ -390,19 +420,19 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
                 const C2 a = u[t];
                 const C2 bm = h == 0 ? u[(RL - t) & (RL - 1)] : u[RL - 1 - t];
                 const int k = h == 0 ? G * t : G / 2 + G * t;
-                emit2<MODE, SPEC>(p, twp, o, k, a, bm, true);      // t = 0, h = 0: X[0] and X[Mc]
+                emit2<MODE, SPEC, STAGE>(p, twp, o, k, a, bm, true);      // t = 0, h = 0: X[0] and X[Mc]
             }
-            if (h == 0) emit2<MODE, SPEC>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
+            if (h == 0) emit2<MODE, SPEC, STAGE>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
         }
     }
     // kernel variants: ONES = one-sided layouts (modes 2, 3), SPEC = |X|^2 output.  Keeping the
     // two-sided address arithmetic out of the one-sided kernels matters: the compiler hoists it.
-    template <bool ONES, bool SPEC>
+    template <bool ONES, bool SPEC, bool STAGE = false>
     VHD static void last_emit_v(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL], const C2 *pu) {
         const int mode = c.a.mode;
         if (ONES) {
-            if (mode == 3) last_emit_t<3, SPEC>(c, tid, it, u, pu);
-            else last_emit_t<2, SPEC>(c, tid, it, u, pu);
+            if (mode == 3) last_emit_t<3, SPEC, STAGE>(c, tid, it, u, pu);
+            else last_emit_t<2, SPEC, STAGE>(c, tid, it, u, pu);
         } else {
             if (mode == 1) last_emit_t<1, SPEC>(c, tid, it, u, pu);
             else last_emit_t<0, SPEC>(c, tid, it, u, pu);

@@ -1,0 +1,96 @@
+// tma.cuh -- Tensor Memory Accelerator plumbing for the packed kernels (sm_100a):
+//   * host: tensor-map encoding through the driver entry point (no link-time libcuda dependency);
+//   * device: bulk-tensor store / load PTX, bulk-group bookkeeping, mbarrier helpers.
+// The kernels stage a tile of the STFT matrix S[b][f][p] in shared memory and let the TMA engine
+// move it: the slice-lane layout makes every group of RL bins a dense [RL rows][TF slices] box.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace veils {
+namespace tma {
+
+using EncodeFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                              const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeFn encode_fn() {
+    static EncodeFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeFn)p;
+    }();
+    return fn;
+}
+
+// Tensor map of S[b][f][p] (element size esz = 4 or 8 bytes, row pitch ldp elements) seen as
+//   dim0 = p (size P), dim1 = g (size G, stride ldp), dim2 = d (size RL + 1, stride G ldp),
+//   dim3 = b (size B, stride F ldp):  row f = g + G d  (F = G RL + 1; d = RL exists for g = 0 only
+//   and is the Nyquist row -- the other (g, RL) coordinates are never touched).
+// Box = [TF slices][1][rows][1].  Returns false when the layout cannot be described (alignment).
+inline bool make_s_map(CUtensorMap *m, const void *base, int esz, int64_t P, int64_t ldp, int64_t F, int64_t B,
+                       int G, int RL, int TF, int box_rows) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) != 0 || (ldp * esz) % 16 != 0 || (TF * esz) % 16 != 0) return false;
+    if (P <= 0 || B <= 0 || P >= (1LL << 32) || B >= (1LL << 32)) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)P, (cuuint64_t)G, (cuuint64_t)(RL + 1), (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)(ldp * esz), (cuuint64_t)(G * ldp * esz), (cuuint64_t)(F * ldp * esz)};
+    for (int i = 0; i < 3; ++i)
+        if (strides[i] >= (1ULL << 40) || strides[i] % 16 != 0) return false;
+    const cuuint32_t box[4] = {(cuuint32_t)TF, 1, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    const CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+// shared -> global, box at coordinates (c0, c1, c2, c3); completion tracked by the bulk group
+__device__ __forceinline__ void store_4d(const CUtensorMap *m, unsigned src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory become visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_map(const CUtensorMap *m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
+}
+// global -> shared, completion on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void load_4d(const CUtensorMap *m, unsigned dst, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+#endif
+
+}  // namespace tma
+}  // namespace veils
