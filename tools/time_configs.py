@@ -18,7 +18,8 @@ CASES = [
     ("f32 2048/512 onesided B=256x480000", hann(2048), 512, "onesided", None, "f32", 256, 480000, False),
     ("f32 256/64 onesided B=1024x160000", hann(256), 64, "onesided", None, "f32", 1024, 160000, False),
 ]
-sel = sys.argv[1:] 
+ALIGN = "--align" in sys.argv      # pad S rows to 32-byte sectors (what veils_b200.stft does for device tensors)
+sel = [a for a in sys.argv[1:] if not a.startswith("--")]
 L = lib()
 dev = torch.device("cuda", 0)
 for name, win, hop, mode, scale, prec, B, n, spec in CASES:
@@ -29,7 +30,9 @@ for name, win, hop, mode, scale, prec, B, n, spec in CASES:
     sz = 4 if prec == "f32" else 8
     x = torch.rand((B, n), device=dev, dtype=rdt) * 2 - 1
     P, F = st.p_num(n), st.f_pts
-    S = torch.empty((B, F, P), dtype=rdt if spec else cdt, device=dev)
+    q = (32 // (sz if spec else 2 * sz)) if ALIGN else 1
+    ldp = (P + q - 1) // q * q
+    S = torch.empty((B, F, ldp), dtype=rdt if spec else cdt, device=dev)
     def t(fn, reps=5):
         fn(); fn(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -38,14 +41,14 @@ for name, win, hop, mode, scale, prec, B, n, spec in CASES:
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
     if spec:
-        ms = t(lambda: L.veils_spectrogram_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), P, None))
+        ms = t(lambda: L.veils_spectrogram_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), ldp, None))
         by = B * (n * sz + F * P * sz)
         print(f"{name}: [{st.kernel_name()}] spectrogram {ms:.3f} ms  {by/ms/1e6:.0f} GB/s  {by/ms/1e6/PEAK*100:.1f}% ; {B*n/ms/1e3:.0f} Msmp/s", flush=True)
         continue
-    ms_f = t(lambda: L.veils_stft_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), P, None))
+    ms_f = t(lambda: L.veils_stft_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), ldp, None))
     k0, k1 = st.istft_range(P)
     y = torch.empty((B, k1 - k0), dtype=rdt, device=dev)
-    ms_i = t(lambda: L.veils_istft_dev(st._h, S.data_ptr(), P, B, P, None, None, y.data_ptr(), k1 - k0, None))
+    ms_i = t(lambda: L.veils_istft_dev(st._h, S.data_ptr(), P, B, ldp, None, None, y.data_ptr(), k1 - k0, None))
     bf = B * (n * sz + F * P * 2 * sz); bi = B * (F * P * 2 * sz + (k1 - k0) * sz)
     err = float((y[:, :n] - x).abs().max())
     print(f"{name}: [{st.kernel_name()}/{st.kernel_name(True)}] fwd {ms_f:.3f} ms {bf/ms_f/1e6/PEAK*100:.1f}%  inv {ms_i:.3f} ms {bi/ms_i/1e6/PEAK*100:.1f}%  "

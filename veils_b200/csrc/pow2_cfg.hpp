@@ -174,6 +174,7 @@ inline InvArgs<T> make_inv_args(const void *S, T *xo, const InvParams &p, const 
     a.halo = inv_halo(p.N, p.H);
     a.ostride = inv_ostride(p.N);
     a.pair = 0;
+    a.dbg = 0;
     const int own = tf - a.halo;
     const int64_t qh0 = fdiv64(p.k0 + p.mid, p.H), qh1 = fdiv64(p.k1 - 1 + p.mid, p.H);
     a.ntiles = (qh1 - qh0 + 1 + own - 1) / own;

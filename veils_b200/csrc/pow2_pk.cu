@@ -18,15 +18,21 @@ __device__ __forceinline__ void copy_table_f(float *dst, const float *src, int n
     for (int i = tid; i < n; i += nt) dst[i] = __ldg(src + i);
 }
 
-template <int LOGMC, int TF>
-constexpr int pk_min_ctas() { return 8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1; }
+// co-resident CTAs the register budget is sized for: what the work buffer allows, capped so
+// that every thread keeps 128 registers (512 threads per SM)
+template <int LOGMC, int TF, int NT>
+constexpr int pk_min_ctas() {
+    constexpr int by_smem = 8 * (1 << LOGMC) * TF <= 40 * 1024 ? 4 : (8 * (1 << LOGMC) * TF <= 80 * 1024 ? 2 : 1);
+    constexpr int by_regs = 512 / NT < 1 ? 1 : 512 / NT;
+    return by_smem < by_regs ? by_smem : by_regs;
+}
 
 // STAGE (one-sided layouts): the last pass overwrites its own work rows with the finished bins
 // -- every thread writes exactly the bytes it has read, so no barrier is needed -- and each
 // half-warp hands its group's dense [RL rows][TF slices] box to the TMA engine (tma.cuh): the
 // global stores cost the compute warps one instruction per group and drain asynchronously.
 template <int LOGMC, int TF, int NSUB, bool ONES, bool SPEC, bool STAGE>
-__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
+__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restrict__ ptab_g,
               const int64_t total, const int xin_elems, const int zero_off, const int stagger_ns,
               const int num_sms, const __grid_constant__ CUtensorMap smap) {
@@ -134,7 +140,7 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
 }
 
 template <int LOGMC, int TF, int NSUB, bool ONES>
-__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF>())
+__global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
               const int64_t total, const int work_bytes) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -178,7 +184,20 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
             for (int i = 0; i < K::WPT; ++i) {
                 Raw x[K::R1];
                 Raw xn;
+#ifdef VEILS_ABLATE
+                if (args.dbg & 1) {            // ablation: no global loads
+#pragma unroll
+                    for (int a = 0; a < K::R1; ++a) { x[a].r0 = tid + a; x[a].i0 = a; x[a].r1 = tid; x[a].i1 = 1.f; }
+                    xn = x[0];
+                } else
+#endif
                 K::template p1_load_v<ONES>(c, tid, i, x, xn);
+#ifdef VEILS_ABLATE
+                if (args.dbg & 16) {           // ablation: no pass 1 arithmetic
+                    if (x[3].r0 == 12345.678f) c.work[tid] = x[5].i1 + xn.r0;
+                    continue;
+                }
+#endif
                 K::p1_rest(c, tid, i, x, xn, nullptr);
             }
             __syncthreads();
@@ -186,6 +205,9 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
                 K::pass_mid(c, tid);
                 __syncthreads();
             }
+#ifdef VEILS_ABLATE
+            if (!(args.dbg & 8))
+#endif
             {
                 C2 r[K::GPT][K::RL];
                 K::last_load(c, tid, r);
@@ -193,6 +215,9 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
                 K::last_store(c, tid, r);
             }
             __syncthreads();
+#ifdef VEILS_ABLATE
+            if (!(args.dbg & 4))
+#endif
             K::gather(c, tid);
             __syncthreads();                   // `ola` consumed before the next tile overwrites `work`
         }
@@ -266,6 +291,7 @@ struct PkInvLaunch {
         InvArgs<float> a = make_inv_args<float>(S, xo, p, nullptr, tw, TF);
         a.ostride = pk_ostride(p.N, p.ps);
         a.pair = pk_pair(p.N, p.ps) ? 1 : 0;
+        a.dbg = pk_env_int("VEILS_PK_DBG_INV", 0);
         const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
         const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
         using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int);

@@ -7,11 +7,14 @@
 namespace veils {
 namespace p2 {
 
+#ifndef VEILS_PK_TF8
+#define VEILS_PK_TF8 32                               // slices per tile for mfft = 512 (tuning knob)
+#endif
 inline bool pk_cfg_for(int64_t M, Cfg *c) {
     const int lm = ilog2_exact(M);
     if (lm < 5 || lm > 13) return false;
     c->logmc = lm - 1;
-    static const int tf[13] = {0, 0, 0, 0, 32, 32, 32, 32, 32, 32, 16, 8, 4};
+    static const int tf[13] = {0, 0, 0, 0, 32, 32, 32, 32, VEILS_PK_TF8, 32, 16, 8, 4};
     c->tf = tf[c->logmc];
     c->nsub = 0;                                      // fixed by the dispatch table below
     return true;
@@ -161,7 +164,7 @@ template <typename FN>
 inline auto pk_dispatch(int logmc, FN &fn) -> decltype(fn.template run<4, 32, 4>()) {
     switch (logmc) {
         VEILS_PK_CASE(4, 32, 4) VEILS_PK_CASE(5, 32, 8) VEILS_PK_CASE(6, 32, 8) VEILS_PK_CASE(7, 32, 16)
-        VEILS_PK_CASE(8, 32, 16) VEILS_PK_CASE(9, 32, 32) VEILS_PK_CASE(10, 16, 64)
+        VEILS_PK_CASE(8, VEILS_PK_TF8, 16) VEILS_PK_CASE(9, 32, 32) VEILS_PK_CASE(10, 16, 64)
         VEILS_PK_CASE(11, 8, 128) VEILS_PK_CASE(12, 4, 256)          // 3-pass plans: 512 threads, 1 CTA/SM
     }
     return decltype(fn.template run<4, 32, 4>())(-1);

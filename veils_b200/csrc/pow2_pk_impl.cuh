@@ -477,18 +477,27 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         int64_t rb;
         bool live0, live1;
     };
+    VHD static fl2 ldS(const char *q) {              // one complex of S: global memory, read once
+#if defined(__CUDA_ARCH__)
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(q));
+        fl2 r; r.x = v.x; r.y = v.y;
+        return r;
+#else
+        return *reinterpret_cast<const fl2 *>(q);
+#endif
+    }
     template <bool FULL>
     VHD static Raw get_at(const In &in, const char *q) {
         Raw r;
         if (FULL) {                                  // both slices inside [q0, q1): no predication
-            const fl2 a = *reinterpret_cast<const fl2 *>(q);
-            const fl2 b = *reinterpret_cast<const fl2 *>(q + 8 * LN);
+            const fl2 a = ldS(q);
+            const fl2 b = ldS(q + 8 * LN);
             r.r0 = a.x; r.i0 = a.y; r.r1 = b.x; r.i1 = b.y;
             return r;
         }
         r.r0 = r.i0 = r.r1 = r.i1 = 0.f;
-        if (in.live0) { const fl2 v = *reinterpret_cast<const fl2 *>(q); r.r0 = v.x; r.i0 = v.y; }
-        if (in.live1) { const fl2 v = *reinterpret_cast<const fl2 *>(q + 8 * LN); r.r1 = v.x; r.i1 = v.y; }
+        if (in.live0) { const fl2 v = ldS(q); r.r0 = v.x; r.i0 = v.y; }
+        if (in.live1) { const fl2 v = ldS(q + 8 * LN); r.r1 = v.x; r.i1 = v.y; }
         return r;
     }
     // Hermitian one-sided bin k (src/lib.rs:414-487); two-sided layouts: S[k] + conj(S[M-k]).
@@ -604,7 +613,11 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             const int tstep = rev ? -4 * L1 : 4 * L1;
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
+#ifdef VEILS_ABLATE
+                const Raw rcv = (c.a.dbg & 2) ? x[a] : xchg_raw<LN>(x[a], px ? px + a : nullptr, mask);
+#else
                 const Raw rcv = xchg_raw<LN>(x[a], px ? px + a : nullptr, mask);
+#endif
                 v[a] = merge1(GEO::tw4(tq), x[a], rcv);
                 tq += tstep;
             }
@@ -751,6 +764,29 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             const int step = p.ostride - H;
             const bool inner = ua <= u_hot && ub >= TFH;
             const int cnt = TFH - hH;
+            const int rs = (int)mulhi_u32((unsigned)(2 * NT), p.magic_h);    // (2 NT) / H
+            if (inner && rs * H == 2 * NT) {
+                // the thread's column inside a slice never changes and its row advances by rs per
+                // iteration: pure pointer increments, no index arithmetic in the loop
+                const int e0 = 2 * tid;
+                const int r0 = (int)mulhi_u32((unsigned)e0, p.magic_h);
+                const float *pa = c.ola + r0 * p.ostride + (e0 - r0 * H) + hH;
+                const float *pb = pa + step, *pc = pb + step, *pd = pc + step;
+                const int adv = rs * p.ostride;
+                float *po = xo + e0 + hH;
+                for (int e = e0; e < cnt; e += 2 * NT) {
+                    const fl2 a0 = *reinterpret_cast<const fl2 *>(pa);
+                    const fl2 a1 = *reinterpret_cast<const fl2 *>(pb);
+                    const fl2 a2 = *reinterpret_cast<const fl2 *>(pc);
+                    const fl2 a3 = *reinterpret_cast<const fl2 *>(pd);
+                    fl2 o;
+                    o.x = ((a0.x + a1.x) + a2.x) + a3.x;
+                    o.y = ((a0.y + a1.y) + a2.y) + a3.y;
+                    *reinterpret_cast<fl2 *>(po) = o;
+                    pa += adv; pb += adv; pc += adv; pd += adv;
+                    po += 2 * NT;
+                }
+            } else
             for (int e = 2 * tid; e < cnt; e += 2 * NT) {               // two samples per thread
                 const int u = e + hH;
                 const int r = (int)mulhi_u32((unsigned)e, p.magic_h);

@@ -488,6 +488,7 @@ struct InvArgs {
     // chunk_tiles consecutive tiles that one CTA walks in order, carrying the overlap tail
     int64_t qh0, qh1, cps;   // first / last owned (latest contributing) slice, chunks per signal
     int chunk_tiles;
+    int dbg;                 // ablation mask (VEILS_ABLATE builds only)
 };
 
 template <typename T>
