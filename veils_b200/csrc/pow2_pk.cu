@@ -108,29 +108,40 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
             K::pass_mid(c, tid);
             __syncthreads();
         }
+        if (STAGE) {
 #pragma unroll 1
-        for (int i = 0; i < K::WPT; ++i) {
-            C2 u[K::RL];
+            for (int i = 0; i < K::WPT2; ++i) {
+                C2 u[K::RL];
 #ifdef VEILS_ABLATE
-            if (args.dbg & 8) continue;
+                if (args.dbg & 8) continue;
 #endif
-            K::last_dft(c, tid, i, u);
-            if (STAGE && SPEC) __syncwarp();   // |X|^2 rows are half as wide: lanes overwrite each other's inputs
-            K::template last_emit_v<ONES, SPEC, STAGE>(c, tid, i, u, nullptr);
-            if (STAGE) {
+                K::last_dft2(c, tid, i, u);
+                __syncwarp();                  // the rows of a group pair belong to the threads of one warp:
+                                               // all of them have read before anyone overwrites
+                K::template last_emit2<SPEC>(c, tid, i, u);
                 tma::fence_async_smem();
                 __syncwarp();
-                const int l = tid % K::LN, sub = tid / K::LN;
-                const int wg = (sub >> 1) + i * (NSUB / 2), h = sub & 1;
-                if (l == 0 && wg < K::G / 2) {
-                    const int g = K::group_of(wg, h);
+                const int lam = tid % TF, wg = tid / TF + i * K::NW2;
+                if (lam == 0 && wg < K::G / 2) {
                     const unsigned wbase = tma::smem_u32(c.work);
                     const int p0 = (int)(cpt * TF);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * (TF * 8), p0, g, 0, (int)cb);
-                    if (wg == 0 && h == 0)      // Nyquist row: rows past d = RL are clipped by the map
+                    const int g0 = K::group_of(wg, 0), g1 = K::group_of(wg, 1);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g0) * (TF * 8), p0, g0, 0, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g1) * (TF * 8), p0, g1, 0, (int)cb);
+                    if (wg == 0)                // Nyquist row: rows past d = RL are clipped by the map
                         tma::store_4d(&smap, wbase + K::MC * (TF * 8), p0, 0, K::RL, (int)cb);
                     tma::commit_group();
                 }
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < K::WPT; ++i) {
+                C2 u[K::RL];
+#ifdef VEILS_ABLATE
+                if (args.dbg & 8) continue;
+#endif
+                K::last_dft(c, tid, i, u);
+                K::template last_emit_v<ONES, SPEC, false>(c, tid, i, u, nullptr);
             }
         }
         cb = nb;

@@ -64,6 +64,16 @@ struct PkGeo {
 #endif
         return *reinterpret_cast<const fl4 *>(q);
     }
+    VHD static fl2 tw2(const float *q) {               // first half (wr, wi) of a table entry
+#if defined(__CUDA_ARCH__)
+        if (!STAB) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(q));
+            fl2 r; r.x = v.x; r.y = v.y;
+            return r;
+        }
+#endif
+        return *reinterpret_cast<const fl2 *>(q);
+    }
     VHD static PTab pt4(const PTab *q) {
 #if defined(__CUDA_ARCH__)
         if (!STAB) {
@@ -242,9 +252,9 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             wstore(wj, TF, v[0]);
 #pragma unroll
             for (int cc = 1; cc < R1; ++cc) {
-                const fl4 t = GEO::tw4(twj + 4 * cc);
+                const fl2 t = GEO::tw2(twj + 4 * cc);          // (wr, wi): 8-byte broadcast read
                 float *dst = GEO::rev_group(cc) ? wr : wj;
-                wstore(dst + (L1 * cc * 2) * TF, TF, cmulw(v[cc], bc(t.x), bc(t.y), bc(t.w)));
+                wstore(dst + (L1 * cc * 2) * TF, TF, cmulw(v[cc], bc(t.x), bc(t.y), bc(-t.y)));
             }
         }
     }
@@ -425,6 +435,82 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
             if (h == 0) emit2<MODE, SPEC, STAGE>(p, twp, o, MC / 2, u[RL / 2], u[RL / 2], false);
         }
     }
+    // ================= staged ("paired") last pass: one slice per lane, no partner exchange ===========
+    // Thread (w, lam): lam = tid % TF is a POSITION of the work buffer (slice sigma(lam): the pass-1
+    // lanes interleave their two slices), w selects the mirrored group pair (w, G - w) -- w = 0:
+    // (0, G/2).  The two groups ride in the two halves of one f32x2 register, so ONE packed DFT
+    // transforms both and the bins k and Mc - k of the real-FFT split (src/lib.rs:367-375 computes
+    // them with a full-length FFT) meet in the same thread: no shuffles, no selects, no redundant
+    // adds.  The finished bins overwrite the group's own work rows (TMA staging, pk_fwd_kernel).
+    static constexpr int NW2 = NT / TF;                                  // group pairs in flight
+    static constexpr int WPT2 = (G / 2 + NW2 - 1) / NW2;
+    VHD static int sigma(int lam) { return (lam & 1) ? LN + (lam >> 1) : (lam >> 1); }
+    VHD static void last_dft2(const PkFwdCtx &c, int tid, int it, C2 (&u)[RL]) {
+        const int lam = tid % TF, w = tid / TF + it * NW2;
+        if (w >= G / 2) return;
+        const float *a0 = c.work + (GEO::goff(group_of(w, 0)) * 2) * TF + lam;
+        const float *a1 = c.work + (GEO::goff(group_of(w, 1)) * 2) * TF + lam;
+#pragma unroll
+        for (int d = 0; d < RL; ++d) {
+            u[d].x = mk2(a0[(d * 2) * TF], a1[(d * 2) * TF]);
+            u[d].y = mk2(a0[(d * 2 + 1) * TF], a1[(d * 2 + 1) * TF]);
+        }
+        Dft<RL, false, f2>::run(u);
+    }
+    // one slice, one mirrored bin pair: A = Z[k]/2, B = Z[Mc-k]/2, (wr, wi) = W_M^k.
+    //   X[k] = (Ex + P, ey + Q),  X[Mc-k] = (Ex - P, Q - ey)   with
+    //   Ex = Ar + Br, Oy = Ai + Bi, ey = Ai - Bi, ox = Ar - Br, P = wi ox + wr Oy, Q = wi Oy - wr ox
+    template <int MODE, bool SPEC>
+    VHD static void put1(const FwdArgs<float> &p, char *q, int k, float re, float im) {
+        if (k == 0 || k == MC) im = 0.f;                                  // src/lib.rs:378-384
+        else if (MODE == 3) { re *= p.fac2x; im *= p.fac2x; }             // :397-403
+        if (SPEC) *reinterpret_cast<float *>(q) = re * re + im * im;
+        else { fl2 v; v.x = re; v.y = im; *reinterpret_cast<fl2 *>(q) = v; }
+    }
+    template <int MODE, bool SPEC>
+    VHD static void emit_pair(const FwdArgs<float> &p, const float *twp, char *ob, int k, float ar, float ai,
+                              float br, float bi, bool both) {
+        const fl2 t = *reinterpret_cast<const fl2 *>(twp + 4 * k);
+        const float Ex = ar + br, Oy = ai + bi, ey = ai - bi, ox = ar - br;
+        const float P = t.y * ox + t.x * Oy, Q = t.y * Oy - t.x * ox;
+        put1<MODE, SPEC>(p, ob + srow<SPEC>(k), k, Ex + P, ey + Q);
+        if (both) put1<MODE, SPEC>(p, ob + srow<SPEC>(MC - k), MC - k, Ex - P, Q - ey);
+    }
+    template <int MODE, bool SPEC>
+    VHD static void last_emit2_t(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL]) {
+        const FwdArgs<float> &p = c.a;
+        const int lam = tid % TF, w = tid / TF + it * NW2;
+        if (w >= G / 2) return;
+        char *ob = reinterpret_cast<char *>(c.work) + sigma(lam) * (SPEC ? 4 : 8);
+        const float *twp = c.tw + GEO::TWP;
+        if (w != 0) {
+            // lo half: group w, bin k = w + G d;  hi half: group G - w, holding Z[Mc - k] at index d
+            // (REVG: stored reversed by pass 1) or RL-1-d
+#pragma unroll
+            for (int d = 0; d < RL; ++d) {
+                const int dm = GEO::REVG ? d : RL - 1 - d;
+                emit_pair<MODE, SPEC>(p, twp, ob, w + G * d, lo(u[d].x), lo(u[d].y), hi(u[dm].x), hi(u[dm].y), true);
+            }
+        } else {
+            // self-mirrored groups: lo = group 0 (bin G t <-> G (RL - t)), hi = group G/2
+            // (bin G/2 + G t <-> G/2 + G (RL-1-t))
+#pragma unroll
+            for (int t = 0; t < RL / 2; ++t) {
+                const int tm = (RL - t) & (RL - 1);
+                emit_pair<MODE, SPEC>(p, twp, ob, G * t, lo(u[t].x), lo(u[t].y), lo(u[tm].x), lo(u[tm].y), true);
+                emit_pair<MODE, SPEC>(p, twp, ob, G / 2 + G * t, hi(u[t].x), hi(u[t].y), hi(u[RL - 1 - t].x),
+                                      hi(u[RL - 1 - t].y), true);
+            }
+            emit_pair<MODE, SPEC>(p, twp, ob, MC / 2, lo(u[RL / 2].x), lo(u[RL / 2].y), lo(u[RL / 2].x),
+                                  lo(u[RL / 2].y), false);
+        }
+    }
+    template <bool SPEC>
+    VHD static void last_emit2(const PkFwdCtx &c, int tid, int it, const C2 (&u)[RL]) {
+        if (c.a.mode == 3) last_emit2_t<3, SPEC>(c, tid, it, u);
+        else last_emit2_t<2, SPEC>(c, tid, it, u);
+    }
+
     // kernel variants: ONES = one-sided layouts (modes 2, 3), SPEC = |X|^2 output.  Keeping the
     // two-sided address arithmetic out of the one-sided kernels matters: the compiler hoists it.
     template <bool ONES, bool SPEC, bool STAGE = false>
