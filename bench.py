@@ -207,7 +207,7 @@ def workload_config(cfg, name):
                         f"{cfg['win']} {cfg['m']} / hop {cfg['hop']}, {cfg['mode']}, {cfg['prec']}, stft+istft",
             "batch": cfg["batch"], "n": cfg["n"], "m_num": cfg["m"], "hop": cfg["hop"],
             "fft_mode": cfg["mode"], "l2_policy": "working set (input + S) >> 126 MB L2, no flush needed",
-            "s_row_pitch": "rows padded to 32-byte sectors (ldp = ceil(P/4)*4 for f32); --dense-pitch for ldp = P"}
+            "s_row_pitch": "rows padded to 128-byte lines (ldp = ceil(P/16)*16 for f32); --dense-pitch for ldp = P"}
 
 
 def main():

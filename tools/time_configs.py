@@ -18,7 +18,7 @@ CASES = [
     ("f32 2048/512 onesided B=256x480000", hann(2048), 512, "onesided", None, "f32", 256, 480000, False),
     ("f32 256/64 onesided B=1024x160000", hann(256), 64, "onesided", None, "f32", 1024, 160000, False),
 ]
-ALIGN = "--align" in sys.argv      # pad S rows to 32-byte sectors (what veils_b200.stft does for device tensors)
+ALIGN = "--align" in sys.argv      # pad S rows to 128-byte lines (what veils_b200.stft does for device tensors)
 sel = [a for a in sys.argv[1:] if not a.startswith("--")]
 L = lib()
 dev = torch.device("cuda", 0)
@@ -30,7 +30,7 @@ for name, win, hop, mode, scale, prec, B, n, spec in CASES:
     sz = 4 if prec == "f32" else 8
     x = torch.rand((B, n), device=dev, dtype=rdt) * 2 - 1
     P, F = st.p_num(n), st.f_pts
-    q = (32 // (sz if spec else 2 * sz)) if ALIGN else 1
+    q = (128 // (sz if spec else 2 * sz)) if ALIGN else 1
     ldp = (P + q - 1) // q * q
     S = torch.empty((B, F, ldp), dtype=rdt if spec else cdt, device=dev)
     def t(fn, reps=5):

@@ -55,6 +55,12 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         c.tw = args.tw;
         c.ptab = ptab_g;
     }
+    constexpr bool SPLIT1 = STAGE && K::L1 == NSUB;
+    const unsigned drain_bar = tma::smem_u32(c.work + (size_t)K::MC * 2 * TF + PK_NYQ_ROW - 4);
+    if (SPLIT1 && tid == 0) {
+        tma::mbar_init(drain_bar, K::NT / TF);
+        tma::fence_mbar_init();
+    }
     if (tid < 2) {                         // the zero pair behind the staged span
         xin0[zero_off + tid] = 0.f;
         xin1[zero_off + tid] = 0.f;
@@ -75,7 +81,10 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
     }
     for (int it = 0; w < total; w += gridDim.x, ++it) {
         cp_async_wait_all();
-        if (STAGE) tma::wait_read_all();       // the previous tile's boxes have left the work buffer
+        // STAGE: the previous tile's boxes must have left the work buffer before pass 1 overwrites
+        // it.  One group per thread: that wait moves behind the tile reads + DFT of pass 1 (which
+        // do not touch the work buffer) and is handed to the other threads through an mbarrier.
+        if (STAGE && !SPLIT1) tma::wait_read_all();
         __syncthreads();
         float *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
         const int64_t wn = w + gridDim.x;
@@ -92,10 +101,21 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         c.pt = cpt;
         c.xin = cur;
 #ifdef VEILS_ABLATE
-        if (!(args.dbg & 4)) K::pass1(c, tid);
-#else
-        K::pass1(c, tid);
+        if (args.dbg & 4) {
+        } else
 #endif
+        if (SPLIT1) {
+            C2 v[K::R1];
+            K::pass1_in(c, tid, tid / K::LN, v);
+            if (tid % TF == 0) {
+                tma::wait_read_all();          // this thread's boxes of the previous tile
+                tma::mbar_arrive(drain_bar);
+            }
+            tma::mbar_wait(drain_bar, (unsigned)(it & 1));
+            K::pass1_out(c, tid, tid / K::LN, v);
+        } else {
+            K::pass1(c, tid);
+        }
         __syncthreads();
         if (!K::DBUF && wn < total) {
             PkFwdCtx cn = c;
@@ -115,14 +135,27 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
 #ifdef VEILS_ABLATE
                 if (args.dbg & 8) continue;
 #endif
+#ifdef VEILS_ABLATE
+                if (!(args.dbg & 16)) {        // ablation 16: only the TMA stores remain of the last pass
+#endif
                 K::last_dft2(c, tid, i, u);
                 __syncwarp();                  // the rows of a group pair belong to the threads of one warp:
                                                // all of them have read before anyone overwrites
                 K::template last_emit2<SPEC>(c, tid, i, u);
+#ifdef VEILS_ABLATE
+                }
+#endif
                 tma::fence_async_smem();
                 __syncwarp();
                 const int lam = tid % TF, wg = tid / TF + i * K::NW2;
+#ifdef VEILS_ABLATE
+                if (args.dbg & 1) continue;     // ablation: nothing leaves the SM
+#endif
                 if (lam == 0 && wg < K::G / 2) {
+                    // one box [RL rows][TF slices] per group of the pair (+ the Nyquist row with pair 0).
+                    // (1-D bulk copies, one per row, have the higher ceiling in a store-only kernel --
+                    // 6.0 vs 5.0 TB/s, profiles/r1b_store_paths.txt -- but their per-lane issue loop
+                    // costs more here than it gains.)
                     const unsigned wbase = tma::smem_u32(c.work);
                     const int p0 = (int)(cpt * TF);
                     const int g0 = K::group_of(wg, 0), g1 = K::group_of(wg, 1);

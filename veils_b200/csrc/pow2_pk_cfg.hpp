@@ -70,7 +70,8 @@ inline void pk_twiddle_fill(int64_t M, bool inverse, double *t) {
     for (int64_t i = 0; i < l1; ++i) put2(0, 1, 0, 1);
 }
 
-constexpr int PK_NYQ_ROW = 64;    // floats kept behind the work buffer: the staged Nyquist row (TMA stores)
+constexpr int PK_NYQ_ROW = 64 + 4; // floats kept behind the work buffer: the staged Nyquist row (TMA stores)
+                                   // + 16 bytes for the drain mbarrier
 template <int LOGMC, int TF>
 inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
     using G = PkGeo<LOGMC, TF, 2>;

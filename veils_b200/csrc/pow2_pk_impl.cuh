@@ -224,12 +224,25 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
     }
     template <bool PADDED>
     VHD static void pass1_t(const PkFwdCtx &c, int tid) {
-        const FwdArgs<float> &p = c.a;
-        const int l = tid % LN, sub = tid / LN;
-        const int hs = p.H + p.lay.padw;
-        const float *xf0 = c.xin + l * hs, *xf1 = xf0 + LN * hs;
+        const int sub = tid / LN;
         for (int j = sub; j < L1; j += NSUB) {
             C2 v[R1];
+            pass1_in<PADDED>(c, tid, j, v);
+            pass1_out(c, tid, j, v);
+        }
+    }
+    // pass 1 of group j, first half: tile reads, window, DFT_R1 -- does not touch the work buffer
+    VHD static void pass1_in(const PkFwdCtx &c, int tid, int j, C2 (&v)[R1]) {
+        if (c.a.padded) pass1_in<true>(c, tid, j, v);
+        else pass1_in<false>(c, tid, j, v);
+    }
+    template <bool PADDED>
+    VHD static void pass1_in(const PkFwdCtx &c, int tid, int j, C2 (&v)[R1]) {
+        const FwdArgs<float> &p = c.a;
+        const int l = tid % LN;
+        const int hs = p.H + p.lay.padw;
+        const float *xf0 = c.xin + l * hs, *xf1 = xf0 + LN * hs;
+        {
             const PTab *pj = c.ptab + j;
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
@@ -244,6 +257,12 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
                 v[a].y = mk2(x0.y * e.w1, x1.y * e.w1);
             }
             Dft<R1, false, f2>::run(v);
+        }
+    }
+    // second half: twiddle W_Mc^(j c) and the stores into the work buffer
+    VHD static void pass1_out(const PkFwdCtx &c, int tid, int j, const C2 (&v)[R1]) {
+        const int l = tid % LN;
+        {
             float *wj = c.work + (j * 2) * TF + 2 * l;
             // 2-pass plans: column cc IS last-pass group cc; reversed groups are stored at row
             // (L1 - j) mod L1 (the extra W_L1^(-j) is already in the forward tw1 table)
@@ -436,20 +455,22 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         }
     }
     // ================= staged ("paired") last pass: one slice per lane, no partner exchange ===========
-    // Thread (w, lam): lam = tid % TF is a POSITION of the work buffer (slice sigma(lam): the pass-1
-    // lanes interleave their two slices), w selects the mirrored group pair (w, G - w) -- w = 0:
+    // Thread (w, lam): lam = tid % TF is the slice, w selects the mirrored group pair (w, G - w) -- w = 0:
     // (0, G/2).  The two groups ride in the two halves of one f32x2 register, so ONE packed DFT
     // transforms both and the bins k and Mc - k of the real-FFT split (src/lib.rs:367-375 computes
     // them with a full-length FFT) meet in the same thread: no shuffles, no selects, no redundant
     // adds.  The finished bins overwrite the group's own work rows (TMA staging, pk_fwd_kernel).
     static constexpr int NW2 = NT / TF;                                  // group pairs in flight
     static constexpr int WPT2 = (G / 2 + NW2 - 1) / NW2;
-    VHD static int sigma(int lam) { return (lam & 1) ? LN + (lam >> 1) : (lam >> 1); }
+    // lane lam handles slice lam; the pass-1 lanes interleave their two slices (l, l + LN) in the
+    // work buffer, so slice lam sits at position wpos(lam).  Reads: 32 lanes on 32 distinct banks;
+    // staged stores: 32 consecutive 8-byte slots -- both conflict free.
+    VHD static int wpos(int lam) { return lam < LN ? 2 * lam : 2 * (lam - LN) + 1; }
     VHD static void last_dft2(const PkFwdCtx &c, int tid, int it, C2 (&u)[RL]) {
         const int lam = tid % TF, w = tid / TF + it * NW2;
         if (w >= G / 2) return;
-        const float *a0 = c.work + (GEO::goff(group_of(w, 0)) * 2) * TF + lam;
-        const float *a1 = c.work + (GEO::goff(group_of(w, 1)) * 2) * TF + lam;
+        const float *a0 = c.work + (GEO::goff(group_of(w, 0)) * 2) * TF + wpos(lam);
+        const float *a1 = c.work + (GEO::goff(group_of(w, 1)) * 2) * TF + wpos(lam);
 #pragma unroll
         for (int d = 0; d < RL; ++d) {
             u[d].x = mk2(a0[(d * 2) * TF], a1[(d * 2) * TF]);
@@ -481,7 +502,7 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         const FwdArgs<float> &p = c.a;
         const int lam = tid % TF, w = tid / TF + it * NW2;
         if (w >= G / 2) return;
-        char *ob = reinterpret_cast<char *>(c.work) + sigma(lam) * (SPEC ? 4 : 8);
+        char *ob = reinterpret_cast<char *>(c.work) + lam * (SPEC ? 4 : 8);
         const float *twp = c.tw + GEO::TWP;
         if (w != 0) {
             // lo half: group w, bin k = w + G d;  hi half: group G - w, holding Z[Mc - k] at index d
