@@ -101,7 +101,7 @@ struct EmuPkFwd {
         pk_ptab_fill(prm.M, prm.N, prm.H, prm.ps, pl->win.data(), TF, ptab.data());
         PkFwdCtx c;
         c.a = make_fwd_args<float>((const float *)x, out, prm, nullptr, tw.data(), TF);
-        std::vector<fl4> work((size_t)K::MC * 2 * TF / 4 + 4);
+        std::vector<fl4> work((size_t)K::MC * 2 * TF / 4 + TF / 2 + 4);      // + staged Nyquist row
         std::vector<fl4> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay) / 4 + 4);
         c.work = (float *)work.data(); c.xin = (float *)xin.data(); c.tw = tw.data(); c.ptab = ptab.data();
         const int zo = pk_zero_off(prm.N, prm.H, TF);
@@ -114,6 +114,40 @@ struct EmuPkFwd {
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
+            if (prm.mode >= 2) {
+                // staged path of pk_fwd_kernel (one-sided layouts): paired last pass writes the finished
+                // bins over its own work rows; the TMA boxes are replayed here as clipped row copies
+                const int esz = prm.spectrogram ? 4 : 8;
+                for (int i = 0; i < K::WPT2; ++i) {
+                    for (int t = 0; t < K::NT; ++t) {
+                        C2 u[K::RL];
+                        K::last_dft2(c, t, i, u);
+                        std::memcpy(&regs[(size_t)t * K::RL], u, sizeof(u));
+                    }
+                    for (int t = 0; t < K::NT; ++t) {
+                        C2 u[K::RL];
+                        std::memcpy(u, &regs[(size_t)t * K::RL], sizeof(u));
+                        if (prm.spectrogram) K::template last_emit2<true>(c, t, i, u);
+                        else K::template last_emit2<false>(c, t, i, u);
+                    }
+                    for (int wg = i * K::NW2; wg < (i + 1) * K::NW2 && wg < K::G / 2; ++wg) {
+                        for (int h = 0; h < 2; ++h) {
+                            const int g = K::group_of(wg, h);
+                            for (int d = 0; d < K::RL + (g == 0 ? 1 : 0); ++d) {
+                                const int f = g + K::G * d;
+                                const char *src = (const char *)c.work + (d == K::RL ? (size_t)K::MC * TF * 8
+                                                  : (size_t)K::GEO::goff(g) * TF * 8 + (size_t)d * TF * esz);
+                                for (int sl = 0; sl < TF; ++sl) {
+                                    const int64_t pcol = c.pt * TF + sl;
+                                    if (pcol >= prm.P) continue;
+                                    char *dst = (char *)out + (((size_t)c.b * prm.F + f) * prm.ldp + pcol) * esz;
+                                    std::memcpy(dst, src + (size_t)sl * esz, esz);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else
             for (int i = 0; i < K::WPT; ++i) {
                 for (int t = 0; t < K::NT; ++t) {
                     C2 u[K::RL];
@@ -171,6 +205,10 @@ struct EmuPkInv {
                 c.carry_in = flip ? carry1.data() : carry0.data();
                 c.carry_out = flip ? carry0.data() : carry1.data();
                 flip ^= 1;
+                if (prm.mode >= 2) {           // paired pass 1 of pk_inv_kernel (one-sided layouts)
+                    for (int i = 0; i < K::WPT2; ++i)
+                        for (int tt = 0; tt < K::NT; ++tt) K::p1p(c, tt, i);
+                } else
                 for (int i = 0; i < K::WPT; ++i) {
                     for (int tt = 0; tt < K::NT; ++tt) {
                         Raw xr[K::R1]; Raw xn;

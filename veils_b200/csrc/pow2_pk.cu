@@ -224,6 +224,15 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
             c.carry_in = flip ? carry1 : carry0;
             c.carry_out = flip ? carry0 : carry1;
             flip ^= 1;
+            if (ONES && !(args.dbg & 64)) {
+#pragma unroll 1
+                for (int i = 0; i < K::WPT2; ++i) {
+#ifdef VEILS_ABLATE
+                    if (args.dbg & 16) continue;
+#endif
+                    K::p1p(c, tid, i);
+                }
+            } else
 #pragma unroll 1
             for (int i = 0; i < K::WPT; ++i) {
                 Raw x[K::R1];

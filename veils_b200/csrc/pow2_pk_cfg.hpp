@@ -26,7 +26,7 @@ inline int64_t pk_twiddle_count(int64_t M) {          // floats
     int np, r1, r2, r3;
     fac_of(c.logmc, &np, &r1, &r2, &r3);
     const int64_t mc = M / 2, l1 = mc / r1;
-    return 4 * (3 * mc + 2 * l1 + 1);
+    return 4 * (3 * mc + 2 * l1 + 1 + mc / 2);
 }
 // entries (wr, wi, -wr, -wi), w = product of unit roots exp(-2 pi i m / n):
 //   [tw1: MC  at j*R1+c ][tw2: L1 at j2*R2+c2][twp: W_M^k, k <= Mc][tw1x: MC][tw2x: L1]
@@ -68,6 +68,16 @@ inline void pk_twiddle_fill(int64_t M, bool inverse, double *t) {
             else put2(0, 1, 0, 1);
         }
     for (int64_t i = 0; i < l1; ++i) put2(0, 1, 0, 1);
+    // tw1p (paired inverse pass 1): (Re W^(j0 c), Re W^(j1 c), Im W^(j0 c), Im W^(j1 c)), W = W_Mc
+    for (int64_t w = 0; w < l1 / 2; ++w)
+        for (int64_t cc = 0; cc < r1; ++cc) {
+            const int64_t j0 = w, j1 = w == 0 ? l1 / 2 : l1 - w;
+            double a, b, cr, ci;
+            tw_exact(j0 * cc, mc, &a, &b);
+            tw_exact(j1 * cc, mc, &cr, &ci);
+            p[0] = a; p[1] = cr; p[2] = b; p[3] = ci;
+            p += 4;
+        }
 }
 
 constexpr int PK_NYQ_ROW = 64 + 4; // floats kept behind the work buffer: the staged Nyquist row (TMA stores)

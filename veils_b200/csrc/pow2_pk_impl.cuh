@@ -43,8 +43,11 @@ struct PkGeo {
     // twiddle table: entries of 4 floats (wr, wi, -wr, -wi):
     //   [tw1: MC][tw2: L1][twp: MC + 1][tw1x: MC][tw2x: L1]   (pow2_pk_cfg.hpp: separate forward and
     //   inverse tables; the x-tables serve the "reversed" groups of the second warp halves)
+    //   [tw1p: MC/2]  inverse, paired pass 1: (Re W^(j0 c), Re W^(j1 c), Im W^(j0 c), Im W^(j1 c)),
+    //                 W = W_Mc, for the group pair (j0, j1) of w = 0 .. L1/2-1 at entry w*R1 + c
     static constexpr int TW1 = 0, TW2 = 4 * MC, TWP = 4 * (MC + L1), TW1X = 4 * (2 * MC + L1 + 1),
-                         TW2X = 4 * (3 * MC + L1 + 1), TWN = 4 * (3 * MC + 2 * L1 + 1);
+                         TW2X = 4 * (3 * MC + L1 + 1), TW1P = 4 * (3 * MC + 2 * L1 + 1),
+                         TWN = 4 * (3 * MC + 2 * L1 + 1 + MC / 2);
     // last-pass groups > G/2 are handled by the second halves (h = 1) of the warp row pairs: they
     // need their DFT outputs in REVERSED order (their partner's u[d] mirrors their u[RL-1-d]).
     // DFT(y)[e] = X[RL-1-e] for y[n] = x[(-n) mod RL] W_RL^n, so the producer pass stores such a
@@ -765,6 +768,118 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             wq += wstep;
             const fl4 t = GEO::tw4(twj + 4 * cc);
             wstore(wq, TF, cmulwc(v[cc], bc(t.x), bc(t.y), bc(t.w)));
+        }
+    }
+
+    // ================= paired pass 1 (one-sided layouts): one slice per lane, no partner exchange =====
+    // Thread (w, lam): slice lam of the tile, mirrored group pair (j0, j1) = (w, L1 - w), w = 0:
+    // (0, L1/2).  It loads the 2 R1 bins of both groups for its slice -- a warp reads one 256-byte
+    // row run per instruction -- merges each mirrored bin pair (k, Mc - k) ONCE (src/lib.rs:428-453
+    // builds the full Hermitian spectrum instead), and runs one packed IDFT over both groups: group
+    // j0 rides in the low halves of the f32x2 registers, group j1 in the high halves.
+    static constexpr int NW2 = NT / TF;
+    static constexpr int WPT2 = (L1 / 2 + NW2 - 1) / NW2;
+    VHD static int wpos(int lam) { return lam < LN ? 2 * lam : 2 * (lam - LN) + 1; }
+    struct Cp { float r, i; };
+    template <int MODE, bool LIVE>
+    VHD static Cp ldbin(const InvArgs<float> &p, const char *q, int k) {
+        Cp v; v.r = 0.f; v.i = 0.f;
+        if (LIVE) {
+#ifdef VEILS_ABLATE
+            if (p.dbg & 1) { v.r = 1.f + k; v.i = 0.5f; return v; }      // ablation: no global loads
+#endif
+            const fl2 t = ldS(q);
+            v.r = t.x; v.i = t.y;
+            if (MODE == 3 && k >= 1 && k <= MC - 1) { v.r *= p.rfac2x; v.i *= p.rfac2x; }
+        }
+        return v;
+    }
+    // Z'[k] -> (zr, zi), Z'[Mc-k] -> (mr, mi) from A = X[k], B = X[Mc-k], (wr, wi) = W_M^k
+    VHD static void merge_pair(fl2 t, Cp A, Cp B, float &zr, float &zi, float &mr, float &mi) {
+        const float Ex = A.r + B.r, Dy = A.i + B.i, ey = A.i - B.i, dx = A.r - B.r;
+        const float P = t.x * Dy - t.y * dx, Q = t.x * dx + t.y * Dy;
+        zr = Ex - P; zi = ey + Q;
+        mr = Ex + P; mi = Q - ey;
+    }
+    template <int MODE, bool LIVE>
+    VHD static void p1p_t(const PkInvCtx &c, int tid, int it, const char *sb) {
+        const InvArgs<float> &p = c.a;
+        const int lam = tid % TF, w = tid / TF + it * NW2;
+        if (w >= L1 / 2) return;
+        const int j0 = w, j1 = w == 0 ? L1 / 2 : L1 - w;
+        const int64_t rb = p.ldp * 8;
+        Cp x0[R1], x1[R1];
+        {
+            const char *q0 = sb + j0 * rb, *q1 = sb + j1 * rb;
+            const int64_t st = L1 * rb;
+#pragma unroll
+            for (int a = 0; a < R1; ++a) {
+                x0[a] = ldbin<MODE, LIVE>(p, q0, j0 + L1 * a);
+                x1[a] = ldbin<MODE, LIVE>(p, q1, j1 + L1 * a);
+                q0 += st;
+                keep(q0);
+                q1 += st;
+                keep(q1);
+            }
+        }
+        const float *twp = c.tw + GEO::TWP;
+        float lr[R1], li[R1], hr[R1], hi_[R1];
+        if (w != 0) {
+            // bin k = j0 + L1 a  <->  Mc - k = j1 + L1 (R1-1-a)
+#pragma unroll
+            for (int a = 0; a < R1; ++a)
+                merge_pair(GEO::tw2(twp + 4 * (j0 + L1 * a)), x0[a], x1[R1 - 1 - a], lr[a], li[a], hr[R1 - 1 - a], hi_[R1 - 1 - a]);
+        } else {
+            // group 0: bin L1 a <-> L1 (R1 - a), DC <-> Nyquist (their imaginary parts are ignored,
+            // irfft semantics); group L1/2: bin L1/2 + L1 a <-> L1/2 + L1 (R1-1-a)
+            const Cp xn = ldbin<MODE, LIVE>(p, sb + MC * rb, MC);
+            lr[0] = x0[0].r + xn.r;
+            li[0] = x0[0].r - xn.r;
+#pragma unroll
+            for (int a = 1; a < R1 / 2; ++a)
+                merge_pair(GEO::tw2(twp + 4 * (L1 * a)), x0[a], x0[R1 - a], lr[a], li[a], lr[R1 - a], li[R1 - a]);
+            {
+                float mr, mi;
+                merge_pair(GEO::tw2(twp + 4 * (MC / 2)), x0[R1 / 2], x0[R1 / 2], lr[R1 / 2], li[R1 / 2], mr, mi);
+            }
+#pragma unroll
+            for (int a = 0; a < R1 / 2; ++a)
+                merge_pair(GEO::tw2(twp + 4 * (j1 + L1 * a)), x1[a], x1[R1 - 1 - a], hr[a], hi_[a], hr[R1 - 1 - a], hi_[R1 - 1 - a]);
+        }
+        C2 v[R1];
+#pragma unroll
+        for (int a = 0; a < R1; ++a) {
+            v[a].x = mk2(lr[a], hr[a]);
+            v[a].y = mk2(li[a], hi_[a]);
+        }
+        Dft<R1, true, f2>::run(v);
+        // twiddle W_Mc^(-j c) (each half its own group) and the stores: group j output c goes to
+        // work row j + L1 c, planar [re: TF][im: TF], slice lam at position wpos(lam)
+        float *w0 = c.work + (j0 * 2) * TF + wpos(lam), *w1 = c.work + (j1 * 2) * TF + wpos(lam);
+        const float *tq = c.tw + GEO::TW1P + 4 * w * R1;
+        w0[0] = lo(v[0].x); w0[TF] = lo(v[0].y);
+        w1[0] = hi(v[0].x); w1[TF] = hi(v[0].y);
+#pragma unroll
+        for (int cc = 1; cc < R1; ++cc) {
+            const fl4 t = GEO::tw4(tq + 4 * cc);
+            const f2 wr = mk2(t.x, t.y), wi = mk2(t.z, t.w);
+            const C2 z = cmulwc(v[cc], wr, wi, bc(0.f) - wi);
+            w0[(L1 * cc * 2) * TF] = lo(z.x); w0[(L1 * cc * 2 + 1) * TF] = lo(z.y);
+            w1[(L1 * cc * 2) * TF] = hi(z.x); w1[(L1 * cc * 2 + 1) * TF] = hi(z.y);
+        }
+    }
+    VHD static void p1p(const PkInvCtx &c, int tid, int it) {
+        const InvArgs<float> &p = c.a;
+        const int lam = tid % TF;
+        const int64_t q = c.qa + lam, col = q - p.p_min;
+        const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+        const char *sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + col) * 8;
+        if (p.mode == 3) {
+            if (live) p1p_t<3, true>(c, tid, it, sb);
+            else p1p_t<3, false>(c, tid, it, sb);
+        } else {
+            if (live) p1p_t<2, true>(c, tid, it, sb);
+            else p1p_t<2, false>(c, tid, it, sb);
         }
     }
 
