@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--dense-pitch", action="store_true", help="S row pitch ldp = P (reference-dense)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="sub-batches per e2e step")
+    ap.add_argument("--e2e-streams", type=int, default=3)
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
@@ -345,11 +347,11 @@ def main():
     # ---- e2e: host (pinned) -> device -> stft -> istft -> host (pinned), public tensor API ----
     e2e = None
     if not args.no_e2e:
-        chunk = max(1, B // 8)
+        chunk = max(1, -(-B // args.e2e_chunks))
         xh = torch.empty((B, n), dtype=x.dtype, pin_memory=True)
         xh.copy_(x)
         yh = torch.empty((B, n_out), dtype=x.dtype, pin_memory=True)
-        streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        streams = [torch.cuda.Stream(dev) for _ in range(args.e2e_streams)]
 
         def e2e_step():
             for i, a in enumerate(range(0, B, chunk)):
@@ -380,7 +382,7 @@ def main():
                "d2h_bytes_per_step": int(yh.numel() * yh.element_size()),
                "ms_per_step": dt * 1e3, "steps": k,
                "note": "x pinned host -> H2D -> stft -> istft -> D2H reconstructed signal; "
-                       "S stays in HBM; 8 sub-batches on 3 streams"}
+                       f"S stays in HBM; {args.e2e_chunks} sub-batches on {args.e2e_streams} streams"}
         e2e["recon_max_abs_err"] = float((yh[:, :n] - xh).abs().max().item())
 
     # ---- cpu_baseline + parity of a sample against the reference's CPU path (rank 0, N = 1) ----
