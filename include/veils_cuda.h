@@ -133,6 +133,18 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
                         const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
                         void *stream);
 
+/* stft with the twin's border handling (python/standalone_stft.py:309-336; the Rust crate pads
+ * with zeros only, src/lib.rs:631-645): padding = NULL | "zeros" | "edge" | "even" | "odd".
+ * For the non-zero modes the signal is first extended on the device into the caller's workspace
+ * x_ext (batch rows of ext_pitch >= n_ext elements; sizes from veils_pad_extent), then transformed
+ * by the same kernels.  spectrogram != 0 writes |S|^2 (real) instead. */
+int32_t veils_pad_extent(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t *p1,
+                         int64_t k_offset, int64_t *left, int64_t *n_ext);
+int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                              const int64_t *p0, const int64_t *p1, int64_t k_offset,
+                              const char *padding, void *x_ext, int64_t ext_pitch, void *S,
+                              int64_t ldp, void *stream, int32_t spectrogram);
+
 /* ---- compute: host pointers (drop-in for the Vec API; copies inside) ------------------- */
 /* Also performs the reference's NaN scan for one-sided modes (src/lib.rs:696-698).
  * S is dense: ldp == P.  Synchronous. */

@@ -4,6 +4,7 @@ features the reference lacks).  TEST INFRASTRUCTURE -- runs only in the build co
 where /root/reference exists; the fixtures it writes are committed and travel to the GPU box.
 
     python oracle/make_golden.py            # rewrites tests/golden/
+    python oracle/make_golden.py padding    # rewrites only the named fixture(s)
 
 Sources of truth used here (nothing is copied from the reference, it is imported/executed):
   * /root/reference/python/standalone_stft.py  -- StandaloneSTFT (twin of src/lib.rs)
@@ -53,7 +54,12 @@ def run_twin(Twin, win, hop, fs, mode, x, mfft=None, phase_shift=0, dual_win=Non
     return rec
 
 
+ONLY = set(sys.argv[1:])
+
+
 def save(name, recs):
+    if ONLY and name not in ONLY:
+        return
     flat = {}
     for i, r in enumerate(recs):
         for k, v in r.items():
@@ -182,6 +188,21 @@ def main():
                          win_scaled=st.win, dual=st.dual_win, p_min=st.p_min,
                          p_max=st.p_max(len(x))))
     save("scipy_scaling", recs)
+
+    # 7. the twin's border modes (python/standalone_stft.py:309-336; not in the Rust crate)
+    recs = []
+    prng = np.random.default_rng(7)
+    for (m, hop, mfft, mode, n, koff) in [(16, 4, 16, "onesided", 64, 0), (15, 5, 20, "twosided", 47, 0),
+                                          (32, 8, 32, "centered", 100, 3), (24, 6, 32, "onesided2X", 90, -2),
+                                          (64, 16, 64, "onesided", 300, 0), (12, 12, 12, "onesided", 40, 0)]:
+        win = hann_periodic(m) + 0.05
+        x = prng.standard_normal(n)
+        for padding in ("zeros", "edge", "even", "odd"):
+            tw = Twin(win=win, hop=hop, fs=2.0, fft_mode=mode, mfft=mfft)
+            S = tw.stft(x, k_offset=koff, padding=padding)
+            recs.append(dict(win=win, hop=hop, fs=2.0, mode=mode, mfft=mfft, x=x, k_offset=koff,
+                             padding=padding, S=S, p_min=tw.p_min, p_max=tw.p_max(n)))
+    save("padding", recs)
 
 
 if __name__ == "__main__":

@@ -221,13 +221,25 @@ class OracleSTFT:
         return p0, p1
 
     # -- forward: x_slices + window + fft_func + transpose (src/lib.rs:612-749) -----------
-    def _frames(self, x, p0, p1, k_offset):
-        """All frames p0..p1 as a (P, m_num) array, zeros outside [0, n) (lib.rs:612-652)."""
+    def _frames(self, x, p0, p1, k_offset, padding="zeros"):
+        """All frames p0..p1 as a (P, m_num) array, zeros outside [0, n) (lib.rs:612-652).
+        padding 'edge' | 'even' | 'odd': the twin's border values (python/standalone_stft.py:309-336;
+        absent from the Rust crate): edge x[0] / x[n-1]; even x[min(-s, n-1)] left of 0 and
+        x[clamp(2n-2-s)] right of n-1; odd the negative of even."""
         n = len(x)
         starts = np.arange(p0, p1, dtype=np.int64) * self.hop + k_offset - self.m_num_mid
         idx = starts[:, None] + np.arange(self.m_num, dtype=np.int64)[None, :]
         ok = (idx >= 0) & (idx < n)
-        return np.where(ok, x[np.clip(idx, 0, n - 1)], 0.0)
+        inside = x[np.clip(idx, 0, n - 1)]
+        if padding == "zeros":
+            return np.where(ok, inside, 0.0)
+        if padding == "edge":
+            return inside
+        if padding not in ("even", "odd"):
+            raise ValueError(f"Parameter padding='{padding}' not in ['zeros', 'edge', 'even', 'odd']!")
+        mirror = np.where(idx < 0, np.minimum(-idx, n - 1), np.clip(2 * n - 2 - idx, 0, n - 1))
+        pad = x[np.clip(mirror, 0, n - 1)]
+        return np.where(ok, inside, pad if padding == "even" else -pad)
 
     def _fft_func(self, y):
         """Rows of y (P, m_num) -> (P, f_pts).  src/lib.rs:336-411."""
@@ -245,7 +257,7 @@ class OracleSTFT:
             X[..., 1:(-1 if M % 2 == 0 else None)] *= self._fac2x
         return X
 
-    def stft(self, x, p0=None, p1=None, k_offset=0):
+    def stft(self, x, p0=None, p1=None, k_offset=0, padding="zeros"):
         """src/lib.rs:689-749.  Returns S[f_pts][P] complex128."""
         x = np.asarray(x, dtype=np.float64)
         if self.onesided_fft and np.any(np.isnan(x)):
@@ -259,7 +271,7 @@ class OracleSTFT:
         chunk = max(1, (1 << 22) // max(self.mfft, 1))        # bound temporaries
         for a in range(p0, p1, chunk):
             b = min(p1, a + chunk)
-            y = self._frames(x, a, b, k_offset) * self.win[None, :]
+            y = self._frames(x, a, b, k_offset, padding) * self.win[None, :]
             S[:, a - p0:b - p0] = self._fft_func(y).T
         return S
 

@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libveils_cuda.so")
-SOURCES = ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu"]
+CLI = os.path.join(HERE, "veils_comparison_helper")          # csrc/cli/comparison_helper.cpp
+SOURCES = ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu", "pad.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--use_fast_math=false"]
 
@@ -25,7 +26,10 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if not os.path.exists(CLI):
+        return True
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if os.path.isfile(os.path.join(CSRC, f))]
+    deps.append(os.path.join(CSRC, "cli", "comparison_helper.cpp"))
     deps.append(os.path.join(HERE, "..", "include", "veils_cuda.h"))
     deps.append(os.path.abspath(__file__))
     return any(os.path.getmtime(d) > t for d in deps)
@@ -58,6 +62,13 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    # the comparison-helper CLI (reference: src/bin/python_rust_comparison_helper.rs) links the C ABI
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI, os.path.join(CSRC, "cli", "comparison_helper.cpp"),
+           "-L" + HERE, "-l:libveils_cuda.so", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("CLI build failed")
     if verbose:
         print("\n".join(log))
     return LIB

@@ -364,6 +364,59 @@ int32_t veils_spectrogram_dev(veils_plan *p, const void *x, int64_t n, int64_t b
     return forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, Sxx, ldp, stream, 1);
 }
 
+static int padding_mode(const char *padding) {
+    if (!padding || !strcmp(padding, "zeros")) return 0;
+    if (!strcmp(padding, "edge")) return 1;
+    if (!strcmp(padding, "even")) return 2;
+    if (!strcmp(padding, "odd")) return 3;
+    return -1;
+}
+
+int32_t veils_pad_extent(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t *p1, int64_t k_offset,
+                         int64_t *left, int64_t *n_ext) {
+    if (!p || !left || !n_ext) return fail(VEILS_ERR_INVALID, "null argument");
+    const Plan &pl = p->pl;
+    int64_t a, b;
+    std::string e = plan_p_range(pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    const int64_t lo = a * pl.H + k_offset - pl.mid, hi = (b - 1) * pl.H + k_offset - pl.mid + pl.N;
+    const int64_t l = lo < 0 ? -lo : 0, r = hi > n ? hi - n : 0;
+    *left = l;
+    *n_ext = l + n + r;
+    return VEILS_OK;
+}
+
+int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                              const int64_t *p0, const int64_t *p1, int64_t k_offset, const char *padding,
+                              void *x_ext, int64_t ext_pitch, void *S, int64_t ldp, void *stream, int32_t spectrogram) {
+    if (!p || !x || !S) return fail(VEILS_ERR_INVALID, "null argument");
+    const int mode = padding_mode(padding);
+    if (mode < 0) return fail(VEILS_ERR_INVALID, std::string("Parameter padding='") + padding + "' not in ['zeros', 'edge', 'even', 'odd']!");
+    if (mode == 0) return forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, S, ldp, stream, spectrogram ? 1 : 0);
+    Plan &pl = p->pl;
+    const int64_t m2p = pl.N - pl.mid;
+    if (n < m2p)
+        return fail(VEILS_ERR_INVALID, "Input length " + std::to_string((long long)n) +
+                                           " must be >= ceil(m_num/2) = " + std::to_string((long long)m2p));
+    int64_t a, b, left, n_ext;
+    std::string e = plan_p_range(pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    int32_t rc = veils_pad_extent(p, n, p0, p1, k_offset, &left, &n_ext);
+    if (rc != VEILS_OK) return rc;
+    if (!x_ext) return fail(VEILS_ERR_INVALID, "x_ext workspace required for padding != 'zeros' (size: veils_pad_extent)");
+    if (ext_pitch < n_ext) return fail(VEILS_ERR_INVALID, "ext_pitch must be >= n_ext");
+    if (x_pitch < n) return fail(VEILS_ERR_INVALID, "x_pitch must be >= n");
+    if (batch <= 0) return batch == 0 ? VEILS_OK : fail(VEILS_ERR_INVALID, "batch must be >= 0");
+    rc = ensure_device(pl, false);
+    if (rc != VEILS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = pl.precision == F32
+                         ? pad_signal<float>((const float *)x, (float *)x_ext, n, batch, x_pitch, left, n_ext, ext_pitch, mode, st)
+                         : pad_signal<double>((const double *)x, (double *)x_ext, n, batch, x_pitch, left, n_ext, ext_pitch, mode, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "pad launch");
+    return forward_impl(p, x_ext, n_ext, batch, ext_pitch, &a, &b, k_offset + left, S, ldp, stream, spectrogram ? 1 : 0);
+}
+
 int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,
                         const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
                         void *stream) {

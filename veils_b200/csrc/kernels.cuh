@@ -76,4 +76,9 @@ void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double
 cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st);
 cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const Tables<float> &tb, cudaStream_t st);
 
+// ---- border extension for the twin's padding modes (pad.cu): mode 0 zeros, 1 edge, 2 even, 3 odd
+template <typename T>
+cudaError_t pad_signal(const T *x, T *x_ext, int64_t n, int64_t batch, int64_t x_pitch, int64_t left, int64_t n_ext,
+                       int64_t ext_pitch, int mode, cudaStream_t st);
+
 }  // namespace veils

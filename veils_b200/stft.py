@@ -159,10 +159,21 @@ class StandaloneSTFT:
     def _is_tensor(x):
         return type(x).__module__.startswith("torch")
 
-    def _fwd(self, x, p0, p1, k_offset, spectrogram):
+    PADDINGS = ("zeros", "edge", "even", "odd")
+
+    def _fwd(self, x, p0, p1, k_offset, spectrogram, padding="zeros"):
+        if padding not in self.PADDINGS:
+            raise VeilsError(_lib.ERR_INVALID, f"Parameter padding='{padding}' not in {list(self.PADDINGS)}!")
         if self._is_tensor(x):
-            return self._fwd_tensor(x, p0, p1, k_offset, spectrogram)
+            return self._fwd_tensor(x, p0, p1, k_offset, spectrogram, padding)
         x = np.asarray(x)
+        if padding != "zeros":
+            # the border extension runs on the device (veils_stft_dev_padded): stage through torch
+            import torch
+            if np.iscomplexobj(x):
+                raise VeilsError(_lib.ERR_INVALID, "Complex-valued input not allowed (real input only)")
+            xt = torch.from_numpy(np.ascontiguousarray(x, dtype=self._rdt)).cuda(self.device)
+            return self._fwd_tensor(xt, p0, p1, k_offset, spectrogram, padding).cpu().numpy()
         if np.iscomplexobj(x):
             raise VeilsError(_lib.ERR_INVALID, "Complex-valued input not allowed (real input only)")
         squeeze = x.ndim == 1
@@ -179,7 +190,7 @@ class StandaloneSTFT:
                   out.ctypes.data))
         return out[0] if squeeze else out
 
-    def _fwd_tensor(self, x, p0, p1, k_offset, spectrogram):
+    def _fwd_tensor(self, x, p0, p1, k_offset, spectrogram, padding="zeros"):
         import torch
         tdt = torch.float32 if self.precision == "f32" else torch.float64
         if not x.is_cuda or x.dtype != tdt:
@@ -205,20 +216,33 @@ class StandaloneSTFT:
         else:
             out = torch.empty((batch, self.f_pts, ldp), device=x.device,
                               dtype=torch.complex64 if self.precision == "f32" else torch.complex128)
-        fn = self._L.veils_spectrogram_dev if spectrogram else self._L.veils_stft_dev
         st = torch.cuda.current_stream(x.device).cuda_stream
+        if padding != "zeros":
+            left, n_ext = C.c_int64(0), C.c_int64(0)
+            _check(self._L.veils_pad_extent(self._h, n, opt_i64(a), opt_i64(b), int(k_offset),
+                                            C.byref(left), C.byref(n_ext)))
+            xe = torch.empty((batch, n_ext.value), dtype=tdt, device=x.device)
+            _check(self._L.veils_stft_dev_padded(self._h, x2.data_ptr(), n, batch,
+                                                 x2.stride(0) if batch > 1 else n, opt_i64(a), opt_i64(b),
+                                                 int(k_offset), padding.encode(), xe.data_ptr(), n_ext.value,
+                                                 out.data_ptr(), ldp, st, 1 if spectrogram else 0))
+            out = out[:, :, :P]
+            return out[0] if squeeze else out
+        fn = self._L.veils_spectrogram_dev if spectrogram else self._L.veils_stft_dev
         _check(fn(self._h, x2.data_ptr(), n, batch, x2.stride(0) if batch > 1 else n, opt_i64(a),
                   opt_i64(b), int(k_offset), out.data_ptr(), ldp, st))
         out = out[:, :, :P]
         return out[0] if squeeze else out
 
-    def stft(self, x, p0=None, p1=None, *, k_offset=0):
-        """src/lib.rs:689-749 -> S[f_pts][P] (or [batch][f_pts][P] for 2-d input)."""
-        return self._fwd(x, p0, p1, k_offset, False)
+    def stft(self, x, p0=None, p1=None, *, k_offset=0, padding="zeros"):
+        """src/lib.rs:689-749 -> S[f_pts][P] (or [batch][f_pts][P] for 2-d input).
+        padding: 'zeros' (the Rust crate's only mode) or the twin's 'edge' | 'even' | 'odd'
+        (python/standalone_stft.py:309-336)."""
+        return self._fwd(x, p0, p1, k_offset, False, padding)
 
-    def spectrogram(self, x, p0=None, p1=None, *, k_offset=0):
+    def spectrogram(self, x, p0=None, p1=None, *, k_offset=0, padding="zeros"):
         """scipy ShortTimeFFT.spectrogram: |stft(x)|^2, real."""
-        return self._fwd(x, p0, p1, k_offset, True)
+        return self._fwd(x, p0, p1, k_offset, True, padding)
 
     def istft(self, S, k0=None, k1=None):
         """src/lib.rs:792-914 -> real signal of length k1-k0 (default k0=0, k1=k_max of S)."""
