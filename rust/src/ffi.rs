@@ -63,6 +63,12 @@ extern "C" {
     pub fn veils_stft_dev(p: *mut veils_plan, x: *const c_void, n: i64, batch: i64, x_pitch: i64,
                           p0: *const i64, p1: *const i64, k_offset: i64, s: *mut c_void, ldp: i64,
                           stream: *mut c_void) -> i32;
+    pub fn veils_pad_extent(p: *const veils_plan, n: i64, p0: *const i64, p1: *const i64, k_offset: i64,
+                            left: *mut i64, n_ext: *mut i64) -> i32;
+    pub fn veils_stft_dev_padded(p: *mut veils_plan, x: *const c_void, n: i64, batch: i64, x_pitch: i64,
+                                 p0: *const i64, p1: *const i64, k_offset: i64, padding: *const c_char,
+                                 x_ext: *mut c_void, ext_pitch: i64, s: *mut c_void, ldp: i64,
+                                 stream: *mut c_void, spectrogram: i32) -> i32;
     pub fn veils_istft_dev(p: *mut veils_plan, s: *const c_void, cols: i64, batch: i64, ldp: i64,
                            k0: *const i64, k1: *const i64, x_out: *mut c_void, out_pitch: i64,
                            stream: *mut c_void) -> i32;
