@@ -43,11 +43,21 @@ def _worker(rank, world, port, q):
         # public API on the sub-signal: slice indices stay global through k_offset
         Sl = o.stft(sub, sh.p_a, sh.p_b, sh.k_offset)
         Sg = sharding.gather_frames(torch.from_numpy(np.ascontiguousarray(Sl)), o.p_num(n), dist, rank, world)
+        # (3) inverse of the long signal: slice shards + one neighbour exchange of halo columns
+        P = o.p_num(n)
+        shards = [sharding.inverse_shard(P, o.m_num, o.hop, o.p_min, r, world) for r in range(world)]
+        me = shards[rank]
+        nxt = shards[rank + 1].halo_cols if rank + 1 < world else 0
+        Sext = sharding.exchange_halo_columns(torch.from_numpy(np.ascontiguousarray(Sl)), nxt, me.halo_cols,
+                                              dist, rank, world)
+        yl = o.istft(Sext.numpy(), me.k0_local, me.k1_local)
+        yg = sharding.gather_samples(torch.from_numpy(yl), 0, shards[-1].k_b, shards, dist, rank, world)
         if rank == 0:
             ref_rows = np.stack([o.stft(r) for r in x])
             ref_long = o.stft(xl)
+            ref_y = o.istft(ref_long)
             q.put((float(np.max(np.abs(S.numpy() - ref_rows))), float(np.max(np.abs(Sg.numpy() - ref_long))),
-                   sh.halo))
+                   sh.halo, yg.shape[0] == ref_y.shape[0] and float(np.max(np.abs(yg.numpy() - ref_y)))))
     finally:
         dist.destroy_process_group()
 
@@ -62,10 +72,11 @@ def test_row_and_frame_sharding_world2():
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
-    e_rows, e_long, halo = q.get(timeout=10)
+    e_rows, e_long, halo, e_inv = q.get(timeout=10)
     assert e_rows == 0.0
     assert e_long == 0.0          # identical arithmetic on identical frames -> bit exact
     assert halo == 64 - 16
+    assert e_inv is not False and e_inv == 0.0   # same increasing-q overlap-add order -> bit exact
 
 
 def test_partition_properties():
@@ -81,6 +92,39 @@ def test_partition_properties():
     for r in range(7):
         assert sh[r].p_b == sh[r + 1].p_a
         assert sh[r].s_b - sh[r + 1].s_a == m - hop
+
+
+def test_inverse_shards_tile_the_output():
+    for world in (1, 2, 3, 8):
+        for (P, m, hop, p_min) in [(316, 64, 16, -2), (1253, 512, 128, -1), (100, 15, 4, -1)]:
+            sh = [sharding.inverse_shard(P, m, hop, p_min, r, world) for r in range(world)]
+            assert sh[0].k_a == 0 and sh[-1].k_b == (p_min + P - 1) * hop + m - m // 2
+            assert all(sh[r].k_b == sh[r + 1].k_a for r in range(world - 1))
+            assert all(s.halo_cols == (0 if r == 0 else (m + hop - 1) // hop - 1) for r, s in enumerate(sh))
+
+
+@pytest.mark.gpu
+def test_inverse_sharding_cuda_matches_unsharded():
+    """Inverse of one long signal in 4 slice shards (run one after the other on one GPU): each
+    shard sees [halo | own] columns and shifted (k0, k1); the pieces are bit-identical to the
+    unsharded istft."""
+    from veils_b200 import StandaloneSTFT
+    rng = np.random.default_rng(6)
+    for prec, mode, m, hop in (("f32", "onesided", 512, 128), ("f64", "twosided", 256, 64)):
+        win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(m) / m))
+        st = StandaloneSTFT(win, hop, 16000.0, fft_mode=mode, precision=prec)
+        x = rng.uniform(-1, 1, 150000).astype(np.float32 if prec == "f32" else np.float64)
+        S = st.stft(x)
+        full = st.istft(S)
+        P = S.shape[1]
+        world = 4
+        sh = [sharding.inverse_shard(P, m, hop, st.p_min, r, world) for r in range(world)]
+        parts = []
+        for r, s in enumerate(sh):
+            a = s.p_a - st.p_min - s.halo_cols
+            parts.append(st.istft(np.ascontiguousarray(S[:, a:s.p_b - st.p_min]), s.k0_local, s.k1_local))
+        y = np.concatenate(parts)
+        assert y.shape == full.shape and np.array_equal(y, full)
 
 
 @pytest.mark.gpu

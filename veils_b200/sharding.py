@@ -6,6 +6,12 @@ NO collective:
     samples [p_a*hop - m_num_mid, (p_b-1)*hop - m_num_mid + m_num) of the signal, i.e. neighbouring
     ranks overlap by an (m_num - hop)-sample halo (`frame_shard`), and calls stft(p0=p_a, p1=p_b)
     on its sub-signal with k_offset shifted so that slice indices stay global;
+  * one very long signal, inverse  -> every rank owns the output samples whose LATEST contributing
+    slice is one of its own (`inverse_shard`); it needs the last ceil(m_num/hop)-1 columns of S
+    from the previous rank -- ONE neighbour exchange (`exchange_halo_columns`, point-to-point, a few
+    KB) -- and then runs the ordinary istft on [halo | own] columns with shifted (k0, k1): the
+    overlap-add is local and in the same increasing-q order as the unsharded transform
+    (src/lib.rs:853), hence bit-identical (exchanging partial sums instead would change the order);
   * gathering the per-rank results into one array is the only place a collective
     (`torch.distributed.all_gather` / `gather`, NCCL on GPUs, gloo in the CPU tests) is used.
 
@@ -87,3 +93,68 @@ def gather_frames(local, p_total: int, dist, rank: int, world: int, dst: int = 0
         a, b = row_range(p_total, r, world)
         out.append(parts[r][:, : b - a])
     return torch.cat(out, dim=1)
+
+
+@dataclass
+class InverseShard:
+    p_a: int          # first global slice owned by this rank
+    p_b: int          # one past the last
+    halo_cols: int    # columns of S needed from the previous rank (0 for rank 0)
+    k_a: int          # global output samples [k_a, k_b) this rank produces
+    k_b: int
+    k0_local: int     # (k0, k1) to pass to istft() on the [halo | own] columns
+    k1_local: int
+
+
+def inverse_shard(p_total: int, m_num: int, hop: int, p_min: int, rank: int, world: int,
+                  k0: int = 0, k1=None) -> InverseShard:
+    """Output range and halo of `rank` for the inverse transform of S[F, p_total] sharded by slices.
+
+    Slice q adds to samples [q*hop - mid, q*hop - mid + m_num) (src/lib.rs:876-910).  A sample's
+    latest contributing slice is floor((k + mid) / hop): rank r with slices [p_a, p_b) therefore owns
+    k in [p_a*hop - mid, p_b*hop - mid) (first rank: from k0; last rank: up to k1, default the
+    reference's k_max, src/lib.rs:823-824) and needs the ceil(m_num/hop)-1 slices before p_a.
+    On the local column block the slice index restarts at p_min, so (k0, k1) shift by
+    (p_a - halo_cols - p_min) * hop."""
+    mid = m_num // 2
+    a, b = row_range(p_total, rank, world)
+    p_a, p_b = p_min + a, p_min + b
+    k_max = (p_min + p_total - 1) * hop + m_num - mid
+    k1 = k_max if k1 is None else k1
+    halo = 0 if rank == 0 else min((m_num + hop - 1) // hop - 1, a)
+    k_a = k0 if rank == 0 else max(k0, p_a * hop - mid)
+    k_b = k1 if rank == world - 1 else min(k1, p_b * hop - mid)
+    shift = (p_a - halo - p_min) * hop
+    return InverseShard(p_a, p_b, halo, k_a, max(k_a, k_b), k_a - shift, max(k_a, k_b) - shift)
+
+
+def exchange_halo_columns(local, halo_next: int, halo_mine: int, dist, rank: int, world: int):
+    """The one data-path exchange of the sharded inverse: send my last `halo_next` columns of
+    S_r[F, P_r] to rank+1, receive `halo_mine` columns from rank-1; returns [halo | own] columns.
+    Point-to-point (NCCL send/recv over NVLink on GPUs, gloo in the CPU tests)."""
+    import torch
+    reqs = []
+    recv = None
+    if rank + 1 < world and halo_next > 0:
+        assert local.shape[1] >= halo_next, "a rank must own at least ceil(m_num/hop)-1 slices"
+        tail = local[:, local.shape[1] - halo_next:].contiguous()
+        reqs.append(dist.isend(tail, rank + 1))
+    if rank > 0 and halo_mine > 0:
+        recv = torch.empty((local.shape[0], halo_mine), dtype=local.dtype, device=local.device)
+        reqs.append(dist.irecv(recv, rank - 1))
+    for r in reqs:
+        r.wait()
+    return local if recv is None else torch.cat([recv, local], dim=1)
+
+
+def gather_samples(local, k0: int, k1: int, shards, dist, rank: int, world: int, dst: int = 0):
+    """Gather the per-rank output segments y_r[k_a:k_b) into y[k0:k1) on `dst` (rank order)."""
+    import torch
+    n_max = max(s.k_b - s.k_a for s in shards)
+    pad = torch.zeros((n_max,), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    if rank != dst:
+        return None
+    return torch.cat([parts[r][: shards[r].k_b - shards[r].k_a] for r in range(world)], dim=0)
