@@ -46,8 +46,8 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
     float *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
     if (K::STAB) {
         float *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;     // xin_elems is a multiple of 4
-        PTab *sptab = reinterpret_cast<PTab *>(stw + K::TWN);
-        copy_table_f(stw, args.tw, K::TWN, tid, K::NT);
+        PTab *sptab = reinterpret_cast<PTab *>(stw + K::TWN_FWD);
+        copy_table_f(stw, args.tw, K::TWN_FWD, tid, K::NT);
         copy_table_f(reinterpret_cast<float *>(sptab), reinterpret_cast<const float *>(ptab_g), 4 * K::MC, tid, K::NT);
         c.tw = stw;
         c.ptab = sptab;

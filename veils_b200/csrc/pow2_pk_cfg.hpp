@@ -87,7 +87,7 @@ inline size_t pk_fwd_smem_bytes(int64_t N, int64_t xin_elems) {
     using G = PkGeo<LOGMC, TF, 2>;
     (void)N;
     size_t b = 4 * ((size_t)G::MC * 2 * TF + PK_NYQ_ROW + (size_t)((xin_elems + 3) & ~3LL) * (G::DBUF ? 2 : 1));
-    if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(PTab) * (size_t)G::MC;
+    if (G::STAB) b += 4 * (size_t)G::TWN_FWD + sizeof(PTab) * (size_t)G::MC;
     return b;
 }
 // per-plan tile table: entry m = sample pair (2m, 2m+1) of the rolled, zero-padded, windowed slice
