@@ -183,7 +183,7 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         const bool no_pk = getenv("VEILS_NO_PACKED") != nullptr;
         // measured on B200 (profiles/r1_config_sweep.txt): the packed forward wins for 2-pass plans
         // (mfft <= 512); for the 3-pass plans its 255-register build loses to the scalar family
-        pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && (pl.M <= 512 || !pl.pow2_fwd || getenv("VEILS_PK_FWD_ALL") != nullptr) &&
+        pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && (pl.M <= 1024 || !pl.pow2_fwd || getenv("VEILS_PK_FWD_ALL") != nullptr) &&
                     pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
         pl.pk_inv = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, true);
     }

@@ -10,6 +10,12 @@
 namespace veils {
 namespace p2 {
 
+// threads per CTA: one CTA per SM for mfft >= 2048 (work buffer 128 KiB) -> 512 threads there
+#ifndef VEILS_P2_BIG_THREADS
+#define VEILS_P2_BIG_THREADS 512
+#endif
+#define VEILS_P2_THREADS(logmc) ((logmc) >= 10 ? VEILS_P2_BIG_THREADS : 256)
+
 struct Cfg {
     int logmc;   // log2(mfft / 2)
     int tf;      // slices per tile
@@ -34,7 +40,7 @@ inline bool cfg_for(int64_t M, int precision, Cfg *c) {
     int np, r1, r2, r3;
     fac_of(c->logmc, &np, &r1, &r2, &r3);
     const int l1 = (1 << c->logmc) / r1;
-    int nsub = 256 / c->tf;
+    int nsub = VEILS_P2_THREADS(c->logmc) / c->tf;
     if (nsub > l1 / 2) nsub = l1 / 2;
     if (nsub < 1) nsub = 1;
     c->nsub = nsub;
@@ -186,7 +192,7 @@ inline InvArgs<T> make_inv_args(const void *S, T *xo, const InvParams &p, const 
 #define VEILS_P2_CASE(T, LM, TFV)                                             \
     case LM: {                                                                \
         constexpr int l1_ = (1 << LM) / Fac<LM>::R1;                          \
-        constexpr int ns0_ = 256 / TFV;                                       \
+        constexpr int ns0_ = VEILS_P2_THREADS(LM) / TFV;                      \
         constexpr int ns1_ = ns0_ > l1_ / 2 ? l1_ / 2 : ns0_;                 \
         constexpr int ns_ = ns1_ < 1 ? 1 : ns1_;                              \
         return fn.template run<T, LM, TFV, ns_>();                            \
