@@ -145,6 +145,15 @@ int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t b
                               const char *padding, void *x_ext, int64_t ext_pitch, void *S,
                               int64_t ldp, void *stream, int32_t spectrogram);
 
+/* stft_detrend of the twin (python/standalone_stft.py:38-50, 345-371; not in the Rust crate):
+ * detr = NULL | "constant" (slice mean removed) | "linear" (least-squares line removed), applied
+ * to every slice before windowing -- realised as the rank-2 correction S - a_p W1 - b_p W0 of the
+ * plain stft.  coef_ws: device workspace of 16 bytes per slice and signal (batch * (p1-p0) * 16). */
+int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t batch,
+                               int64_t x_pitch, const int64_t *p0, const int64_t *p1,
+                               int64_t k_offset, const char *padding, const char *detr, void *x_ext,
+                               int64_t ext_pitch, void *coef_ws, void *S, int64_t ldp, void *stream);
+
 /* ---- compute: host pointers (drop-in for the Vec API; copies inside) ------------------- */
 /* Also performs the reference's NaN scan for one-sided modes (src/lib.rs:696-698).
  * S is dense: ldp == P.  Synchronous. */

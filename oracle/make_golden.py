@@ -204,6 +204,22 @@ def main():
                              padding=padding, S=S, p_min=tw.p_min, p_max=tw.p_max(n)))
     save("padding", recs)
 
+    # 8. per-slice detrending (python/standalone_stft.py:38-50, 345-371; not in the Rust crate)
+    recs = []
+    prng = np.random.default_rng(8)
+    for (m, hop, mfft, mode, n) in [(16, 4, 16, "onesided", 64), (15, 5, 20, "twosided", 47),
+                                    (32, 8, 32, "centered", 100), (24, 6, 32, "onesided2X", 90),
+                                    (64, 16, 64, "onesided", 300)]:
+        win = hann_periodic(m) + 0.05
+        x = prng.standard_normal(n) + 0.02 * np.arange(n) + 1.5
+        for detr in ("constant", "linear"):
+            for padding in ("zeros", "even"):
+                tw = Twin(win=win, hop=hop, fs=2.0, fft_mode=mode, mfft=mfft)
+                S = tw.stft_detrend(x, detr, padding=padding)
+                recs.append(dict(win=win, hop=hop, fs=2.0, mode=mode, mfft=mfft, x=x, detr=detr,
+                                 padding=padding, S=S))
+    save("detrend", recs)
+
 
 if __name__ == "__main__":
     main()

@@ -257,7 +257,28 @@ class OracleSTFT:
             X[..., 1:(-1 if M % 2 == 0 else None)] *= self._fac2x
         return X
 
-    def stft(self, x, p0=None, p1=None, k_offset=0, padding="zeros"):
+    @staticmethod
+    def _detrend(frames, detr):
+        """Per-slice detrending of the twin (python/standalone_stft.py:38-50): 'constant' removes the
+        mean, 'linear' the least-squares line a*t + b, t = 0..m_num-1."""
+        if detr is None:
+            return frames
+        if detr == "constant":
+            return frames - frames.mean(axis=1, keepdims=True)
+        if detr != "linear":
+            raise ValueError(f"Unknown detrend type: {detr}")
+        t = np.arange(frames.shape[1], dtype=np.float64)
+        tc = t - t.mean()
+        m = frames.mean(axis=1, keepdims=True)
+        a = ((frames - m) * tc[None, :]).sum(axis=1, keepdims=True) / np.sum(tc ** 2)
+        b = m - a * t.mean()
+        return frames - (a * t[None, :] + b)
+
+    def stft_detrend(self, x, detr, p0=None, p1=None, k_offset=0, padding="zeros"):
+        """python/standalone_stft.py:345-371."""
+        return self.stft(x, p0, p1, k_offset, padding, detr)
+
+    def stft(self, x, p0=None, p1=None, k_offset=0, padding="zeros", detr=None):
         """src/lib.rs:689-749.  Returns S[f_pts][P] complex128."""
         x = np.asarray(x, dtype=np.float64)
         if self.onesided_fft and np.any(np.isnan(x)):
@@ -271,7 +292,7 @@ class OracleSTFT:
         chunk = max(1, (1 << 22) // max(self.mfft, 1))        # bound temporaries
         for a in range(p0, p1, chunk):
             b = min(p1, a + chunk)
-            y = self._frames(x, a, b, k_offset, padding) * self.win[None, :]
+            y = self._detrend(self._frames(x, a, b, k_offset, padding), detr) * self.win[None, :]
             S[:, a - p0:b - p0] = self._fft_func(y).T
         return S
 

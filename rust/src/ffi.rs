@@ -69,6 +69,10 @@ extern "C" {
                                  p0: *const i64, p1: *const i64, k_offset: i64, padding: *const c_char,
                                  x_ext: *mut c_void, ext_pitch: i64, s: *mut c_void, ldp: i64,
                                  stream: *mut c_void, spectrogram: i32) -> i32;
+    pub fn veils_stft_detrend_dev(p: *mut veils_plan, x: *const c_void, n: i64, batch: i64, x_pitch: i64,
+                                  p0: *const i64, p1: *const i64, k_offset: i64, padding: *const c_char,
+                                  detr: *const c_char, x_ext: *mut c_void, ext_pitch: i64,
+                                  coef_ws: *mut c_void, s: *mut c_void, ldp: i64, stream: *mut c_void) -> i32;
     pub fn veils_istft_dev(p: *mut veils_plan, s: *const c_void, cols: i64, batch: i64, ldp: i64,
                            k0: *const i64, k1: *const i64, x_out: *mut c_void, out_pitch: i64,
                            stream: *mut c_void) -> i32;

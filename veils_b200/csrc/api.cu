@@ -27,6 +27,7 @@ struct DeviceTables {
     float *tw_pk_inv = nullptr;
     void *ptab_pk = nullptr;
     void *itab_pk = nullptr;
+    void *detr_w = nullptr;       // [2][F] complex: fft_func(win * 1), fft_func(win * i)  (detrending)
 };
 }  // namespace veils
 
@@ -203,6 +204,7 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->tw_pow2);
         cudaFree(p->pl.dev->tw_pk);
         cudaFree(p->pl.dev->tw_pk_inv);
+        cudaFree(p->pl.dev->detr_w);
         cudaFree(p->pl.dev->ptab_pk);
         cudaFree(p->pl.dev->itab_pk);
         delete p->pl.dev;
@@ -415,6 +417,70 @@ int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t b
                          : pad_signal<double>((const double *)x, (double *)x_ext, n, batch, x_pitch, left, n_ext, ext_pitch, mode, st);
     if (ce != cudaSuccess) return cuda_fail(ce, "pad launch");
     return forward_impl(p, x_ext, n_ext, batch, ext_pitch, &a, &b, k_offset + left, S, ldp, stream, spectrogram ? 1 : 0);
+}
+
+// W0 = fft_func(win * 1), W1 = fft_func(win * i): one slice that covers [0, m_num) of a ones / ramp signal,
+// through the plan's own forward path (same roll, mode epilogue and scaling as S)
+static int32_t ensure_detrend_tables(veils_plan *p, void *stream) {
+    Plan &pl = p->pl;
+    int32_t rc = ensure_device(pl, false);
+    if (rc != VEILS_OK) return rc;
+    if (pl.dev->detr_w) return VEILS_OK;
+    const size_t esz = pl.precision == F32 ? 4 : 8;
+    std::vector<double> sig((size_t)(2 * pl.N));
+    for (int64_t i = 0; i < pl.N; ++i) { sig[(size_t)i] = 1.0; sig[(size_t)(pl.N + i)] = (double)i; }
+    void *xs = nullptr, *w = nullptr;
+    cudaError_t e = upload_prec(pl, sig, &xs);
+    if (e == cudaSuccess) e = cudaMalloc(&w, (size_t)(2 * pl.F) * 2 * esz);
+    if (e != cudaSuccess) { cudaFree(xs); cudaFree(w); return cuda_fail(e, "detrend tables"); }
+    const int64_t zero = 0, one = 1;
+    rc = forward_impl(p, xs, pl.N, 2, pl.N, &zero, &one, pl.mid, w, 1, stream, 0);
+    if (rc == VEILS_OK) {
+        e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "detrend tables");
+    }
+    cudaFree(xs);
+    if (rc != VEILS_OK) { cudaFree(w); return rc; }
+    std::lock_guard<std::mutex> g(pl.mu);
+    if (pl.dev->detr_w) cudaFree(w);
+    else pl.dev->detr_w = w;
+    return VEILS_OK;
+}
+
+int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                               const int64_t *p0, const int64_t *p1, int64_t k_offset, const char *padding,
+                               const char *detr, void *x_ext, int64_t ext_pitch, void *coef_ws, void *S,
+                               int64_t ldp, void *stream) {
+    if (!p || !x || !S) return fail(VEILS_ERR_INVALID, "null argument");
+    if (!detr) return veils_stft_dev_padded(p, x, n, batch, x_pitch, p0, p1, k_offset, padding, x_ext, ext_pitch, S, ldp, stream, 0);
+    const int linear = !strcmp(detr, "linear") ? 1 : (!strcmp(detr, "constant") ? 0 : -1);
+    if (linear < 0) return fail(VEILS_ERR_INVALID, std::string("Unknown detrend type: ") + detr);
+    if (!coef_ws) return fail(VEILS_ERR_INVALID, "coef_ws workspace required (16 bytes per slice and signal)");
+    const int mode = padding_mode(padding);
+    if (mode < 0) return fail(VEILS_ERR_INVALID, std::string("Parameter padding='") + padding + "' not in ['zeros', 'edge', 'even', 'odd']!");
+    Plan &pl = p->pl;
+    int32_t rc = veils_stft_dev_padded(p, x, n, batch, x_pitch, p0, p1, k_offset, padding, x_ext, ext_pitch, S, ldp, stream, 0);
+    if (rc != VEILS_OK || batch == 0) return rc;
+    int64_t a, b, left = 0, n_ext = n;
+    std::string e = plan_p_range(pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    if (mode != 0) {
+        rc = veils_pad_extent(p, n, p0, p1, k_offset, &left, &n_ext);
+        if (rc != VEILS_OK) return rc;
+    }
+    rc = ensure_detrend_tables(p, stream);
+    if (rc != VEILS_OK) return rc;
+    const void *xs = mode != 0 ? x_ext : x;
+    const int64_t pitch = mode != 0 ? ext_pitch : x_pitch;
+    const int64_t start0 = k_offset + left - pl.mid;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = pl.precision == F32
+        ? detrend_correct<float>((const float *)xs, n_ext, batch, pitch, a, b - a, pl.H, pl.N, start0, linear,
+                                 (const float *)pl.dev->detr_w, (double2 *)coef_ws, (float *)S, pl.F, ldp, st)
+        : detrend_correct<double>((const double *)xs, n_ext, batch, pitch, a, b - a, pl.H, pl.N, start0, linear,
+                                  (const double *)pl.dev->detr_w, (double2 *)coef_ws, (double *)S, pl.F, ldp, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "detrend launch");
+    return VEILS_OK;
 }
 
 int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,

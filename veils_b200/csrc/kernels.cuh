@@ -81,4 +81,10 @@ template <typename T>
 cudaError_t pad_signal(const T *x, T *x_ext, int64_t n, int64_t batch, int64_t x_pitch, int64_t left, int64_t n_ext,
                        int64_t ext_pitch, int mode, cudaStream_t st);
 
+// ---- per-slice detrending as a rank-2 correction of S (detrend.cu) ---------------------------
+template <typename T>
+cudaError_t detrend_correct(const T *x, int64_t n, int64_t batch, int64_t x_pitch, int64_t p0, int64_t P, int64_t H,
+                            int64_t N, int64_t start0, int linear, const T *W, double2 *coef, T *S, int64_t F,
+                            int64_t ldp, cudaStream_t st);
+
 }  // namespace veils

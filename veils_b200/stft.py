@@ -161,19 +161,19 @@ class StandaloneSTFT:
 
     PADDINGS = ("zeros", "edge", "even", "odd")
 
-    def _fwd(self, x, p0, p1, k_offset, spectrogram, padding="zeros"):
+    def _fwd(self, x, p0, p1, k_offset, spectrogram, padding="zeros", detr=None):
         if padding not in self.PADDINGS:
             raise VeilsError(_lib.ERR_INVALID, f"Parameter padding='{padding}' not in {list(self.PADDINGS)}!")
         if self._is_tensor(x):
-            return self._fwd_tensor(x, p0, p1, k_offset, spectrogram, padding)
+            return self._fwd_tensor(x, p0, p1, k_offset, spectrogram, padding, detr)
         x = np.asarray(x)
-        if padding != "zeros":
+        if padding != "zeros" or detr is not None:
             # the border extension runs on the device (veils_stft_dev_padded): stage through torch
             import torch
             if np.iscomplexobj(x):
                 raise VeilsError(_lib.ERR_INVALID, "Complex-valued input not allowed (real input only)")
             xt = torch.from_numpy(np.ascontiguousarray(x, dtype=self._rdt)).cuda(self.device)
-            return self._fwd_tensor(xt, p0, p1, k_offset, spectrogram, padding).cpu().numpy()
+            return self._fwd_tensor(xt, p0, p1, k_offset, spectrogram, padding, detr).cpu().numpy()
         if np.iscomplexobj(x):
             raise VeilsError(_lib.ERR_INVALID, "Complex-valued input not allowed (real input only)")
         squeeze = x.ndim == 1
@@ -190,7 +190,7 @@ class StandaloneSTFT:
                   out.ctypes.data))
         return out[0] if squeeze else out
 
-    def _fwd_tensor(self, x, p0, p1, k_offset, spectrogram, padding="zeros"):
+    def _fwd_tensor(self, x, p0, p1, k_offset, spectrogram, padding="zeros", detr=None):
         import torch
         tdt = torch.float32 if self.precision == "f32" else torch.float64
         if not x.is_cuda or x.dtype != tdt:
@@ -217,11 +217,19 @@ class StandaloneSTFT:
             out = torch.empty((batch, self.f_pts, ldp), device=x.device,
                               dtype=torch.complex64 if self.precision == "f32" else torch.complex128)
         st = torch.cuda.current_stream(x.device).cuda_stream
-        if padding != "zeros":
+        if padding != "zeros" or detr is not None:
             left, n_ext = C.c_int64(0), C.c_int64(0)
             _check(self._L.veils_pad_extent(self._h, n, opt_i64(a), opt_i64(b), int(k_offset),
                                             C.byref(left), C.byref(n_ext)))
             xe = torch.empty((batch, n_ext.value), dtype=tdt, device=x.device)
+            if detr is not None:
+                coef = torch.empty((batch, P, 2), dtype=torch.float64, device=x.device)
+                _check(self._L.veils_stft_detrend_dev(self._h, x2.data_ptr(), n, batch,
+                                                      x2.stride(0) if batch > 1 else n, opt_i64(a), opt_i64(b),
+                                                      int(k_offset), padding.encode(), detr.encode(), xe.data_ptr(),
+                                                      n_ext.value, coef.data_ptr(), out.data_ptr(), ldp, st))
+                out = out[:, :, :P]
+                return out[0] if squeeze else out
             _check(self._L.veils_stft_dev_padded(self._h, x2.data_ptr(), n, batch,
                                                  x2.stride(0) if batch > 1 else n, opt_i64(a), opt_i64(b),
                                                  int(k_offset), padding.encode(), xe.data_ptr(), n_ext.value,
@@ -239,6 +247,18 @@ class StandaloneSTFT:
         padding: 'zeros' (the Rust crate's only mode) or the twin's 'edge' | 'even' | 'odd'
         (python/standalone_stft.py:309-336)."""
         return self._fwd(x, p0, p1, k_offset, False, padding)
+
+    def stft_detrend(self, x, detr, p0=None, p1=None, *, k_offset=0, padding="zeros"):
+        """The twin's stft_detrend (python/standalone_stft.py:345-371): detr = None | 'constant' |
+        'linear' is removed from every slice before windowing (callables are not supported on the
+        device).  Runs on the GPU as stft + a rank-2 correction (csrc/detrend.cu)."""
+        if detr is None:
+            return self.stft(x, p0, p1, k_offset=k_offset, padding=padding)
+        if detr not in ("constant", "linear"):
+            if isinstance(detr, str):
+                raise VeilsError(_lib.ERR_INVALID, f"Unknown detrend type: {detr}")
+            raise VeilsError(_lib.ERR_INVALID, f"Parameter detr={detr!r} is not 'constant', 'linear' or None!")
+        return self._fwd(x, p0, p1, k_offset, False, padding, detr)
 
     def spectrogram(self, x, p0=None, p1=None, *, k_offset=0, padding="zeros"):
         """scipy ShortTimeFFT.spectrogram: |stft(x)|^2, real."""
