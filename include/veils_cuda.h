@@ -154,6 +154,11 @@ int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t 
                                int64_t k_offset, const char *padding, const char *detr, void *x_ext,
                                int64_t ext_pitch, void *coef_ws, void *S, int64_t ldp, void *stream);
 
+/* Cross-spectrogram of scipy's ShortTimeFFT.spectrogram(x, y) (_short_time_fft.py:1401-1404):
+ * Sx <- Sx * conj(Sy), element-wise over [batch][f_pts][P] (row pitches ldx, ldy), after two stft calls. */
+int32_t veils_cross_multiply_dev(veils_plan *p, void *Sx, const void *Sy, int64_t P, int64_t batch,
+                                 int64_t ldx, int64_t ldy, void *stream);
+
 /* ---- compute: host pointers (drop-in for the Vec API; copies inside) ------------------- */
 /* Also performs the reference's NaN scan for one-sided modes (src/lib.rs:696-698).
  * S is dense: ldp == P.  Synchronous. */

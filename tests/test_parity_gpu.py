@@ -151,3 +151,21 @@ def test_randomized_pow2_geometry_against_oracle(precision):
             k1 = int(rng.integers(k0 + N, n))
             assert rel_err(s.istft(S0, k0, k1), np.stack([o.istft(q, k0, k1) for q in S0])) <= tol
     assert len(seen) >= 2
+
+
+@pytest.mark.gpu
+def test_cross_spectrogram_matches_scipy():
+    """scipy ShortTimeFFT.spectrogram(x, y) = stft(x) * conj(stft(y)) (_short_time_fft.py:1401-1404)."""
+    from scipy.signal import ShortTimeFFT
+    rng = np.random.default_rng(11)
+    for mode, m, hop, mfft, scale in (("onesided", 64, 16, 64, None), ("onesided2X", 32, 8, 64, "psd"),
+                                      ("centered", 24, 6, 32, "magnitude"), ("twosided", 15, 5, 15, None)):
+        win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(m) / m)) + 0.01
+        x, y = rng.standard_normal(500), rng.standard_normal(500)
+        ref = ShortTimeFFT(win, hop, fs=4.0, fft_mode=mode, mfft=mfft, scale_to=scale).spectrogram(x, y)
+        for prec, tol in (("f64", 1e-12), ("f32", 1e-5)):
+            s = StandaloneSTFT(win, hop, 4.0, fft_mode=mode, mfft=mfft, scale_to=scale, precision=prec)
+            got = s.spectrogram(x, y)
+            assert got.shape == ref.shape and np.iscomplexobj(got)
+            assert rel_err(got, ref) <= 4 * tol, (mode, prec)
+            assert rel_err(s.spectrogram(x, x), np.abs(s.stft(x)) ** 2) <= 4 * tol      # y = x: auto-spectrogram

@@ -483,6 +483,20 @@ int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t 
     return VEILS_OK;
 }
 
+int32_t veils_cross_multiply_dev(veils_plan *p, void *Sx, const void *Sy, int64_t P, int64_t batch, int64_t ldx,
+                                 int64_t ldy, void *stream) {
+    if (!p || !Sx || !Sy) return fail(VEILS_ERR_INVALID, "null argument");
+    if (P < 0 || batch < 0 || ldx < P || ldy < P) return fail(VEILS_ERR_INVALID, "ldx, ldy must be >= P >= 0");
+    Plan &pl = p->pl;
+    int32_t rc = ensure_device(pl, false);
+    if (rc != VEILS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = pl.precision == F32 ? cross_multiply<float>((float *)Sx, (const float *)Sy, batch * pl.F, P, ldx, ldy, st)
+                                         : cross_multiply<double>((double *)Sx, (const double *)Sy, batch * pl.F, P, ldx, ldy, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cross-spectrogram launch");
+    return VEILS_OK;
+}
+
 int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,
                         const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
                         void *stream) {

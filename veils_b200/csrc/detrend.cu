@@ -64,7 +64,33 @@ __global__ void detrend_apply_kernel(T *__restrict__ S, int64_t F, int64_t P, in
     }
 }
 
+// Sxy[b][f][p] = Sx * conj(Sy), in place over Sx (scipy ShortTimeFFT.spectrogram(x, y), :1401-1404)
+template <typename T>
+__global__ void cross_kernel(T *__restrict__ Sx, const T *__restrict__ Sy, int64_t rows, int64_t P, int64_t ldx, int64_t ldy) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        T *a = Sx + 2 * (r * ldx + p);
+        const T *b = Sy + 2 * (r * ldy + p);
+        const T ar = a[0], ai = a[1], br = b[0], bi = b[1];
+        a[0] = ar * br + ai * bi;
+        a[1] = ai * br - ar * bi;
+    }
+}
+
 }  // namespace
+
+template <typename T>
+cudaError_t cross_multiply(T *Sx, const T *Sy, int64_t rows, int64_t P, int64_t ldx, int64_t ldy, cudaStream_t st) {
+    if (rows <= 0 || P <= 0) return cudaSuccess;
+    const int threads = 128;
+    dim3 grid((unsigned)((P + threads - 1) / threads), (unsigned)(rows < 4096 ? rows : 4096));
+    cross_kernel<T><<<grid, threads, 0, st>>>(Sx, Sy, rows, P, ldx, ldy);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+template cudaError_t cross_multiply<float>(float *, const float *, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
+template cudaError_t cross_multiply<double>(double *, const double *, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 
 template <typename T>
 cudaError_t detrend_correct(const T *x, int64_t n, int64_t batch, int64_t x_pitch, int64_t p0, int64_t P, int64_t H,

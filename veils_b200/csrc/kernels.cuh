@@ -87,4 +87,8 @@ cudaError_t detrend_correct(const T *x, int64_t n, int64_t batch, int64_t x_pitc
                             int64_t N, int64_t start0, int linear, const T *W, double2 *coef, T *S, int64_t F,
                             int64_t ldp, cudaStream_t st);
 
+// Sx <- Sx * conj(Sy) over rows x P complex elements (cross-spectrogram, detrend.cu)
+template <typename T>
+cudaError_t cross_multiply(T *Sx, const T *Sy, int64_t rows, int64_t P, int64_t ldx, int64_t ldy, cudaStream_t st);
+
 }  // namespace veils

@@ -314,9 +314,29 @@ class StandaloneSTFT:
             raise VeilsError(_lib.ERR_INVALID, f"Parameter detr={detr!r} is not 'constant', 'linear' or None!")
         return self._fwd(x, p0, p1, k_offset, False, padding, detr)
 
-    def spectrogram(self, x, p0=None, p1=None, *, k_offset=0, padding="zeros"):
-        """scipy ShortTimeFFT.spectrogram: |stft(x)|^2, real."""
-        return self._fwd(x, p0, p1, k_offset, True, padding)
+    def spectrogram(self, x, y=None, p0=None, p1=None, *, k_offset=0, padding="zeros"):
+        """scipy ShortTimeFFT.spectrogram: |stft(x)|^2 (real), or the cross-spectrogram
+        stft(x) * conj(stft(y)) (complex) when a second signal y is given (scipy :1398-1404)."""
+        if y is None or y is x:
+            return self._fwd(x, p0, p1, k_offset, True, padding)
+        import torch
+        was_numpy = not self._is_tensor(x)
+        tdt = torch.float32 if self.precision == "f32" else torch.float64
+        if was_numpy:
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=self._rdt)).cuda(self.device)
+        if not self._is_tensor(y):
+            y = torch.from_numpy(np.ascontiguousarray(y, dtype=self._rdt)).to(x.device)
+        if tuple(x.shape) != tuple(y.shape):
+            raise VeilsError(_lib.ERR_INVALID, f"x.shape={tuple(x.shape)} must equal y.shape={tuple(y.shape)}")
+        Sx = self._fwd(x.to(tdt), p0, p1, k_offset, False, padding)
+        Sy = self._fwd(y.to(tdt), p0, p1, k_offset, False, padding)
+        squeeze = Sx.dim() == 2
+        Sx3, Sy3 = (Sx[None], Sy[None]) if squeeze else (Sx, Sy)
+        batch, F, P = Sx3.shape
+        st = torch.cuda.current_stream(Sx.device).cuda_stream
+        _check(self._L.veils_cross_multiply_dev(self._h, Sx3.data_ptr(), Sy3.data_ptr(), P, batch,
+                                                Sx3.stride(1) if F > 1 else P, Sy3.stride(1) if F > 1 else P, st))
+        return Sx.cpu().numpy() if was_numpy else Sx
 
     def istft(self, S, k0=None, k1=None):
         """src/lib.rs:792-914 -> real signal of length k1-k0 (default k0=0, k1=k_max of S)."""
