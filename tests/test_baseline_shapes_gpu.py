@@ -120,3 +120,36 @@ def test_edge_cases():
         if k0 < o.k_min:
             continue
         assert rel_err(st.istft(S, k0, k1), o.istft(S, k0, k1)) <= 1e-12
+
+
+def test_sample_indices_beyond_2_31():
+    """configs[3] is a 2^32-sample signal: sample and slice indices must be 64 bit (the reference's i32
+    arithmetic, src/lib.rs:617-619, overflows there).  One signal of 2^31 + 12345 f32 samples; the
+    LAST 48 slices (a p0 / p1 sub-range, so S stays small) against the oracle on the signal's tail,
+    and the same slices with the twin's 'even' padding (the extended copy is > 2^31 samples too)."""
+    import torch
+    free, _ = torch.cuda.mem_get_info()
+    n = (1 << 31) + 12345
+    if free < 3 * 4 * n + (1 << 30):
+        pytest.skip("needs about 26 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.empty((n,), device="cuda", dtype=torch.float32)
+    step = 1 << 28
+    for a in range(0, n, step):
+        b = min(n, a + step)
+        x[a:b] = torch.rand((b - a,), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
+    st = StandaloneSTFT(hann(512), 128, 16000.0, precision="f32")
+    p1 = st.p_max(n)
+    p0 = p1 - 48
+    assert p1 * 128 > (1 << 31)
+    tail0 = p0 * 128 - 256                       # first sample slice p0 touches
+    xt = x[tail0:].double().cpu().numpy()
+    o = OracleSTFT(hann(512), 128, 16000.0)
+    for padding in ("zeros", "even"):
+        S = st.stft(x, p0, p1, padding=padding)
+        assert S.shape == (257, 48)
+        # oracle on the tail: slice p of the long signal == slice p of the tail with k_offset = -tail0
+        ref = o.stft(xt, p0, p1, k_offset=-tail0, padding=padding)
+        assert rel_err(S.cpu().numpy(), ref) <= 1e-5, padding
+    t = st.t(n, p0, p1)
+    assert abs(t[-1] - (p1 - 1) * 128 / 16000.0) <= 1e-9 * t[-1]
