@@ -169,3 +169,51 @@ def test_cross_spectrogram_matches_scipy():
             assert got.shape == ref.shape and np.iscomplexobj(got)
             assert rel_err(got, ref) <= 4 * tol, (mode, prec)
             assert rel_err(s.spectrogram(x, x), np.abs(s.stft(x)) ** 2) <= 4 * tol      # y = x: auto-spectrogram
+
+
+@pytest.mark.gpu
+def test_randomized_device_tensor_path_staged_kernels():
+    """The device-tensor flavour (128-byte row pitch) is what selects the TMA-staged forward kernel and
+    the paired inverse pass 1 of the packed family.  Randomized geometry through torch tensors:
+    one-sided layouts (staged / paired paths) and two-sided ones (plain-store paths), all mfft of the
+    family, tiles cut by P, slice sub-ranges, batches, |S|^2, istft sub-ranges -- against the oracle."""
+    import torch
+    rng = np.random.default_rng(909)
+    tol = TOL["f32"]
+    kinds = set()
+    for it in range(36):
+        M = int(2 ** rng.integers(5, 14))
+        N = int(M if rng.random() < 0.7 else 2 * rng.integers(M // 4 + 1, M // 2 + 1))
+        H = int(2 * max(1, rng.choice([N // 8, N // 4, N // 6, N // 2, N // 16]) // 1 // 2 * 1))
+        H = max(2, min(H - H % 2, N))
+        mode = str(rng.choice(["onesided", "onesided", "onesided2X", "twosided", "centered"]))
+        ps = int(2 * rng.integers(-M // 4, M // 4)) if rng.random() < 0.3 else 0
+        scale = rng.choice([None, None, "psd"])
+        win = rng.uniform(0.2, 1.0, N)
+        n_sl = int(rng.integers(40, 140))
+        n = int(N + n_sl * H + rng.integers(0, H))
+        B = int(rng.integers(1, 4))
+        x = rng.uniform(-1, 1, (B, n)).astype(np.float32)
+        o = OracleSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale)
+        s = StandaloneSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale, precision="f32")
+        kinds.add((s.kernel_name(), s.kernel_name(True), mode in ("onesided", "onesided2X")))
+        xt = torch.from_numpy(x).cuda()
+        xd = x.astype(np.float64)
+        Sref = np.stack([o.stft(r) for r in xd])
+        S = s.stft(xt)
+        assert S.stride(1) % 16 == 0 and S.shape == Sref.shape
+        assert rel_err(S.cpu().numpy(), Sref) <= tol, (M, N, H, mode, ps, s.kernel_name())
+        p0 = int(rng.integers(s.p_min, s.p_min + 5))
+        p1 = int(rng.integers(p0 + 3, s.p_max(n) + 1))
+        Ssub = s.stft(xt, p0, p1)
+        assert rel_err(Ssub.cpu().numpy(), Sref[:, :, p0 - s.p_min:p1 - s.p_min]) <= tol
+        assert rel_err(s.spectrogram(xt).cpu().numpy(), np.abs(Sref) ** 2) <= 4 * tol
+        if o.invertible:
+            yref = np.stack([o.istft(q) for q in Sref])
+            y = s.istft(S)                                  # padded-pitch view straight back in
+            assert rel_err(y.cpu().numpy(), yref) <= tol, (M, N, H, mode, ps, s.kernel_name(True))
+            k0 = int(rng.integers(0, n // 3))
+            k1 = int(rng.integers(k0 + N, n))
+            assert rel_err(s.istft(S, k0, k1).cpu().numpy(), np.stack([o.istft(q, k0, k1) for q in Sref])) <= tol
+            assert torch.equal(y, s.istft(S))               # deterministic overlap-add
+    assert any(k[0] == "pow2_packed" and k[2] for k in kinds) and any(not k[2] for k in kinds)
