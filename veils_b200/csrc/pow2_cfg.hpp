@@ -111,7 +111,7 @@ inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) 
 template <typename T, int LOGMC, int TF>
 inline size_t fwd_smem_bytes_t(int64_t N, int64_t xin_elems) {
     using G = Geo<T, LOGMC, TF, 1>;
-    size_t b = sizeof(cx<T>) * (size_t)G::MC * TF + sizeof(T) * (size_t)xin_elems * (G::DBUF ? 2 : 1);
+    size_t b = sizeof(cx<T>) * (size_t)(G::MC + 1) * TF + sizeof(T) * (size_t)xin_elems * (G::DBUF ? 2 : 1);   // + Nyquist row
     if (G::STAB) b += sizeof(T) * ((size_t)G::TWN + (size_t)N);
     return b;
 }

@@ -1,6 +1,10 @@
 // pow2_tile.cu -- CUDA kernels and launchers of the power-of-two "slice-lane" family.
 // The per-phase device code lives in pow2_tile_impl.cuh (shared with the host emulation).
+#include <cstdlib>
+#include <cstring>
+
 #include "pow2_cfg.hpp"
+#include "tma.cuh"
 
 namespace veils {
 
@@ -20,16 +24,21 @@ __device__ __forceinline__ void copy_table(T *dst, const T *src, int n, int tid,
 
 // Persistent forward kernel: each CTA walks the (signal, tile) list with stride gridDim.x.
 // Shared memory: work[Mc][TF] | tile buffer(s) | (STAB) twiddles, window.
-template <typename T, int LOGMC, int TF, int NSUB>
+// STAGE (one-sided layouts, S describable by a tensor map): the last pass overwrites the cells it
+// has read with the finished bins and every group pair leaves as two dense [RL rows][TF slices]
+// boxes through the TMA engine -- the short row runs of the large transforms (TF = 8 / 4 / 2
+// slices) never go through the LSU store path.
+template <typename T, int LOGMC, int TF, int NSUB, bool STAGE>
 __global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
-pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, const int xin_elems) {
-    extern __shared__ __align__(16) unsigned char smem[];
+pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, const int xin_elems,
+                const __grid_constant__ CUtensorMap smap) {
+    extern __shared__ __align__(1024) unsigned char smem[];
     using K = Fwd<T, LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
     FwdCtx<T> c;
     c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
-    T *xin0 = reinterpret_cast<T *>(smem + sizeof(cx<T>) * K::MC * TF);
+    T *xin0 = reinterpret_cast<T *>(smem + sizeof(cx<T>) * (K::MC + 1) * TF);      // + staged Nyquist row
     T *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
     if (K::STAB) {
         T *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;
@@ -52,6 +61,7 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
     }
     for (int it = 0; w < total; w += gridDim.x, ++it) {
         cp_async_wait_all();
+        if (STAGE) tma::wait_read_all();   // the previous tile's boxes have left the work buffer
         __syncthreads();                   // tile w staged; previous tile's reads of `work` done
         T *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
         const int64_t wn = w + gridDim.x;
@@ -78,15 +88,39 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
             K::pass_mid(c, tid);
             __syncthreads();
         }
-        K::pass_last(c, tid);
+        if (STAGE) {
+            const int f = tid % TF;
+            const int64_t cb = c.b, cpt = c.pt;
+            const unsigned wbase = tma::smem_u32(c.work);
+            constexpr int MUL = sizeof(T) == 8 ? 2 : 1;      // complex f64 travels as two 8-byte elements
+            auto hook = [&](int s2) {
+                tma::fence_async_smem();
+                __syncwarp();
+                if (s2 >= 0 && f == 0) {
+                    const int g = s2, gp = (s2 == 0) ? K::G / 2 : K::G - s2;
+                    const int mul = args.spectrogram ? 1 : MUL;
+                    const int p0 = (int)(cpt * TF) * mul;
+                    constexpr unsigned RB = TF * (unsigned)sizeof(cx<T>);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB, p0, g, 0, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(gp) * RB, p0, gp, 0, (int)cb);
+                    if (s2 == 0) tma::store_4d(&smap, wbase + K::MC * RB, p0, 0, K::RL, (int)cb);
+                    tma::commit_group();
+                }
+            };
+            if (args.spectrogram) K::template pass_last_t<true, true, true>(c, tid, hook);
+            else K::template pass_last_t<true, false, true>(c, tid, hook);
+        } else {
+            K::pass_last(c, tid);
+        }
     }
+    if (STAGE) tma::wait_all();
 }
 
 // Persistent inverse kernel.  Shared memory: work[Mc][TF] (aliased by ola) | (STAB) twiddles, dual.
 template <typename T, int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
 pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, const int work_bytes) {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     using K = Inv<T, LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
     InvCtx<T> c;
@@ -144,7 +178,19 @@ struct FwdLaunch {
         FwdArgs<T> a = make_fwd_args<T>((const T *)x, out, p, (const T *)win, (const T *)tw, TF);
         const int xin_elems = (int)fwd_xin_elems(p.N, p.H, TF, a.lay);
         const size_t smem = fwd_smem_bytes_t<T, LOGMC, TF>(p.N, xin_elems);
-        auto kern = pow2_fwd_kernel<T, LOGMC, TF, NSUB>;
+        CUtensorMap smap;
+        memset(&smap, 0, sizeof(smap));
+        const char *no_tma = getenv("VEILS_PK_NO_TMA");
+        // measured (profiles/r1c_ablation.txt): +3 % for f64; the f32 tile kernels (mfft >= 2048 here) are
+        // 5 % faster with their plain stores, so only f64 takes the staged path
+        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !(no_tma && atoi(no_tma));
+        if (stage) {
+            // complex f64 elements are 16 bytes: described as pairs of 8-byte elements
+            const int mul = (!p.spectrogram && sizeof(T) == 8) ? 2 : 1;
+            const int esz = p.spectrogram ? (int)sizeof(T) : (sizeof(T) == 8 ? 8 : 8);
+            stage = tma::make_s_map(&smap, out, esz, p.P * mul, p.ldp * mul, p.F, p.batch, K::G, K::RL, TF * mul, K::RL);
+        }
+        auto kern = stage ? pow2_fwd_kernel<T, LOGMC, TF, NSUB, true> : pow2_fwd_kernel<T, LOGMC, TF, NSUB, false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -155,7 +201,7 @@ struct FwdLaunch {
         const int64_t cap = (int64_t)per_sm * num_sms();
         const unsigned grid = (unsigned)(total < cap ? total : cap);
         (void)sizeof(K);
-        kern<<<grid, TF * NSUB, smem, st>>>(a, total, xin_elems);
+        kern<<<grid, TF * NSUB, smem, st>>>(a, total, xin_elems, smap);
         ++g_launch_count;
         return cudaGetLastError();
     }

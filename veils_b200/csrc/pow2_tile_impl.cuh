@@ -382,7 +382,15 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
     // store one-sided bin k (0 <= k <= Mc) of this thread's slice column.
     // ONES: one-sided layouts (modes 2, 3); SPEC: |X|^2 real output.  ob: byte pointer of
     // (row 0, this column); rb: row pitch in bytes.
-    template <bool ONES, bool SPEC>
+    // byte offset of one-sided bin k in the STAGED tile (one-sided layouts, TMA store path): the RL
+    // rows of last-pass group g = k mod G sit on the group's own work rows; bin Mc has an extra row
+    template <bool SPEC>
+    VHD static int64_t srow(int k) {
+        if (k >= MC) return (int64_t)MC * TF * (int64_t)sizeof(C);
+        return (int64_t)GEO::goff(k & (G - 1)) * TF * (int64_t)sizeof(C) +
+               (int64_t)(k / G) * TF * (int64_t)(SPEC ? sizeof(T) : sizeof(C));
+    }
+    template <bool ONES, bool SPEC, bool STAGE = false>
     VHD static void store_bin(const FwdArgs<T> &p, char *ob, int64_t rb, int k, C X) {
         if (k == 0 || k == MC) X.y = (T)0;                  // src/lib.rs:378-384
         if (ONES) {
@@ -390,8 +398,9 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
                 X.x *= p.fac2x;
                 X.y *= p.fac2x;
             }
-            if (SPEC) *reinterpret_cast<T *>(ob + k * rb) = X.x * X.x + X.y * X.y;
-            else *reinterpret_cast<C *>(ob + k * rb) = X;
+            char *q = STAGE ? ob + srow<SPEC>(k) : ob + k * rb;
+            if (SPEC) *reinterpret_cast<T *>(q) = X.x * X.x + X.y * X.y;
+            else *reinterpret_cast<C *>(q) = X;
             return;
         }
         // two-sided layouts: bin k and its mirror M - k (x is real); fftshift for centered
@@ -409,28 +418,37 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
     }
 
     // split of the half-length spectrum: A = Z[k]/2, Zp = Z[Mc-k]/2  ->  X[k], X[Mc-k]
-    template <bool ONES, bool SPEC>
+    template <bool ONES, bool SPEC, bool STAGE = false>
     VHD static void emit(const FwdArgs<T> &p, const T *twp, char *ob, int64_t rb, int k, C A, C Zp, bool both) {
         const C B = conj(Zp);
         const C E = A + B, Om = A - B;
         const C w = GEO::tlc(twp + 2 * k);                   // W_M^k
         const C D = cmul(mk<T>(w.y, -w.x), Om);             // (-i W) (A - B)
-        store_bin<ONES, SPEC>(p, ob, rb, k, E + D);
-        if (both) store_bin<ONES, SPEC>(p, ob, rb, MC - k, conj(E - D));
+        store_bin<ONES, SPEC, STAGE>(p, ob, rb, k, E + D);
+        if (both) store_bin<ONES, SPEC, STAGE>(p, ob, rb, MC - k, conj(E - D));
     }
 
     // ---- last pass: groups (g, G-g): DFT_RL, real-FFT split, mode epilogue, global store
-    template <bool ONES, bool SPEC>
-    VHD static void pass_last_t(const FwdCtx<T> &c, int tid) {
+    // STAGE: the finished bins overwrite the cells (row, slice) this thread has read (one-sided
+    // layouts); pair(s) is called after every pair of groups so that the caller can hand the two
+    // dense [RL rows][TF slices] boxes to the TMA engine (pow2_tile.cu)
+    struct NoHook { VHD void operator()(int) const {} };
+    template <bool ONES, bool SPEC, bool STAGE = false, typename HOOK = NoHook>
+    VHD static void pass_last_t(const FwdCtx<T> &c, int tid, HOOK hook = HOOK()) {
         const FwdArgs<T> &p = c.a;
         const int f = tid % TF, sub = tid / TF;
         const int64_t pl = c.pt * TF + f;
-        const bool live = pl < p.P;
+        const bool live = STAGE || pl < p.P;
         const int64_t esz = SPEC ? sizeof(T) : sizeof(C);
         const int64_t rb = p.ldp * esz;
-        char *ob = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+        char *ob = STAGE ? reinterpret_cast<char *>(c.work) + f * esz
+                         : reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
         const T *twp = c.tw + GEO::TWP;
-        for (int s = sub; s < G / 2; s += NSUB) {
+        for (int s = sub; s < (G / 2 + NSUB - 1) / NSUB * NSUB; s += NSUB) {
+            if (s >= G / 2) {                  // STAGE: every thread of the warp reaches the hook
+                if (STAGE) hook(-1);
+                continue;
+            }
             const int g = s, gp = (s == 0) ? G / 2 : G - s;
             C u[RL], up[RL];
             const C *w1 = c.work + GEO::goff(g) * TF + f, *w2 = c.work + GEO::goff(gp) * TF + f;
@@ -442,19 +460,23 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
             Dft<RL, false, T>::run(u);
             Dft<RL, false, T>::run(up);
             if (!live) continue;
+#if defined(__CUDA_ARCH__)
+            if (STAGE && SPEC) __syncwarp();   // |X|^2 cells are half as wide: lanes overwrite each other's inputs
+#endif
             if (s != 0) {
 #pragma unroll
                 for (int d = 0; d < RL; ++d)
-                    emit<ONES, SPEC>(p, twp, ob, rb, g + G * d, u[d], up[RL - 1 - d], true);
+                    emit<ONES, SPEC, STAGE>(p, twp, ob, rb, g + G * d, u[d], up[RL - 1 - d], true);
             } else {
-                emit<ONES, SPEC>(p, twp, ob, rb, 0, u[0], u[0], true);                  // X[0], X[Mc]
+                emit<ONES, SPEC, STAGE>(p, twp, ob, rb, 0, u[0], u[0], true);                  // X[0], X[Mc]
 #pragma unroll
-                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC>(p, twp, ob, rb, G * d, u[d], u[RL - d], true);
-                emit<ONES, SPEC>(p, twp, ob, rb, MC / 2, u[RL / 2], u[RL / 2], false);  // self-mirrored
+                for (int d = 1; d < RL / 2; ++d) emit<ONES, SPEC, STAGE>(p, twp, ob, rb, G * d, u[d], u[RL - d], true);
+                emit<ONES, SPEC, STAGE>(p, twp, ob, rb, MC / 2, u[RL / 2], u[RL / 2], false);  // self-mirrored
 #pragma unroll
                 for (int d = 0; d < RL / 2; ++d)
-                    emit<ONES, SPEC>(p, twp, ob, rb, G / 2 + G * d, up[d], up[RL - 1 - d], true);
+                    emit<ONES, SPEC, STAGE>(p, twp, ob, rb, G / 2 + G * d, up[d], up[RL - 1 - d], true);
             }
+            if (STAGE) hook(s);
         }
     }
     VHD static void pass_last(const FwdCtx<T> &c, int tid) {
