@@ -221,3 +221,36 @@ def test_randomized_device_tensor_path_staged_kernels(precision):
     assert any(k[2] for k in kinds) and any(not k[2] for k in kinds)
     if precision == "f32":
         assert any(k[0] == "pow2_packed" and k[2] for k in kinds) and any(k[0] == "pow2_tile" and k[2] for k in kinds)
+
+
+@pytest.mark.gpu
+def test_unaligned_output_views_take_the_plain_store_path():
+    """S rows that are not 16-byte aligned (odd pitch, or a view starting at an odd column) cannot be
+    described by a tensor map: the same call must silently run the plain-store kernels and give
+    bit-identical results (the arithmetic per slice is the same; only the way the tile leaves the SM
+    differs for the packed family's paired / two-slices-per-lane last passes -> compare to tolerance)."""
+    import torch
+    from veils_b200 import lib
+    L = lib()
+    rng = np.random.default_rng(5)
+    win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(512) / 512))
+    for prec, dt, cdt, tol in (("f32", torch.float32, torch.complex64, 2e-6), ("f64", torch.float64, torch.complex128, 1e-14)):
+        s = StandaloneSTFT(win, 128, 16000.0, precision=prec)
+        x = torch.from_numpy(rng.uniform(-1, 1, (3, 20000))).to("cuda", dt)
+        n = x.shape[1]
+        P, F = s.p_num(n), s.f_pts
+        ref = s.stft(x)                                               # aligned pitch: staged kernels
+        st = torch.cuda.current_stream().cuda_stream
+        for ldp, off in ((P, 0), (P + 3, 1), (P + 16, 1)):            # odd pitch / odd column offset
+            big = torch.zeros((3, F, ldp + 2), dtype=cdt, device="cuda")
+            view = big[:, :, off:off + P]
+            rc = L.veils_stft_dev(s._h, x.data_ptr(), n, 3, n, None, None, 0, view.data_ptr(), ldp + 2, st)
+            assert rc == 0, L.veils_last_error()
+            torch.cuda.synchronize()
+            assert rel_err(view.cpu().numpy(), ref.cpu().numpy()) <= tol
+            assert float(big[:, :, :off].abs().max()) == 0.0 if off else True      # nothing written outside
+            assert float(big[:, :, off + P:].abs().max()) == 0.0
+            y = torch.empty((3, s.istft_range(P)[1]), dtype=dt, device="cuda")
+            rc = L.veils_istft_dev(s._h, view.data_ptr(), P, 3, ldp + 2, None, None, y.data_ptr(), y.shape[1], st)
+            assert rc == 0, L.veils_last_error()
+            assert float((y[:, :n] - x).abs().max()) <= 10 * tol
