@@ -44,8 +44,13 @@ __device__ __forceinline__ void tma_store(const CUtensorMap *m, unsigned src, in
                  ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
-enum { TMA16 = 0, TMA1, STG2, STG1, STG128, BULK };
+enum { TMA16 = 0, TMA1, STG2, STG1, STG128, BULK, LD_TMA, LD_LDG, LD_LDG2 };
+__device__ __forceinline__ void tma_load(const CUtensorMap *m, unsigned dst, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
+__device__ int g_ld_off = 0;       // column offset of the TMA loads (alignment probe)
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) k(float *S, int P, int ldp, int F, int ptiles, long total,
                                              const __grid_constant__ CUtensorMap m16, const __grid_constant__ CUtensorMap m1) {
@@ -56,9 +61,18 @@ __global__ void __launch_bounds__(256, 2) k(float *S, int P, int ldp, int F, int
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     const unsigned wb = (unsigned)__cvta_generic_to_shared(w);
+    __shared__ __align__(8) unsigned long long bar_mem;
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&bar_mem);
+    if (MODE == LD_TMA && tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    float acc = 0.f;
+    unsigned phase = 0;
     for (long t = blockIdx.x; t < total; t += gridDim.x) {
         const int b = (int)(t / ptiles), pt = (int)(t % ptiles);
-        const int p0 = pt * 32;
+        const int p0 = pt * 32 + (MODE == LD_TMA ? g_ld_off : 0);
         if (MODE == TMA16) {
             if (lane == 0) {
                 tma_store(&m16, wb + (2 * warp) * 4096, p0, 0, 2 * warp, b);
@@ -84,6 +98,39 @@ __global__ void __launch_bounds__(256, 2) k(float *S, int P, int ldp, int F, int
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        } else if (MODE == LD_TMA) {
+            // 17 boxes [16 rows][32 slices] -> shared memory, completion on one mbarrier; then every
+            // lane reads its slice of the 33 rows of its warp (what the paired inverse pass 1 needs)
+            if (tid == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(17 * 4096) : "memory");   // OOB rows of a box are zero-filled and counted
+                for (int g = 0; g < 16; ++g) tma_load(&m16, wb + g * 4096, bar, p0, 0, g, b);
+                tma_load(&m16, wb + 65536, bar, p0, 16, 0, b);
+            }
+            asm volatile(
+                "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n"
+                ::"r"(bar), "r"(phase) : "memory");
+            phase ^= 1;
+            for (int r = warp * 32; r < warp * 32 + 32; ++r) {
+                const float2 v = *reinterpret_cast<const float2 *>(w + r * 64 + 2 * lane);
+                acc += v.x + v.y;
+            }
+        } else if (MODE == LD_LDG || MODE == LD_LDG2) {
+            // LD_LDG: one 256-byte row run per warp instruction (paired pass 1); LD_LDG2: two 128-byte
+            // runs of two rows per instruction (the two-slices-per-lane pass 1)
+            if (MODE == LD_LDG) {
+                for (int r = warp * 32; r < warp * 32 + 32 + (warp == 0); ++r) {
+                    const int rr = r < 257 ? r : 256;
+                    const char *row = reinterpret_cast<const char *>(S) + (((size_t)b * F + rr) * ldp + p0) * 8;
+                    if (p0 + lane < P) { const float2 v = __ldg(reinterpret_cast<const float2 *>(row + 8 * lane)); acc += v.x + v.y; }
+                }
+            } else {
+                const int l = lane & 15, sub = lane >> 4;
+                for (int r = warp * 2 + sub; r < 257; r += 16) {
+                    const char *row = reinterpret_cast<const char *>(S) + (((size_t)b * F + r) * ldp + p0) * 8;
+                    if (p0 + l < P) { const float2 v = __ldg(reinterpret_cast<const float2 *>(row + 8 * l)); acc += v.x + v.y; }
+                    if (p0 + l + 16 < P) { const float2 v = __ldg(reinterpret_cast<const float2 *>(row + 8 * (l + 16))); acc += v.x + v.y; }
+                }
+            }
         } else if (MODE == STG2) {
             const int l = lane & 15, sub = lane >> 4;
             for (int r = warp * 2 + sub; r < 257; r += 16) {
@@ -110,6 +157,7 @@ __global__ void __launch_bounds__(256, 2) k(float *S, int P, int ldp, int F, int
         __syncthreads();
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (acc == 12345.678f) S[0] = acc;
 }
 
 template <int MODE>
@@ -135,10 +183,17 @@ static void run(const char *name, float *S, int P, int ldp, int F, int B, int ns
 }
 
 int main() {
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, 0));
     const int nsm = pr.multiProcessorCount;
     const int B = 1024, F = 257, P = 1253;
     float *S; CK(cudaMalloc(&S, (size_t)B * F * 1280 * 8 + 65536));
+    for (int off : {0, 2, 1, -3}) {      // does the start column of a tensor load have to be 16-byte aligned?
+        CK(cudaMemcpyToSymbol(g_ld_off, &off, sizeof(int)));
+        printf("ld_tma column offset %d: ", off);
+        run<LD_TMA>("ld_tma", S, P, 1256, F, B, nsm);
+    }
+    { int off = 0; CK(cudaMemcpyToSymbol(g_ld_off, &off, sizeof(int))); }
     for (int ldp : {1256, 1280}) {
         run<TMA16>("tma16", S, P, ldp, F, B, nsm);
         run<TMA1>("tma1", S, P, ldp, F, B, nsm);
@@ -146,6 +201,9 @@ int main() {
         run<STG2>("stg2", S, P, ldp, F, B, nsm);
         run<STG1>("stg1", S, P, ldp, F, B, nsm);
         run<STG128>("stg128", S, P, ldp, F, B, nsm);
+        run<LD_TMA>("ld_tma", S, P, ldp, F, B, nsm);
+        run<LD_LDG>("ld_ldg1", S, P, ldp, F, B, nsm);
+        run<LD_LDG2>("ld_ldg2", S, P, ldp, F, B, nsm);
     }
     return 0;
 }

@@ -159,10 +159,10 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
                     const unsigned wbase = tma::smem_u32(c.work);
                     const int p0 = (int)(cpt * TF);
                     const int g0 = K::group_of(wg, 0), g1 = K::group_of(wg, 1);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(g0) * (TF * 8), p0, g0, 0, (int)cb);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(g1) * (TF * 8), p0, g1, 0, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g0) * (TF * 8), p0, 0, g0, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g1) * (TF * 8), p0, 0, g1, (int)cb);
                     if (wg == 0)                // Nyquist row: rows past d = RL are clipped by the map
-                        tma::store_4d(&smap, wbase + K::MC * (TF * 8), p0, 0, K::RL, (int)cb);
+                        tma::store_4d(&smap, wbase + K::MC * (TF * 8), p0, K::RL, 0, (int)cb);
                     tma::commit_group();
                 }
             }
@@ -186,7 +186,8 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
 template <int LOGMC, int TF, int NSUB, bool ONES>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
-              const int64_t total, const int work_bytes) {
+              const int64_t total, const int work_bytes, const int use_tma,
+              const __grid_constant__ CUtensorMap smap, const __grid_constant__ CUtensorMap smap_nyq) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using K = PkInv<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -208,6 +209,18 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         c.tw = args.tw;
         c.itab = itab_g;
     }
+    // TMA path (one-sided layouts, one pass-1 group pair per thread): the S tile of [Mc + 1 rows][TF
+    // slices] lands OVER the work buffer -- one box [R1 rows][TF slices] per pass-1 group, row
+    // j R1 + a = bin j + L1 a, plus the Nyquist row -- at 7 TB/s with no load instructions in the
+    // warps (profiles/r1c_microbench_store_lds.txt); columns outside S arrive as zeros.
+    __shared__ __align__(8) unsigned long long land_bar_mem;
+    const unsigned land_bar = tma::smem_u32(&land_bar_mem);
+    const bool tma_path = ONES && use_tma && K::WPT2 == 1;
+    unsigned land_phase = 0;
+    if (tma_path && tid == 0) {
+        tma::mbar_init(land_bar, 1);
+        tma::fence_mbar_init();
+    }
     __syncthreads();
     // A CTA walks the tiles of one chunk of one signal in order (streaming overlap-add): only the
     // first tile of a chunk re-computes the halo slices, every other tile owns all TF slices.
@@ -224,7 +237,26 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
             c.carry_in = flip ? carry1 : carry0;
             c.carry_out = flip ? carry0 : carry1;
             flip ^= 1;
-            if (ONES && !(args.dbg & 64)) {
+            if (tma_path) {
+                if (tid == 0) {
+                    // the previous tile's overlap rows (generic-proxy writes) lived in this buffer
+                    tma::fence_async_smem();
+                    const unsigned wbase = tma::smem_u32(c.work);
+                    const int col = (int)((c.qa - args.p_min) & ~(int64_t)1);      // even: 16-byte aligned start
+                    tma::mbar_expect_tx(land_bar, (unsigned)K::LAND_BYTES);
+#pragma unroll 1
+                    for (int j = 0; j < K::L1; ++j)
+                        tma::load_4d(&smap, wbase + j * (K::R1 * K::LTF * 8), land_bar, col, 0, j, (int)c.b);
+                    tma::load_4d(&smap_nyq, wbase + K::MC * (K::LTF * 8), land_bar, col, K::R1, 0, (int)c.b);
+                }
+                c.land_shift = (int)((c.qa - args.p_min) & 1);
+                typename K::Cp x0[K::R1], x1[K::R1], xn;
+                tma::mbar_wait(land_bar, land_phase);
+                land_phase ^= 1;
+                K::p1p_load_smem(c, tid, 0, x0, x1, xn);
+                __syncthreads();               // every thread holds its bins before anyone overwrites the tile
+                K::p1p_rest(c, tid, 0, x0, x1, xn);
+            } else if (ONES && !(args.dbg & 64)) {
 #pragma unroll 1
                 for (int i = 0; i < K::WPT2; ++i) {
 #ifdef VEILS_ABLATE
@@ -347,8 +379,24 @@ struct PkInvLaunch {
         a.dbg = pk_env_int("VEILS_PK_DBG_INV", 0);
         const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
         const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
-        using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int);
+        using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int, const int, const CUtensorMap,
+                               const CUtensorMap);
         KernT kern = p.mode >= 2 ? (KernT)pk_inv_kernel<LOGMC, TF, NSUB, true> : (KernT)pk_inv_kernel<LOGMC, TF, NSUB, false>;
+        // one-sided layouts: S tiles land through the TMA engine when S can be described by a tensor map
+        // (16-byte aligned base / row pitch) and the landed tile fits the work buffer
+        using K = PkInv<LOGMC, TF, NSUB>;
+        CUtensorMap smap, smap_nyq;
+        memset(&smap, 0, sizeof(smap));
+        memset(&smap_nyq, 0, sizeof(smap_nyq));
+        // Measured (profiles/r1c_ablation.txt): 1.05 -> 0.96 ms for mfft = 512 (2 CTAs per SM hide each
+        // other's landing latency); slower for mfft = 256 (1.20 -> 1.62 ms) and for mfft >= 2048
+        // (one CTA per SM: nothing overlaps the landing), so only mfft = 512 takes this path.
+        const int use_tma = LOGMC == 8 && (K::R1 * K::LTF * 8) % 128 == 0 &&
+                            p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
+                            !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) &&
+                            (size_t)work_bytes >= K::LAND_BYTES &&
+                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1) &&
+                            tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -358,7 +406,7 @@ struct PkInvLaunch {
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         pk_inv_chunks(a, p, TF, p.batch, cap);
         const int64_t total = a.cps * p.batch;
-        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes);
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes, use_tma, smap, smap_nyq);
         ++g_launch_count;
         return cudaGetLastError();
     }

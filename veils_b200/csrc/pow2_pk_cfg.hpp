@@ -145,7 +145,10 @@ inline size_t pk_inv_work_bytes(int64_t N) {
     size_t work = 4 * (size_t)G::MC * 2 * TF;
     const size_t ola = 4 * (size_t)TF * (size_t)(N + 6);
     if (ola > work) work = ola;
-    return (work + 15) & ~(size_t)15;
+    // TMA path of the one-sided inverse: the S tile lands over this buffer, [Mc + 1 rows][TF + 2 slices]
+    const size_t land = (size_t)(G::MC + 1) * (TF + 2) * 8;
+    if (LOGMC <= 11 && land > work) work = land;
+    return (work + 127) & ~(size_t)127;
 }
 // streaming overlap-add: chunk geometry for a launch (owned slices qh0..qh1 per signal)
 inline void pk_inv_chunks(InvArgs<float> &a, const InvParams &p, int tf, int64_t batch, int64_t grid_hint) {

@@ -573,6 +573,7 @@ struct PkInvCtx {
     const float *carry_in;   // [N - H] partial overlap sums of the samples this tile completes
     float *carry_out;        // [N - H] ... and of the samples the next tile completes
     int first;               // first tile of a chunk: no carry-in, its first `halo` slices are a re-computed halo
+    int land_shift;          // TMA path: the landed tile starts land_shift (0 / 1) columns before slice 0
     int64_t b, qa;
 };
 
@@ -782,16 +783,19 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     // j0 rides in the low halves of the f32x2 registers, group j1 in the high halves.
     static constexpr int NW2 = NT / TF;
     static constexpr int WPT2 = (L1 / 2 + NW2 - 1) / NW2;
+    static constexpr int LTF = TF + 2;                 // slices per landed row (TMA path)
+    static constexpr size_t LAND_BYTES = (size_t)(MC + 1) * LTF * 8;
     VHD static int wpos(int lam) { return lam < LN ? 2 * lam : 2 * (lam - LN) + 1; }
     struct Cp { float r, i; };
-    template <int MODE, bool LIVE>
+    // SMEM: q points into the tile that the TMA engine has landed in shared memory (pk_inv_kernel)
+    template <int MODE, bool LIVE, bool SMEM = false>
     VHD static Cp ldbin(const InvArgs<float> &p, const char *q, int k) {
         Cp v; v.r = 0.f; v.i = 0.f;
         if (LIVE) {
 #ifdef VEILS_ABLATE
             if (p.dbg & 1) { v.r = 1.f + k; v.i = 0.5f; return v; }      // ablation: no global loads
 #endif
-            const fl2 t = ldS(q);
+            const fl2 t = SMEM ? *reinterpret_cast<const fl2 *>(q) : ldS(q);
             v.r = t.x; v.i = t.y;
             if (MODE == 3 && k >= 1 && k <= MC - 1) { v.r *= p.rfac2x; v.i *= p.rfac2x; }
         }
@@ -806,25 +810,53 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     }
     template <int MODE, bool LIVE>
     VHD static void p1p_t(const PkInvCtx &c, int tid, int it, const char *sb) {
+        const int w = tid / TF + it * NW2;
+        if (w >= L1 / 2) return;
+        Cp x0[R1], x1[R1], xn;
+        p1p_load<MODE, LIVE, false>(c, tid, it, sb, x0, x1, xn);
+        p1p_rest(c, tid, it, x0, x1, xn);
+    }
+    // loads of the 2 R1 (+1) bins of group pair w for this thread's slice.  SMEM = false: from S
+    // (sb = byte pointer of (row 0, this slice's column)); SMEM = true: from the tile the TMA engine
+    // has landed over the work buffer -- row j R1 + a holds bin j + L1 a, [TF slices] of 8 bytes.
+    template <int MODE, bool LIVE, bool SMEM>
+    VHD static void p1p_load(const PkInvCtx &c, int tid, int it, const char *sb, Cp (&x0)[R1], Cp (&x1)[R1], Cp &xn) {
         const InvArgs<float> &p = c.a;
+        const int lam = tid % TF, w = tid / TF + it * NW2;
+        xn.r = xn.i = 0.f;
+        if (w >= L1 / 2) return;
+        const int j0 = w, j1 = w == 0 ? L1 / 2 : L1 - w;
+        if (SMEM) {
+            // landed rows are LTF = TF + 2 slices wide (the load starts at an even column)
+            const char *base = reinterpret_cast<const char *>(c.work) + (lam + c.land_shift) * 8;
+            const char *q0 = base + (size_t)(j0 * R1) * (LTF * 8);
+            const char *q1 = base + (size_t)(j1 * R1) * (LTF * 8);
+#pragma unroll
+            for (int a = 0; a < R1; ++a) {
+                x0[a] = ldbin<MODE, LIVE, true>(p, q0 + a * (LTF * 8), j0 + L1 * a);
+                x1[a] = ldbin<MODE, LIVE, true>(p, q1 + a * (LTF * 8), j1 + L1 * a);
+            }
+            if (w == 0) xn = ldbin<MODE, LIVE, true>(p, base + (size_t)MC * (LTF * 8), MC);
+            return;
+        }
+        const int64_t rb = p.ldp * 8;
+        const char *q0 = sb + j0 * rb, *q1 = sb + j1 * rb;
+        const int64_t st = L1 * rb;
+#pragma unroll
+        for (int a = 0; a < R1; ++a) {
+            x0[a] = ldbin<MODE, LIVE>(p, q0, j0 + L1 * a);
+            x1[a] = ldbin<MODE, LIVE>(p, q1, j1 + L1 * a);
+            q0 += st;
+            keep(q0);
+            q1 += st;
+            keep(q1);
+        }
+        if (w == 0) xn = ldbin<MODE, LIVE>(p, sb + MC * rb, MC);
+    }
+    VHD static void p1p_rest(const PkInvCtx &c, int tid, int it, const Cp (&x0)[R1], const Cp (&x1)[R1], const Cp &xn) {
         const int lam = tid % TF, w = tid / TF + it * NW2;
         if (w >= L1 / 2) return;
         const int j0 = w, j1 = w == 0 ? L1 / 2 : L1 - w;
-        const int64_t rb = p.ldp * 8;
-        Cp x0[R1], x1[R1];
-        {
-            const char *q0 = sb + j0 * rb, *q1 = sb + j1 * rb;
-            const int64_t st = L1 * rb;
-#pragma unroll
-            for (int a = 0; a < R1; ++a) {
-                x0[a] = ldbin<MODE, LIVE>(p, q0, j0 + L1 * a);
-                x1[a] = ldbin<MODE, LIVE>(p, q1, j1 + L1 * a);
-                q0 += st;
-                keep(q0);
-                q1 += st;
-                keep(q1);
-            }
-        }
         const float *twp = c.tw + GEO::TWP;
         float lr[R1], li[R1], hr[R1], hi_[R1];
         if (w != 0) {
@@ -835,7 +867,6 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         } else {
             // group 0: bin L1 a <-> L1 (R1 - a), DC <-> Nyquist (their imaginary parts are ignored,
             // irfft semantics); group L1/2: bin L1/2 + L1 a <-> L1/2 + L1 (R1-1-a)
-            const Cp xn = ldbin<MODE, LIVE>(p, sb + MC * rb, MC);
             lr[0] = x0[0].r + xn.r;
             li[0] = x0[0].r - xn.r;
 #pragma unroll
@@ -869,6 +900,23 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             const C2 z = cmulwc(v[cc], wr, wi, bc(0.f) - wi);
             w0[(L1 * cc * 2) * TF] = lo(z.x); w0[(L1 * cc * 2 + 1) * TF] = lo(z.y);
             w1[(L1 * cc * 2) * TF] = hi(z.x); w1[(L1 * cc * 2 + 1) * TF] = hi(z.y);
+        }
+    }
+    // slice of this thread inside [q0, q1) and inside S?
+    VHD static bool p1p_live(const PkInvCtx &c, int tid) {
+        const InvArgs<float> &p = c.a;
+        const int64_t q = c.qa + tid % TF, col = q - p.p_min;
+        return q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+    }
+    // from the landed tile (TMA path): loads only; the caller synchronises the CTA before p1p_rest
+    VHD static void p1p_load_smem(const PkInvCtx &c, int tid, int it, Cp (&x0)[R1], Cp (&x1)[R1], Cp &xn) {
+        const bool live = p1p_live(c, tid);
+        if (c.a.mode == 3) {
+            if (live) p1p_load<3, true, true>(c, tid, it, nullptr, x0, x1, xn);
+            else p1p_load<3, false, true>(c, tid, it, nullptr, x0, x1, xn);
+        } else {
+            if (live) p1p_load<2, true, true>(c, tid, it, nullptr, x0, x1, xn);
+            else p1p_load<2, false, true>(c, tid, it, nullptr, x0, x1, xn);
         }
     }
     VHD static void p1p(const PkInvCtx &c, int tid, int it) {

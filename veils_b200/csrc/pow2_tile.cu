@@ -101,9 +101,9 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
                     const int mul = args.spectrogram ? 1 : MUL;
                     const int p0 = (int)(cpt * TF) * mul;
                     constexpr unsigned RB = TF * (unsigned)sizeof(cx<T>);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB, p0, g, 0, (int)cb);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(gp) * RB, p0, gp, 0, (int)cb);
-                    if (s2 == 0) tma::store_4d(&smap, wbase + K::MC * RB, p0, 0, K::RL, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB, p0, 0, g, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(gp) * RB, p0, 0, gp, (int)cb);
+                    if (s2 == 0) tma::store_4d(&smap, wbase + K::MC * RB, p0, K::RL, 0, (int)cb);
                     tma::commit_group();
                 }
             };

@@ -28,25 +28,29 @@ inline EncodeFn encode_fn() {
 }
 
 // Tensor map of S[b][f][p] (element size esz = 4 or 8 bytes, row pitch ldp elements) seen as
-//   dim0 = p (size P), dim1 = g (size G, stride ldp), dim2 = d (size RL + 1, stride G ldp),
+//   dim0 = p (size P), dim1 = d (size RL + 1, stride G ldp), dim2 = g (size G, stride ldp),
 //   dim3 = b (size B, stride F ldp):  row f = g + G d  (F = G RL + 1; d = RL exists for g = 0 only
-//   and is the Nyquist row -- the other (g, RL) coordinates are never touched).
-// Box = [TF slices][1][rows][1].  Returns false when the layout cannot be described (alignment).
+//   and is the Nyquist row -- the other (RL, g) coordinates are never touched).
+// Box = [TF slices][rows][1][1]; coordinates (p, d, g, b).  (This dimension order is the one the
+// load direction accepts: with g before d, tensor loads / prefetches trap as "illegal instruction"
+// on this driver while stores work.)  Returns false when the layout cannot be described (alignment).
+// Tensor LOADS need a 16-byte aligned start address in the innermost dimension (measured: an odd
+// column of 8-byte elements traps as "illegal instruction"); stores from aligned tiles never hit it.
 inline bool make_s_map(CUtensorMap *m, const void *base, int esz, int64_t P, int64_t ldp, int64_t F, int64_t B,
                        int G, int RL, int TF, int box_rows) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
     if (((uintptr_t)base & 15) != 0 || (ldp * esz) % 16 != 0 || (TF * esz) % 16 != 0) return false;
     if (P <= 0 || B <= 0 || P >= (1LL << 32) || B >= (1LL << 32)) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)P, (cuuint64_t)G, (cuuint64_t)(RL + 1), (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)(ldp * esz), (cuuint64_t)(G * ldp * esz), (cuuint64_t)(F * ldp * esz)};
+    const cuuint64_t dims[4] = {(cuuint64_t)P, (cuuint64_t)(RL + 1), (cuuint64_t)G, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)(G * ldp * esz), (cuuint64_t)(ldp * esz), (cuuint64_t)(F * ldp * esz)};
     for (int i = 0; i < 3; ++i)
         if (strides[i] >= (1ULL << 40) || strides[i] % 16 != 0) return false;
-    const cuuint32_t box[4] = {(cuuint32_t)TF, 1, (cuuint32_t)box_rows, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)TF, (cuuint32_t)box_rows, 1, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     const CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
