@@ -147,7 +147,8 @@ inline size_t pk_inv_work_bytes(int64_t N) {
     if (ola > work) work = ola;
     // TMA path of the one-sided inverse: the S tile lands over this buffer, [Mc + 1 rows][TF + 2 slices]
     const size_t land = (size_t)(G::MC + 1) * (TF + 2) * 8;
-    if (LOGMC <= 11 && land > work) work = land;
+    if (LOGMC == 8 && land > work) work = land;        // only mfft = 512 takes the TMA path (pow2_pk.cu); a larger
+                                                       // carve-out elsewhere only shrinks L1 (mfft 4096: 2.57 -> 2.88 ms)
     return (work + 127) & ~(size_t)127;
 }
 // streaming overlap-add: chunk geometry for a launch (owned slices qh0..qh1 per signal)
