@@ -186,7 +186,7 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
 template <int LOGMC, int TF, int NSUB, bool ONES>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
-              const int64_t total, const int work_bytes, const int use_tma,
+              const int64_t total, const int work_bytes, const int use_tma, const int acc_path,
               const __grid_constant__ CUtensorMap smap, const __grid_constant__ CUtensorMap smap_nyq) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using K = PkInv<LOGMC, TF, NSUB>;
@@ -198,6 +198,9 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
     float *carry0 = reinterpret_cast<float *>(smem + work_bytes);
     const int carry_elems = (args.N + 3) & ~3;
     float *carry1 = carry0 + carry_elems;
+    int acc_off = work_bytes + 2 * 4 * carry_elems;
+    if (K::STAB) acc_off += 4 * K::TWN + (int)sizeof(ITab) * K::MC;
+    acc_off = (acc_off + 15) & ~15;
     if (K::STAB) {
         float *stw = carry1 + carry_elems;
         ITab *sitab = reinterpret_cast<ITab *>(stw + K::TWN);
@@ -222,9 +225,80 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         tma::fence_mbar_init();
     }
     __syncthreads();
+    const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
+    if (ONES && LOGMC == 8 && tma_path && acc_path) {
+        // mfft 512, 75 % overlap: TMA-landed S + accumulator overlap-add.  The next tile's boxes are
+        // requested as soon as the last pass has read the work buffer and land during the four
+        // accumulator passes and the output of the current tile.
+        float *acc = reinterpret_cast<float *>(smem + acc_off);
+        auto land = [&](int64_t b, int64_t qa) {
+            tma::fence_async_smem();
+            const unsigned wbase = tma::smem_u32(c.work);
+            const int col = (int)((qa - args.p_min) & ~(int64_t)1);
+            tma::mbar_expect_tx(land_bar, (unsigned)K::LAND_BYTES);
+#pragma unroll 1
+            for (int j = 0; j < K::L1; ++j)
+                tma::load_4d(&smap, wbase + j * (K::R1 * K::LTF * 8), land_bar, col, 0, j, (int)b);
+            tma::load_4d(&smap_nyq, wbase + K::MC * (K::LTF * 8), land_bar, col, K::R1, 0, (int)b);
+        };
+        int64_t ch = blockIdx.x;
+        int t = 0;
+        bool have = ch < total;
+        int64_t b = 0, qa = 0;
+        if (have) {
+            b = ch / args.cps;
+            qa = args.qh0 + (ch - b * args.cps) * lc - args.halo;
+            if (tid == 0) land(b, qa);
+        }
+        while (have) {
+            // the tile after this one (same chunk, or the first tile of this CTA's next chunk)
+            int64_t chn = ch, bn = b, qan = qa + TF;
+            int tn = t + 1;
+            bool have_n = true;
+            if (tn >= args.chunk_tiles || qan > args.qh1) {
+                chn = ch + gridDim.x;
+                tn = 0;
+                have_n = chn < total;
+                if (have_n) {
+                    bn = chn / args.cps;
+                    qan = args.qh0 + (chn - bn * args.cps) * lc - args.halo;
+                }
+            }
+            c.b = b;
+            c.qa = qa;
+            c.first = t == 0;
+            c.land_shift = (int)((qa - args.p_min) & 1);
+            typename K::Cp x0[K::R1], x1[K::R1], xn;
+            tma::mbar_wait(land_bar, land_phase);
+            land_phase ^= 1;
+            K::p1p_load_smem(c, tid, 0, x0, x1, xn);
+            __syncthreads();                   // every thread holds its bins before anyone overwrites the tile
+            K::p1p_rest(c, tid, 0, x0, x1, xn);
+            __syncthreads();
+            {
+                C2 r[K::GPT][K::RL];
+                K::last_load(c, tid, r);
+                __syncthreads();               // the work buffer is free from here on
+                if (have_n && tid == 0) land(bn, qan);
+                if (c.first) K::ola_zero_head(tid, acc);
+                K::template ola_acc<3>(c, tid, r, acc);
+                __syncthreads();
+                K::template ola_acc<2>(c, tid, r, acc);
+                __syncthreads();
+                K::template ola_acc<1>(c, tid, r, acc);
+                __syncthreads();
+                K::template ola_acc<0>(c, tid, r, acc);
+            }
+            __syncthreads();
+            const fl2 tail = K::ola_out(c, tid, acc);
+            __syncthreads();                   // head and tail read before the head is replaced
+            K::ola_keep_tail(tid, acc, tail);
+            ch = chn; t = tn; b = bn; qa = qan; have = have_n;
+        }
+        return;
+    }
     // A CTA walks the tiles of one chunk of one signal in order (streaming overlap-add): only the
     // first tile of a chunk re-computes the halo slices, every other tile owns all TF slices.
-    const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
     for (int64_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
         c.b = ch / args.cps;
         const int64_t a0 = args.qh0 + (ch - c.b * args.cps) * lc;      // first owned slice
@@ -379,8 +453,8 @@ struct PkInvLaunch {
         a.dbg = pk_env_int("VEILS_PK_DBG_INV", 0);
         const int work_bytes = (int)pk_inv_work_bytes<LOGMC, TF>(p.N);
         const size_t smem = pk_inv_smem_bytes<LOGMC, TF>(p.N);
-        using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int, const int, const CUtensorMap,
-                               const CUtensorMap);
+        using KernT = void (*)(const InvArgs<float>, const ITab *, const int64_t, const int, const int, const int,
+                               const CUtensorMap, const CUtensorMap);
         KernT kern = p.mode >= 2 ? (KernT)pk_inv_kernel<LOGMC, TF, NSUB, true> : (KernT)pk_inv_kernel<LOGMC, TF, NSUB, false>;
         // one-sided layouts: S tiles land through the TMA engine when S can be described by a tensor map
         // (16-byte aligned base / row pitch) and the landed tile fits the work buffer
@@ -397,6 +471,10 @@ struct PkInvLaunch {
                             (size_t)work_bytes >= K::LAND_BYTES &&
                             tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1) &&
                             tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
+        // accumulator overlap-add: 75 % overlap with the default roll, 8-byte aligned output pairs
+        const int acc_path = use_tma && a.halo == 3 && p.N == p.M && 4 * p.H == p.N && p.ps == p.N / 2 && a.pair &&
+                             p.out_pitch % 2 == 0 && p.k0 % 2 == 0 && (((uintptr_t)xo) & 7) == 0 &&
+                             !pk_env_int("VEILS_PK_NO_ACC", 0);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
@@ -406,7 +484,7 @@ struct PkInvLaunch {
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         pk_inv_chunks(a, p, TF, p.batch, cap);
         const int64_t total = a.cps * p.batch;
-        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes, use_tma, smap, smap_nyq);
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes, use_tma, acc_path, smap, smap_nyq);
         ++g_launch_count;
         return cudaGetLastError();
     }

@@ -169,6 +169,7 @@ inline size_t pk_inv_smem_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
     size_t b = pk_inv_work_bytes<LOGMC, TF>(N) + 2 * 4 * (size_t)((N + 3) & ~3LL);   // + 2 carry buffers
     if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(ITab) * (size_t)G::MC;
+    if (LOGMC == 8) b += 4 * (size_t)((TF + 3) * (G::MC / 2 + 2)) + 16;              // accumulator overlap-add (mfft 512)
     return b;
 }
 

@@ -1003,6 +1003,86 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
         }
     }
 
+    // ================= accumulator overlap-add (75 % overlap, m_num = mfft = 4 hop, default roll) ======
+    // Instead of TF rows of m_num samples (66 KB) the tile's output lives in ONE padded accumulator
+    // acc[u + 2 (u / H)], u in [0, (TF + 3) H): sample u of the tile, slice sl contributes its quarter
+    // c = 0..3 to u in [(sl + c) H, (sl + c + 1) H).  Four passes, OLDEST slice first (c = 3, 2, 1, 0),
+    // each a conflict-free store / read-modify-write of one quarter of every slice: within a pass every
+    // accumulator cell receives exactly one contribution, across passes the slices arrive in increasing
+    // q -- the reference's summation order (src/lib.rs:853, 876-910), deterministic, no atomics.  The
+    // head [0, 3H) carries the previous tile's tail.  The work buffer is free as soon as the last
+    // pass has loaded its inputs, so the next tile's S boxes land during these passes (pk_inv_kernel).
+    VHD static float mul_rn(float x, float y) {
+#if defined(__CUDA_ARCH__)
+        return __fmul_rn(x, y);
+#else
+        return x * y;
+#endif
+    }
+    static constexpr int HC = MC / 2;                  // hop of this path (m_num = 2 Mc = 4 hop)
+    static constexpr int HP = HC + 2;                  // padded quarter: lanes (slices) hit distinct banks
+    static constexpr int ACC_FLOATS = (TF + 3) * HP;
+    VHD static int apos(int u) { return u + 2 * (u / HC); }
+    template <int Q>
+    VHD static void ola_acc(const PkInvCtx &c, int tid, const C2 (&r)[GPT][RL], float *acc) {
+        static_assert(GPT == 1 || Q >= 0, "");
+        const int l = tid % LN, g = tid / LN;
+        float *a0 = acc + l * HP + 2 * Q, *a1 = a0 + LN * HP;
+        const ITab *tg = c.itab + g;
+#pragma unroll
+        for (int dd = 0; dd < RL / 4; ++dd) {
+            constexpr int RQ = RL / 4;
+            const int d = (Q * RQ + dd + RL / 2) % RL;           // sample pairs g + G d of quarter Q (roll = m_num / 2)
+            const ITab e = GEO::it4(tg + G * d);
+            // products rounded on their own (no contraction into the adds below): the sums are then
+            // bit-identical to the row-based overlap-add of the other kernels, whatever path a call takes
+            fl2 a, b;
+            a.x = mul_rn(lo(r[0][d].x), e.d0); a.y = mul_rn(lo(r[0][d].y), e.d1);
+            b.x = mul_rn(hi(r[0][d].x), e.d0); b.y = mul_rn(hi(r[0][d].y), e.d1);
+            fl2 *p0 = reinterpret_cast<fl2 *>(a0 + e.o0), *p1 = reinterpret_cast<fl2 *>(a1 + e.o0);
+            if (Q == 3) {                                         // oldest contribution of every cell it touches
+                *p0 = a;
+                *p1 = b;
+            } else {
+                fl2 t0 = *p0, t1 = *p1;
+                t0.x += a.x; t0.y += a.y;
+                t1.x += b.x; t1.y += b.y;
+                *p0 = t0;
+                *p1 = t1;
+            }
+        }
+    }
+    VHD static void ola_zero_head(int tid, float *acc) {
+        for (int i = tid; i < 3 * HP; i += NT) acc[i] = 0.f;
+    }
+    // completed samples [0, TF H) -> global (clipped to [k0, k1) and, for the first tile of a chunk, to the
+    // samples it owns); returns this thread's pair of the tail (handed to the next tile as its head)
+    VHD static fl2 ola_out(const PkInvCtx &c, int tid, const float *acc) {
+        const InvArgs<float> &p = c.a;
+        constexpr int TFH = TF * HC;
+        const int64_t base = c.qa * (int64_t)HC - p.mid;
+        float *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
+        int64_t ka = base + (c.first ? 3 * HC : 0), kb = base + TFH;
+        if (ka < p.k0) ka = p.k0;
+        if (kb > p.k1) kb = p.k1;
+        const int ua = (int)(ka - base), ub = (int)(kb - base);
+        const bool inner = ua <= 0 && ub >= TFH;
+        for (int u = 2 * tid; u < TFH; u += 2 * NT) {
+            const fl2 o = *reinterpret_cast<const fl2 *>(acc + apos(u));
+            if (inner || (u >= ua && u + 1 < ub)) *reinterpret_cast<fl2 *>(xo + u) = o;
+            else {
+                if (u >= ua && u < ub) xo[u] = o.x;
+                if (u + 1 >= ua && u + 1 < ub) xo[u + 1] = o.y;
+            }
+        }
+        fl2 tail; tail.x = 0.f; tail.y = 0.f;
+        if (2 * tid < 3 * HC) tail = *reinterpret_cast<const fl2 *>(acc + apos(TFH + 2 * tid));
+        return tail;
+    }
+    VHD static void ola_keep_tail(int tid, float *acc, fl2 tail) {
+        if (2 * tid < 3 * HC) *reinterpret_cast<fl2 *>(acc + apos(2 * tid)) = tail;
+    }
+
     // Streaming overlap-add (src/lib.rs:853-911), increasing q:  local sample u = k + mid - qa*H.
     //   u in [0, TF*H)           : completed by this tile -> global memory.  Contributions of earlier
     //                              slices arrive in carry_in (u < N - H); the first tile of a chunk has
