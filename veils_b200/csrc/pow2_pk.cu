@@ -196,7 +196,8 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
     c.work = reinterpret_cast<float *>(smem);
     c.ola = reinterpret_cast<float *>(smem);
     float *carry0 = reinterpret_cast<float *>(smem + work_bytes);
-    const int carry_elems = (args.N + 3) & ~3;
+    // acc_path == 2: accumulator layout [work | landing][tables][accumulator] without carry buffers
+    const int carry_elems = acc_path == 2 ? 0 : (args.N + 3) & ~3;
     float *carry1 = carry0 + carry_elems;
     int acc_off = work_bytes + 2 * 4 * carry_elems;
     if (K::STAB) acc_off += 4 * K::TWN + (int)sizeof(ITab) * K::MC;
@@ -226,7 +227,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
     }
     __syncthreads();
     const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
-    if (ONES && LOGMC == 8 && tma_path && acc_path) {
+    if (ONES && tma_path && acc_path) {
         // mfft 512, 75 % overlap: TMA-landed S + accumulator overlap-add.  The next tile's boxes are
         // requested as soon as the last pass has read the work buffer and land during the four
         // accumulator passes and the output of the current tile.
@@ -275,6 +276,10 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
             __syncthreads();                   // every thread holds its bins before anyone overwrites the tile
             K::p1p_rest(c, tid, 0, x0, x1, xn);
             __syncthreads();
+            if (K::NP == 3) {
+                K::pass_mid(c, tid);
+                __syncthreads();
+            }
             {
                 C2 r[K::GPT][K::RL];
                 K::last_load(c, tid, r);
@@ -290,7 +295,8 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
                 K::template ola_acc<0>(c, tid, r, acc);
             }
             __syncthreads();
-            const fl2 tail = K::ola_out(c, tid, acc);
+            K::ola_out(c, tid, acc);
+            const typename K::Tail tail = K::ola_take_tail(tid, acc);
             __syncthreads();                   // head and tail read before the head is replaced
             K::ola_keep_tail(tid, acc, tail);
             ch = chn; t = tn; b = bn; qa = qan; have = have_n;
@@ -462,29 +468,41 @@ struct PkInvLaunch {
         CUtensorMap smap, smap_nyq;
         memset(&smap, 0, sizeof(smap));
         memset(&smap_nyq, 0, sizeof(smap_nyq));
-        // Measured (profiles/r1c_ablation.txt): 1.05 -> 0.96 ms for mfft = 512 (2 CTAs per SM hide each
-        // other's landing latency); slower for mfft = 256 (1.20 -> 1.62 ms) and for mfft >= 2048
-        // (one CTA per SM: nothing overlaps the landing), so only mfft = 512 takes this path.
-        const int use_tma = LOGMC == 8 && (K::R1 * K::LTF * 8) % 128 == 0 &&
-                            p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
-                            !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) &&
-                            (size_t)work_bytes >= K::LAND_BYTES &&
-                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1) &&
-                            tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
-        // accumulator overlap-add: 75 % overlap with the default roll, 8-byte aligned output pairs
-        const int acc_path = use_tma && a.halo == 3 && p.N == p.M && 4 * p.H == p.N && p.ps == p.N / 2 && a.pair &&
+        // Measured (profiles/r1c_ablation.txt): landing alone (waited for at the start of the tile) pays
+        // only for mfft = 512 (1.05 -> 0.96 ms; slower for mfft 256 and >= 2048); together with the
+        // accumulator overlap-add the next tile lands during the current one's overlap-add.
+        const bool acc_geo = a.halo == 3 && p.N == p.M && 4 * p.H == p.N && p.ps == p.N / 2 && a.pair &&
                              p.out_pitch % 2 == 0 && p.k0 % 2 == 0 && (((uintptr_t)xo) & 7) == 0 &&
                              !pk_env_int("VEILS_PK_NO_ACC", 0);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // measured: mfft 256 1.21 -> 0.98 ms, mfft 512 0.96 -> 0.82 ms; mfft 2048 1.35 -> 1.37 ms and
+        // mfft 4096 2.61 -> 3.26 ms (one CTA per SM, four more CTA-wide barriers) stay on the row-based path
+        const bool acc_size = (LOGMC == 7 || LOGMC == 8) &&
+                              pk_inv_acc_smem_bytes<LOGMC, TF>(p.N) + 1024 <= SMEM_LIMIT;
+        const int use_tma = (LOGMC == 8 || (acc_geo && acc_size)) && (K::R1 * K::LTF * 8) % 128 == 0 &&
+                            p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
+                            !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) &&
+                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1) &&
+                            tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
+        // accumulator overlap-add: 75 % overlap with the default roll, 8-byte aligned output pairs.
+        // 2 = its own shared-memory layout (no carry buffers); the plain TMA path keeps the base layout
+        const int acc_path = (use_tma && acc_geo && acc_size) ? 2 : 0;
+        int work_bytes_l = work_bytes;
+        size_t smem_l = smem;
+        if (acc_path) {
+            work_bytes_l = (int)pk_inv_acc_work_bytes<LOGMC, TF>(p.N);
+            smem_l = pk_inv_acc_smem_bytes<LOGMC, TF>(p.N);
+        }
+        const int use_tma_l = use_tma && (acc_path || (size_t)work_bytes >= K::LAND_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
         if (e != cudaSuccess) return e;
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem_l);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         pk_inv_chunks(a, p, TF, p.batch, cap);
         const int64_t total = a.cps * p.batch;
-        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(a, itab, total, work_bytes, use_tma, acc_path, smap, smap_nyq);
+        kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem_l, st>>>(a, itab, total, work_bytes_l, use_tma_l, acc_path, smap, smap_nyq);
         ++g_launch_count;
         return cudaGetLastError();
     }

@@ -169,7 +169,24 @@ inline size_t pk_inv_smem_bytes(int64_t N) {
     using G = PkGeo<LOGMC, TF, 2>;
     size_t b = pk_inv_work_bytes<LOGMC, TF>(N) + 2 * 4 * (size_t)((N + 3) & ~3LL);   // + 2 carry buffers
     if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(ITab) * (size_t)G::MC;
-    if (LOGMC == 8) b += 4 * (size_t)((TF + 3) * (G::MC / 2 + 2)) + 16;              // accumulator overlap-add (mfft 512)
+    return b;
+}
+// shared memory of the TMA-landing + accumulator path (pow2_pk.cu): [work | landing][tables][accumulator]
+template <int LOGMC, int TF>
+inline size_t pk_inv_acc_work_bytes(int64_t N) {
+    using G = PkGeo<LOGMC, TF, 2>;
+    (void)N;
+    size_t work = 4 * (size_t)G::MC * 2 * TF;
+    const size_t land = (size_t)(G::MC + 1) * (TF + 2) * 8;
+    if (land > work) work = land;
+    return (work + 127) & ~(size_t)127;
+}
+template <int LOGMC, int TF>
+inline size_t pk_inv_acc_smem_bytes(int64_t N) {
+    using G = PkGeo<LOGMC, TF, 2>;
+    size_t b = pk_inv_acc_work_bytes<LOGMC, TF>(N);
+    if (G::STAB) b += 4 * (size_t)G::TWN + sizeof(ITab) * (size_t)G::MC;
+    b += 4 * (size_t)((TF + 3) * (G::MC / 2 + 2)) + 32;
     return b;
 }
 

@@ -1025,30 +1025,34 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
     VHD static int apos(int u) { return u + 2 * (u / HC); }
     template <int Q>
     VHD static void ola_acc(const PkInvCtx &c, int tid, const C2 (&r)[GPT][RL], float *acc) {
-        static_assert(GPT == 1 || Q >= 0, "");
-        const int l = tid % LN, g = tid / LN;
+        const int l = tid % LN, sub = tid / LN;
         float *a0 = acc + l * HP + 2 * Q, *a1 = a0 + LN * HP;
-        const ITab *tg = c.itab + g;
 #pragma unroll
-        for (int dd = 0; dd < RL / 4; ++dd) {
-            constexpr int RQ = RL / 4;
-            const int d = (Q * RQ + dd + RL / 2) % RL;           // sample pairs g + G d of quarter Q (roll = m_num / 2)
-            const ITab e = GEO::it4(tg + G * d);
-            // products rounded on their own (no contraction into the adds below): the sums are then
-            // bit-identical to the row-based overlap-add of the other kernels, whatever path a call takes
-            fl2 a, b;
-            a.x = mul_rn(lo(r[0][d].x), e.d0); a.y = mul_rn(lo(r[0][d].y), e.d1);
-            b.x = mul_rn(hi(r[0][d].x), e.d0); b.y = mul_rn(hi(r[0][d].y), e.d1);
-            fl2 *p0 = reinterpret_cast<fl2 *>(a0 + e.o0), *p1 = reinterpret_cast<fl2 *>(a1 + e.o0);
-            if (Q == 3) {                                         // oldest contribution of every cell it touches
-                *p0 = a;
-                *p1 = b;
-            } else {
-                fl2 t0 = *p0, t1 = *p1;
-                t0.x += a.x; t0.y += a.y;
-                t1.x += b.x; t1.y += b.y;
-                *p0 = t0;
-                *p1 = t1;
+        for (int i = 0; i < GPT; ++i) {
+            const int g = sub + NSUB * i;
+            if (g >= G) continue;
+            const ITab *tg = c.itab + g;
+#pragma unroll
+            for (int dd = 0; dd < RL / 4; ++dd) {
+                constexpr int RQ = RL / 4;
+                const int d = (Q * RQ + dd + RL / 2) % RL;       // sample pairs g + G d of quarter Q (roll = m_num / 2)
+                const ITab e = GEO::it4(tg + G * d);
+                // products rounded on their own (no contraction into the adds below): the sums are then
+                // bit-identical to the row-based overlap-add of the other kernels, whatever path a call takes
+                fl2 a, b;
+                a.x = mul_rn(lo(r[i][d].x), e.d0); a.y = mul_rn(lo(r[i][d].y), e.d1);
+                b.x = mul_rn(hi(r[i][d].x), e.d0); b.y = mul_rn(hi(r[i][d].y), e.d1);
+                fl2 *p0 = reinterpret_cast<fl2 *>(a0 + e.o0), *p1 = reinterpret_cast<fl2 *>(a1 + e.o0);
+                if (Q == 3) {                                     // oldest contribution of every cell it touches
+                    *p0 = a;
+                    *p1 = b;
+                } else {
+                    fl2 t0 = *p0, t1 = *p1;
+                    t0.x += a.x; t0.y += a.y;
+                    t1.x += b.x; t1.y += b.y;
+                    *p0 = t0;
+                    *p1 = t1;
+                }
             }
         }
     }
@@ -1076,11 +1080,27 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             }
         }
         fl2 tail; tail.x = 0.f; tail.y = 0.f;
-        if (2 * tid < 3 * HC) tail = *reinterpret_cast<const fl2 *>(acc + apos(TFH + 2 * tid));
         return tail;
     }
-    VHD static void ola_keep_tail(int tid, float *acc, fl2 tail) {
-        if (2 * tid < 3 * HC) *reinterpret_cast<fl2 *>(acc + apos(2 * tid)) = tail;
+    // the tail [TF H, TF H + 3H) becomes the next tile's head: each thread carries TPT pairs in registers
+    static constexpr int TPT = (3 * HC / 2 + NT - 1) / NT;
+    struct Tail { fl2 v[TPT]; };
+    VHD static Tail ola_take_tail(int tid, const float *acc) {
+        Tail t;
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            const int u = 2 * (tid + i * NT);
+            t.v[i].x = t.v[i].y = 0.f;
+            if (u < 3 * HC) t.v[i] = *reinterpret_cast<const fl2 *>(acc + apos(TF * HC + u));
+        }
+        return t;
+    }
+    VHD static void ola_keep_tail(int tid, float *acc, const Tail &t) {
+#pragma unroll
+        for (int i = 0; i < TPT; ++i) {
+            const int u = 2 * (tid + i * NT);
+            if (u < 3 * HC) *reinterpret_cast<fl2 *>(acc + apos(u)) = t.v[i];
+        }
     }
 
     // Streaming overlap-add (src/lib.rs:853-911), increasing q:  local sample u = k + mid - qa*H.
