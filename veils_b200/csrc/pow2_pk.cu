@@ -183,6 +183,23 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
     if (STAGE) tma::wait_all();
 }
 
+// Request the S tile whose slice 0 is column `col0` of signal b, landing over the work buffer: ONE box
+// [L1 groups][R1 rows][TF + 2 slices] (shared-memory row j R1 + a = bin j + L1 a) plus the Nyquist
+// row.  (One box per group costs the issuing warp ~120 cycles per TMA instruction -- 17 of them held
+// the whole CTA at the next barrier for 16 % of the kernel time, profiles/r1e_ncu_full_bench_c2.txt.)
+// The start column is rounded down to even: 16-byte aligned.
+template <typename K>
+__device__ __forceinline__ void pk_land(const CUtensorMap &smap, const CUtensorMap &smap_nyq, const float *work,
+                                        unsigned land_bar, int tid, int64_t b, int64_t col0) {
+    if (tid != 0) return;
+    tma::fence_async_smem();                   // earlier generic-proxy accesses to this buffer are ordered first
+    const unsigned wbase = tma::smem_u32(work);
+    const int col = (int)(col0 & ~(int64_t)1);
+    tma::mbar_expect_tx(land_bar, (unsigned)K::LAND_BYTES);
+    tma::load_4d(&smap, wbase, land_bar, col, 0, 0, (int)b);
+    tma::load_4d(&smap_nyq, wbase + K::MC * (K::LTF * 8), land_bar, col, K::R1, 0, (int)b);
+}
+
 template <int LOGMC, int TF, int NSUB, bool ONES>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restrict__ itab_g,
@@ -232,16 +249,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         // requested as soon as the last pass has read the work buffer and land during the four
         // accumulator passes and the output of the current tile.
         float *acc = reinterpret_cast<float *>(smem + acc_off);
-        auto land = [&](int64_t b, int64_t qa) {
-            tma::fence_async_smem();
-            const unsigned wbase = tma::smem_u32(c.work);
-            const int col = (int)((qa - args.p_min) & ~(int64_t)1);
-            tma::mbar_expect_tx(land_bar, (unsigned)K::LAND_BYTES);
-#pragma unroll 1
-            for (int j = 0; j < K::L1; ++j)
-                tma::load_4d(&smap, wbase + j * (K::R1 * K::LTF * 8), land_bar, col, 0, j, (int)b);
-            tma::load_4d(&smap_nyq, wbase + K::MC * (K::LTF * 8), land_bar, col, K::R1, 0, (int)b);
-        };
+        auto land = [&](int64_t b, int64_t qa) { pk_land<K>(smap, smap_nyq, c.work, land_bar, tid, b, qa - args.p_min); };
         int64_t ch = blockIdx.x;
         int t = 0;
         bool have = ch < total;
@@ -249,7 +257,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
         if (have) {
             b = ch / args.cps;
             qa = args.qh0 + (ch - b * args.cps) * lc - args.halo;
-            if (tid == 0) land(b, qa);
+            land(b, qa);
         }
         while (have) {
             // the tile after this one (same chunk, or the first tile of this CTA's next chunk)
@@ -284,7 +292,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
                 C2 r[K::GPT][K::RL];
                 K::last_load(c, tid, r);
                 __syncthreads();               // the work buffer is free from here on
-                if (have_n && tid == 0) land(bn, qan);
+                if (have_n) land(bn, qan);
                 if (c.first) K::ola_zero_head(tid, acc);
                 K::template ola_acc<3>(c, tid, r, acc);
                 __syncthreads();
@@ -318,17 +326,7 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
             c.carry_out = flip ? carry0 : carry1;
             flip ^= 1;
             if (tma_path) {
-                if (tid == 0) {
-                    // the previous tile's overlap rows (generic-proxy writes) lived in this buffer
-                    tma::fence_async_smem();
-                    const unsigned wbase = tma::smem_u32(c.work);
-                    const int col = (int)((c.qa - args.p_min) & ~(int64_t)1);      // even: 16-byte aligned start
-                    tma::mbar_expect_tx(land_bar, (unsigned)K::LAND_BYTES);
-#pragma unroll 1
-                    for (int j = 0; j < K::L1; ++j)
-                        tma::load_4d(&smap, wbase + j * (K::R1 * K::LTF * 8), land_bar, col, 0, j, (int)c.b);
-                    tma::load_4d(&smap_nyq, wbase + K::MC * (K::LTF * 8), land_bar, col, K::R1, 0, (int)c.b);
-                }
+                pk_land<K>(smap, smap_nyq, c.work, land_bar, tid, c.b, c.qa - args.p_min);
                 c.land_shift = (int)((c.qa - args.p_min) & 1);
                 typename K::Cp x0[K::R1], x1[K::R1], xn;
                 tma::mbar_wait(land_bar, land_phase);
@@ -481,7 +479,8 @@ struct PkInvLaunch {
         const int use_tma = (LOGMC == 8 || (acc_geo && acc_size)) && (K::R1 * K::LTF * 8) % 128 == 0 &&
                             p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
                             !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) &&
-                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1) &&
+                            K::L1 <= 256 &&
+                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1, K::L1) &&
                             tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
         // accumulator overlap-add: 75 % overlap with the default roll, 8-byte aligned output pairs.
         // 2 = its own shared-memory layout (no carry buffers); the plain TMA path keeps the base layout

@@ -37,7 +37,7 @@ inline EncodeFn encode_fn() {
 // Tensor LOADS need a 16-byte aligned start address in the innermost dimension (measured: an odd
 // column of 8-byte elements traps as "illegal instruction"); stores from aligned tiles never hit it.
 inline bool make_s_map(CUtensorMap *m, const void *base, int esz, int64_t P, int64_t ldp, int64_t F, int64_t B,
-                       int G, int RL, int TF, int box_rows) {
+                       int G, int RL, int TF, int box_rows, int box_groups = 1) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
     if (((uintptr_t)base & 15) != 0 || (ldp * esz) % 16 != 0 || (TF * esz) % 16 != 0) return false;
@@ -46,7 +46,7 @@ inline bool make_s_map(CUtensorMap *m, const void *base, int esz, int64_t P, int
     const cuuint64_t strides[3] = {(cuuint64_t)(G * ldp * esz), (cuuint64_t)(ldp * esz), (cuuint64_t)(F * ldp * esz)};
     for (int i = 0; i < 3; ++i)
         if (strides[i] >= (1ULL << 40) || strides[i] % 16 != 0) return false;
-    const cuuint32_t box[4] = {(cuuint32_t)TF, (cuuint32_t)box_rows, 1, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)TF, (cuuint32_t)box_rows, (cuuint32_t)box_groups, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
     const CUresult r = fn(m, dt, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
