@@ -35,7 +35,8 @@ template <int LOGMC, int TF, int NSUB, bool ONES, bool SPEC, bool STAGE>
 __global__ void __launch_bounds__((TF / 2) * NSUB, pk_min_ctas<LOGMC, TF, (TF / 2) * NSUB>())
 pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restrict__ ptab_g,
               const int64_t total, const int xin_elems, const int zero_off, const int stagger_ns,
-              const int num_sms, const __grid_constant__ CUtensorMap smap) {
+              const int num_sms, const __grid_constant__ CUtensorMap smap,
+              const __grid_constant__ CUtensorMap smap_tile) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using K = PkFwd<LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -56,6 +57,12 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         c.ptab = ptab_g;
     }
     constexpr bool SPLIT1 = STAGE && K::L1 == NSUB;
+    // 2-pass plans, complex output: the staged rows of all groups are contiguous (row g RL + d), so the
+    // whole tile leaves as ONE box [G][RL][TF] (+ the Nyquist row), requested by one thread after the
+    // barrier at the top of the next iteration -- a TMA instruction costs the issuing warp ~120 cycles,
+    // 17 per tile spread over the warps' last passes cost ~9 % of the kernel
+    constexpr bool ONEBOX = SPLIT1 && !SPEC && K::NP == 2;
+    int64_t pb = 0, ppt = 0;               // previous tile (ONEBOX)
     const unsigned drain_bar = tma::smem_u32(c.work + (size_t)K::MC * 2 * TF + PK_NYQ_ROW - 4);
     if (SPLIT1 && tid == 0) {
         tma::mbar_init(drain_bar, K::NT / TF);
@@ -86,6 +93,12 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         // do not touch the work buffer) and is handed to the other threads through an mbarrier.
         if (STAGE && !SPLIT1) tma::wait_read_all();
         __syncthreads();
+        if (ONEBOX && it > 0 && tid == 0) {
+            const unsigned wbase = tma::smem_u32(c.work);
+            tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            tma::store_4d(&smap, wbase + K::MC * (TF * 8), (int)(ppt * TF), K::RL, 0, (int)pb);
+            tma::commit_group();
+        }
         float *cur = (K::DBUF && (it & 1)) ? xin1 : xin0;
         const int64_t wn = w + gridDim.x;
         int64_t nb = cb + gb, npt = cpt + gr;
@@ -146,6 +159,7 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
                 }
 #endif
                 tma::fence_async_smem();
+                if (ONEBOX) continue;           // requested after the next barrier, by one thread
                 __syncwarp();
                 const int lam = tid % TF, wg = tid / TF + i * K::NW2;
 #ifdef VEILS_ABLATE
@@ -177,8 +191,19 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
                 K::template last_emit_v<ONES, SPEC, false>(c, tid, i, u, nullptr);
             }
         }
+        pb = cb;
+        ppt = cpt;
         cb = nb;
         cpt = npt;
+    }
+    if (ONEBOX) {
+        __syncthreads();
+        if (blockIdx.x < total && tid == 0) {  // the last tile of this CTA
+            const unsigned wbase = tma::smem_u32(c.work);
+            tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            tma::store_4d(&smap, wbase + K::MC * (TF * 8), (int)(ppt * TF), K::RL, 0, (int)pb);
+            tma::commit_group();
+        }
     }
     if (STAGE) tma::wait_all();
 }
@@ -418,15 +443,18 @@ struct PkFwdLaunch {
         const int xin_elems = (int)((fwd_xin_elems(p.N, p.H, TF, a.lay) + 3) & ~3LL);
         const size_t smem = pk_fwd_smem_bytes<LOGMC, TF>(p.N, xin_elems);
         using KernT = void (*)(const FwdArgs<float>, const PTab *, const int64_t, const int, const int, const int, const int,
-                               const CUtensorMap);
+                               const CUtensorMap, const CUtensorMap);
         const bool ones = p.mode >= 2, spec = p.spectrogram != 0;
         using K = PkFwd<LOGMC, TF, NSUB>;
         // one-sided layouts leave through the TMA engine when S can be described by a tensor map
         // (16-byte aligned base and row pitch); VEILS_PK_NO_TMA=1 forces the plain-store kernels
-        CUtensorMap smap;
+        CUtensorMap smap, smap_tile;
         memset(&smap, 0, sizeof(smap));
+        memset(&smap_tile, 0, sizeof(smap_tile));
         const bool stage = ones && p.batch < (1LL << 31) && !pk_env_int("VEILS_PK_NO_TMA", 0) &&
-                           tma::make_s_map(&smap, out, spec ? 4 : 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL);
+                           tma::make_s_map(&smap, out, spec ? 4 : 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL) &&
+                           (spec || K::G > 256 ||
+                            tma::make_s_map(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL, K::G));
         KernT kern = stage ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, true>)
                    : ones  ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, false>)
                            : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false, false>);
@@ -439,7 +467,7 @@ struct PkFwdLaunch {
         const int64_t total = a.ptiles * p.batch;
         const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(
-            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms(), smap);
+            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms(), smap, smap_tile);
         ++g_launch_count;
         return cudaGetLastError();
     }
