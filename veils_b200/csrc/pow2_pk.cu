@@ -500,9 +500,9 @@ struct PkInvLaunch {
         const bool acc_geo = a.halo == 3 && p.N == p.M && 4 * p.H == p.N && p.ps == p.N / 2 && a.pair &&
                              p.out_pitch % 2 == 0 && p.k0 % 2 == 0 && (((uintptr_t)xo) & 7) == 0 &&
                              !pk_env_int("VEILS_PK_NO_ACC", 0);
-        // measured: mfft 256 1.21 -> 0.98 ms, mfft 512 0.96 -> 0.82 ms; mfft 2048 1.35 -> 1.37 ms and
-        // mfft 4096 2.61 -> 3.26 ms (one CTA per SM, four more CTA-wide barriers) stay on the row-based path
-        const bool acc_size = (LOGMC == 7 || LOGMC == 8) &&
+        // measured (one landing box per tile): mfft 256 1.21 -> 0.98 ms, mfft 512 0.96 -> 0.77 ms,
+        // mfft 2048 1.32 -> 1.14 ms, mfft 4096 2.66 -> 2.55 ms (mfft 1024 has two group pairs per thread)
+        const bool acc_size = (LOGMC == 7 || LOGMC == 8 || LOGMC == 10 || LOGMC == 11) &&
                               pk_inv_acc_smem_bytes<LOGMC, TF>(p.N) + 1024 <= SMEM_LIMIT;
         const int use_tma = (LOGMC == 8 || (acc_geo && acc_size)) && (K::R1 * K::LTF * 8) % 128 == 0 &&
                             p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
