@@ -61,7 +61,7 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
     // whole tile leaves as ONE box [G][RL][TF] (+ the Nyquist row), requested by one thread after the
     // barrier at the top of the next iteration -- a TMA instruction costs the issuing warp ~120 cycles,
     // 17 per tile spread over the warps' last passes cost ~9 % of the kernel
-    constexpr bool ONEBOX = SPLIT1 && !SPEC && K::NP == 2;
+    constexpr bool ONEBOX = SPLIT1 && !SPEC;   // 3-pass plans: the same through a 5-D map (tma::make_s_map5)
     int64_t pb = 0, ppt = 0;               // previous tile (ONEBOX)
     const unsigned drain_bar = tma::smem_u32(c.work + (size_t)K::MC * 2 * TF + PK_NYQ_ROW - 4);
     if (SPLIT1 && tid == 0) {
@@ -95,7 +95,8 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         __syncthreads();
         if (ONEBOX && it > 0 && tid == 0) {
             const unsigned wbase = tma::smem_u32(c.work);
-            tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            if (K::NP == 2) tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            else tma::store_5d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, 0, (int)pb);
             tma::store_4d(&smap, wbase + K::MC * (TF * 8), (int)(ppt * TF), K::RL, 0, (int)pb);
             tma::commit_group();
         }
@@ -200,7 +201,8 @@ pk_fwd_kernel(const __grid_constant__ FwdArgs<float> args, const PTab *__restric
         __syncthreads();
         if (blockIdx.x < total && tid == 0) {  // the last tile of this CTA
             const unsigned wbase = tma::smem_u32(c.work);
-            tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            if (K::NP == 2) tma::store_4d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, (int)pb);
+            else tma::store_5d(&smap_tile, wbase, (int)(ppt * TF), 0, 0, 0, (int)pb);
             tma::store_4d(&smap, wbase + K::MC * (TF * 8), (int)(ppt * TF), K::RL, 0, (int)pb);
             tma::commit_group();
         }
@@ -453,8 +455,8 @@ struct PkFwdLaunch {
         memset(&smap_tile, 0, sizeof(smap_tile));
         const bool stage = ones && p.batch < (1LL << 31) && !pk_env_int("VEILS_PK_NO_TMA", 0) &&
                            tma::make_s_map(&smap, out, spec ? 4 : 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL) &&
-                           (spec || K::G > 256 ||
-                            tma::make_s_map(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL, K::G));
+                           (spec || (K::NP == 2 ? tma::make_s_map(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL, K::G)
+                                                : tma::make_s_map5(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, K::R1, TF)));
         KernT kern = stage ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, true>)
                    : ones  ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, false>)
                            : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false, false>);

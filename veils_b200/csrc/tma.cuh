@@ -55,7 +55,34 @@ inline bool make_s_map(CUtensorMap *m, const void *base, int esz, int64_t P, int
     return r == CUDA_SUCCESS;
 }
 
+// 3-pass plans: last-pass group g = g1 + R1 g2 keeps its RL staged rows at work row g1 L1 + g2 L2 + d
+// (L1 = RL G / R1 ... dense in the order g1, g2, d), so the whole tile is one 5-D box:
+//   dim0 = p, dim1 = d (stride G ldp), dim2 = g2 (stride R1 ldp), dim3 = g1 (stride ldp), dim4 = b.
+inline bool make_s_map5(CUtensorMap *m, const void *base, int esz, int64_t P, int64_t ldp, int64_t F, int64_t B,
+                        int G, int RL, int R1, int TF) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    if (((uintptr_t)base & 15) != 0 || (ldp * esz) % 16 != 0 || (TF * esz) % 16 != 0) return false;
+    if (P <= 0 || B <= 0 || P >= (1LL << 32) || B >= (1LL << 32) || G % R1 != 0) return false;
+    const int G2 = G / R1;
+    if (RL > 256 || G2 > 256 || R1 > 256) return false;
+    const cuuint64_t dims[5] = {(cuuint64_t)P, (cuuint64_t)RL, (cuuint64_t)G2, (cuuint64_t)R1, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)(G * ldp * esz), (cuuint64_t)(R1 * ldp * esz), (cuuint64_t)(ldp * esz),
+                                   (cuuint64_t)(F * ldp * esz)};
+    for (int i = 0; i < 4; ++i)
+        if (strides[i] >= (1ULL << 40) || strides[i] % 16 != 0) return false;
+    const cuuint32_t box[5] = {(cuuint32_t)TF, (cuuint32_t)RL, (cuuint32_t)G2, (cuuint32_t)R1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapDataType dt = esz == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : CU_TENSOR_MAP_DATA_TYPE_UINT32;
+    return fn(m, dt, 5, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 #if defined(__CUDACC__)
+__device__ __forceinline__ void store_5d(const CUtensorMap *m, unsigned src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+                 ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 // shared -> global, box at coordinates (c0, c1, c2, c3); completion tracked by the bulk group
 __device__ __forceinline__ void store_4d(const CUtensorMap *m, unsigned src, int c0, int c1, int c2, int c3) {
