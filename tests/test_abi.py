@@ -123,3 +123,25 @@ def test_compute_without_gpu_fails_loudly():
     s = StandaloneSTFT(np.hanning(16), 4, 1.0)
     with pytest.raises(RuntimeError, match="CUDA"):
         s.stft(np.zeros(64))
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under veils_b200/ (Python or C++/CUDA sources) may
+    import, include or link anything from oracle/ -- there is no CPU fallback to fall back to."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(root, "veils_b200")):
+        if os.sep + "build" in dirpath:
+            continue
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                continue
+            text = open(os.path.join(dirpath, f), errors="ignore").read()
+            if re.search(r"(from|import)\s+oracle|#include\s+[\"<][^\">]*oracle|stft_ref|libstft_ref", text):
+                bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    import subprocess
+    import sys
+    code = "import sys, veils_b200; veils_b200.lib(); assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
