@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../veils_b200/csrc/plan.hpp"
@@ -189,6 +190,11 @@ struct EmuPkInv {
         std::vector<C2> regs((size_t)K::NT * K::GPT * K::RL);
         std::vector<Raw> raws((size_t)K::NT * (K::R1 + 1));
         std::vector<float> carry0((size_t)prm.N + 4), carry1((size_t)prm.N + 4);
+        // same conditions as PkInvLaunch::run (pow2_pk.cu) apart from the TMA / alignment ones
+        const bool acc_path = prm.mode >= 2 && c.a.halo == 3 && prm.N == prm.M && 4 * prm.H == prm.N &&
+                              prm.ps == prm.N / 2 && c.a.pair && prm.k0 % 2 == 0 && K::WPT2 == 1 &&
+                              (LOGMC == 7 || LOGMC == 8 || LOGMC == 10 || LOGMC == 11);
+        std::vector<float> acc((size_t)K::ACC_FLOATS + 8);
         pk_inv_chunks(c.a, prm, TF, prm.batch, emu_grid_hint);
         const int64_t lc = (int64_t)TF * c.a.chunk_tiles - c.a.halo;
         for (int64_t ch = 0; ch < c.a.cps * prm.batch; ++ch) {
@@ -229,6 +235,33 @@ struct EmuPkInv {
                     C2 r[K::GPT][K::RL];
                     K::last_load(c, tt, r);
                     std::memcpy(&regs[(size_t)tt * K::GPT * K::RL], r, sizeof(r));
+                }
+                if (acc_path) {
+                    // accumulator overlap-add of pk_inv_kernel (75 % overlap, default roll): four quarter
+                    // passes, output, tail -> head.  The accumulator is NaN-poisoned at every chunk start:
+                    // a tile must only ever read what this chunk has written.
+                    if (c.first) {
+                        for (auto &v : acc) v = std::nanf("");
+                        for (int tt = 0; tt < K::NT; ++tt) K::ola_zero_head(tt, acc.data());
+                    }
+                    auto pass = [&](auto q) {
+                        for (int tt = 0; tt < K::NT; ++tt) {
+                            C2 r[K::GPT][K::RL];
+                            std::memcpy(r, &regs[(size_t)tt * K::GPT * K::RL], sizeof(r));
+                            K::template ola_acc<decltype(q)::value>(c, tt, r, acc.data());
+                        }
+                    };
+                    pass(std::integral_constant<int, 3>());
+                    pass(std::integral_constant<int, 2>());
+                    pass(std::integral_constant<int, 1>());
+                    pass(std::integral_constant<int, 0>());
+                    std::vector<typename K::Tail> tails((size_t)K::NT);
+                    for (int tt = 0; tt < K::NT; ++tt) {
+                        K::ola_out(c, tt, acc.data());
+                        tails[(size_t)tt] = K::ola_take_tail(tt, acc.data());
+                    }
+                    for (int tt = 0; tt < K::NT; ++tt) K::ola_keep_tail(tt, acc.data(), tails[(size_t)tt]);
+                    continue;
                 }
                 for (int tt = 0; tt < K::NT; ++tt) {
                     C2 r[K::GPT][K::RL];

@@ -159,7 +159,13 @@ def test_emulated_packed_inverse_streaming_overlap_add(emu, M, N, H, n):
     assert y is not None and not np.isnan(y).any()
     assert rel_err(y, np.stack([o.istft(s) for s in Sref])) <= 1e-5
     assert np.max(np.abs(y[:, :n] - x)) <= 2e-5
-    k0, k1 = 3 * H + 5, n - 2 * H - 7
-    y2 = emu_istft(emu, o, 0, Sref, k0, k1, family=1)
-    assert not np.isnan(y2).any()
-    assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= 1e-5
+    # odd k0: row-based overlap-add; even k0: the accumulator path (75 % overlap cases) with clipping
+    for k0, k1 in ((3 * H + 5, n - 2 * H - 7), (3 * H + 6, n - 2 * H - 7), (2 * H, 5 * N)):
+        y2 = emu_istft(emu, o, 0, Sref, k0, k1, family=1)
+        assert not np.isnan(y2).any()
+        assert rel_err(y2, np.stack([o.istft(s, k0, k1) for s in Sref])) <= 1e-5
+    if N == 4 * H and M == N:
+        # the two overlap-add paths agree bit for bit (same summation order, products rounded alone)
+        ya = emu_istft(emu, o, 0, Sref, 2 * H, n - 3, family=1)
+        yb = emu_istft(emu, o, 0, Sref, 2 * H - 1, n - 3, family=1)
+        assert np.array_equal(ya, yb[:, 1:])
