@@ -159,6 +159,7 @@ inline FwdArgs<T> make_fwd_args(const T *x, void *out, const FwdParams &p, const
     a.shift = p.mode == 1 ? (int)(p.M / 2) : 0;
     a.spectrogram = p.spectrogram;
     a.dbg = 0;
+    a.fastgeo = (p.N == p.M && 4 * p.H == p.M && p.ps == p.M / 2) ? 1 : 0;
     a.fac2x = p.mode == 3 ? (T)p.fac2x : (T)1;
     return a;
 }

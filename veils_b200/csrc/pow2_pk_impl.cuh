@@ -90,6 +90,16 @@ struct PkGeo {
 #endif
         return *q;
     }
+    VHD static fl2 dw2(const ITab *q) {                // (d0, d1) of an inverse table entry
+#if defined(__CUDA_ARCH__)
+        if (!STAB) {
+            const float2 v = __ldg(reinterpret_cast<const float2 *>(&q->d0));
+            fl2 r; r.x = v.x; r.y = v.y;
+            return r;
+        }
+#endif
+        return *reinterpret_cast<const fl2 *>(&q->d0);
+    }
     VHD static ITab it4(const ITab *q) {
 #if defined(__CUDA_ARCH__)
         if (!STAB) {
@@ -233,14 +243,39 @@ struct PkFwd : PkGeo<LOGMC, TF_, NSUB_> {
         const int sub = tid / LN;
         for (int j = sub; j < L1; j += NSUB) {
             C2 v[R1];
-            pass1_in<PADDED>(c, tid, j, v);
+            if (LOGMC >= 8 && c.a.fastgeo) pass1_in_fast(c, tid, j, v);
+            else pass1_in<PADDED>(c, tid, j, v);
             pass1_out(c, tid, j, v);
         }
     }
     // pass 1 of group j, first half: tile reads, window, DFT_R1 -- does not touch the work buffer
     VHD static void pass1_in(const PkFwdCtx &c, int tid, int j, C2 (&v)[R1]) {
-        if (c.a.padded) pass1_in<true>(c, tid, j, v);
+        if (LOGMC >= 8 && c.a.fastgeo) pass1_in_fast(c, tid, j, v);      // (mfft 256: 3 % slower with it)
+        else if (c.a.padded) pass1_in<true>(c, tid, j, v);
         else pass1_in<false>(c, tid, j, v);
+    }
+    // default geometry (m_num = mfft = 4 hop, roll = m_num / 2): sample pair m = j + L1 a of a slice sits
+    // at tile offset 2j + C(a) with a compile-time C(a), its window pair at ptab[m].w0 -- every read is
+    // base + immediate, nothing waits for a table entry first
+    VHD static void pass1_in_fast(const PkFwdCtx &c, int tid, int j, C2 (&v)[R1]) {
+        constexpr int HC = MC / 2;
+        constexpr int PADW = (2 - HC % 4 + 4) % 4;
+        const int l = tid % LN;
+        const int hs = HC + PADW;
+        const float *xf0 = c.xin + l * hs + 2 * j, *xf1 = xf0 + LN * hs;
+        const float *wj = &c.ptab[j].w0;
+#pragma unroll
+        for (int a = 0; a < R1; ++a) {
+            constexpr int dummy = 0; (void)dummy;
+            const int ca = (2 * L1 * a + M / 2) % M;                   // compile-time after unrolling
+            const int off = ca + (ca / HC) * PADW;
+            const fl2 x0 = *reinterpret_cast<const fl2 *>(xf0 + off);
+            const fl2 x1 = *reinterpret_cast<const fl2 *>(xf1 + off);
+            const fl2 w = *reinterpret_cast<const fl2 *>(wj + 4 * L1 * a);
+            v[a].x = mk2(x0.x * w.x, x1.x * w.x);
+            v[a].y = mk2(x0.y * w.y, x1.y * w.y);
+        }
+        Dft<R1, false, f2>::run(v);
     }
     template <bool PADDED>
     VHD static void pass1_in(const PkFwdCtx &c, int tid, int j, C2 (&v)[R1]) {
@@ -1036,13 +1071,16 @@ struct PkInv : PkGeo<LOGMC, TF_, NSUB_> {
             for (int dd = 0; dd < RL / 4; ++dd) {
                 constexpr int RQ = RL / 4;
                 const int d = (Q * RQ + dd + RL / 2) % RL;       // sample pairs g + G d of quarter Q (roll = m_num / 2)
-                const ITab e = GEO::it4(tg + G * d);
+                // this path's geometry (m_num = mfft, roll = m_num / 2): the pair lands at offset 2g + C(d) of
+                // its slice, C compile-time -- only the dual-window pair is read from the table (8 bytes)
+                const int o0 = 2 * g + (2 * G * d + M / 2) % M;
+                const fl2 dw = GEO::dw2(tg + G * d);
                 // products rounded on their own (no contraction into the adds below): the sums are then
                 // bit-identical to the row-based overlap-add of the other kernels, whatever path a call takes
                 fl2 a, b;
-                a.x = mul_rn(lo(r[i][d].x), e.d0); a.y = mul_rn(lo(r[i][d].y), e.d1);
-                b.x = mul_rn(hi(r[i][d].x), e.d0); b.y = mul_rn(hi(r[i][d].y), e.d1);
-                fl2 *p0 = reinterpret_cast<fl2 *>(a0 + e.o0), *p1 = reinterpret_cast<fl2 *>(a1 + e.o0);
+                a.x = mul_rn(lo(r[i][d].x), dw.x); a.y = mul_rn(lo(r[i][d].y), dw.y);
+                b.x = mul_rn(hi(r[i][d].x), dw.x); b.y = mul_rn(hi(r[i][d].y), dw.y);
+                fl2 *p0 = reinterpret_cast<fl2 *>(a0 + o0), *p1 = reinterpret_cast<fl2 *>(a1 + o0);
                 if (Q == 3) {                                     // oldest contribution of every cell it touches
                     *p0 = a;
                     *p1 = b;

@@ -266,6 +266,7 @@ struct FwdArgs {
     int shift;               // centered: Mc (fftshift), else 0
     int spectrogram;         // 1: |X|^2 real output
     int dbg;                 // ablation mask (VEILS_ABLATE builds only)
+    int fastgeo;             // m_num = mfft = 4 hop and roll = m_num / 2 (the default geometry)
     T fac2x;                 // onesided2X factor, 1 otherwise
 };
 
