@@ -384,6 +384,27 @@ def main():
                "note": "x pinned host -> H2D -> stft -> istft -> D2H reconstructed signal; "
                        f"S stays in HBM; {args.e2e_chunks} sub-batches on {args.e2e_streams} streams"}
         e2e["recon_max_abs_err"] = float((yh[:, :n] - xh).abs().max().item())
+        # the same round trip through the HOST-pointer flavour of the C ABI (the drop-in for the
+        # reference's Vec API: veils_stft_host returns S to the host, veils_istft_host takes it back ->
+        # S crosses PCIe twice), on a bounded sample of rows, for the record
+        if rank == 0:
+            rows_h = min(B, 64)
+            xs = np.ascontiguousarray(xh[:rows_h].numpy())
+            Sh = np.empty((rows_h, F, P), dtype=np.complex64 if cfg["prec"] == "f32" else np.complex128)
+            y2 = np.empty((rows_h, n_out), dtype=xs.dtype)
+            best = None
+            for _ in range(3):
+                t0 = time.perf_counter()
+                rc = L.veils_stft_host(st._h, xs.ctypes.data, n, rows_h, n, None, None, 0, Sh.ctypes.data)
+                assert rc == 0, L.veils_last_error()
+                rc = L.veils_istft_host(st._h, Sh.ctypes.data, P, rows_h, None, None, y2.ctypes.data)
+                assert rc == 0, L.veils_last_error()
+                dth = time.perf_counter() - t0
+                best = dth if best is None else min(best, dth)
+            e2e["host_abi"] = {"value": rows_h * n / best / 1e6, "unit": "Msamples/s", "rows": rows_h,
+                               "recon_max_abs_err": float(np.max(np.abs(y2[:, :n] - xs))),
+                               "note": "veils_stft_host + veils_istft_host on pageable numpy buffers: x in, S out, "
+                                       "S in, y out (S = 16x the signal bytes crosses PCIe twice)"}
 
     # ---- cpu_baseline + parity of a sample against the reference's CPU path (rank 0, N = 1) ----
     cpu = None
