@@ -18,8 +18,11 @@
  *     S[b][f][p] at element offset (b * f_pts + f) * ldp + p, interleaved complex {re, im},
  *     ldp >= P.  Signals: x[b][i] at b * x_pitch + i.
  *   - Element type of device and host buffers == the plan's precision (float / double).
- *   - A plan is immutable after creation: all compute entry points may be called
- *     concurrently from several threads on distinct streams.
+ *   - A plan is immutable after creation: all *_dev compute entry points may be called
+ *     concurrently from several threads on distinct streams.  The *_host flavours stage
+ *     through device buffers owned by the plan (chunked, two streams: upload, transform and
+ *     download overlap when the host buffers are page-locked, see veils_host_alloc_pinned);
+ *     concurrent *_host calls on ONE plan serialise on an internal lock.
  */
 #ifndef VEILS_CUDA_H
 #define VEILS_CUDA_H

@@ -2,6 +2,8 @@
 // compute calls to the kernel families, device-buffer / stream helpers.
 #include "../../include/veils_cuda.h"
 
+#include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -31,8 +33,38 @@ struct DeviceTables {
 };
 }  // namespace veils
 
+// grow-only device staging buffers + two streams for the host-pointer entry points
+struct HostStage {
+    void *buf[4] = {nullptr, nullptr, nullptr, nullptr};   // [2 * slot + {0: input chunk, 1: output chunk}]
+    size_t cap[4] = {0, 0, 0, 0};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    std::mutex mu;                                         // host-pointer calls on one plan serialise
+    int *nan_flag = nullptr;                               // page-locked, written by nan_screen_kernel
+    cudaError_t reserve(int i, size_t bytes) {
+        if (cap[i] >= bytes) return cudaSuccess;
+        if (buf[i]) cudaFree(buf[i]);
+        buf[i] = nullptr; cap[i] = 0;
+        cudaError_t e = cudaMalloc(&buf[i], bytes);
+        if (e == cudaSuccess) cap[i] = bytes;
+        return e;
+    }
+    cudaError_t streams() {
+        for (int i = 0; i < 2; ++i)
+            if (!st[i]) { cudaError_t e = cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking); if (e != cudaSuccess) return e; }
+        if (!nan_flag) { cudaError_t e = cudaMallocHost((void **)&nan_flag, sizeof(int)); if (e != cudaSuccess) return e; }
+        return cudaSuccess;
+    }
+    void release() {
+        for (int i = 0; i < 4; ++i) { if (buf[i]) cudaFree(buf[i]); buf[i] = nullptr; cap[i] = 0; }
+        for (int i = 0; i < 2; ++i) { if (st[i]) cudaStreamDestroy(st[i]); st[i] = nullptr; }
+        if (nan_flag) cudaFreeHost(nan_flag);
+        nan_flag = nullptr;
+    }
+};
+
 struct veils_plan {
     Plan pl;
+    HostStage stage;
 };
 
 static thread_local std::string t_err;
@@ -209,6 +241,8 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->itab_pk);
         delete p->pl.dev;
     }
+    cudaSetDevice(p->pl.device);
+    p->stage.release();
     delete p;
 }
 
@@ -533,7 +567,36 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
 }
 
 // ---- host-pointer flavour ------------------------------------------------------------------
+// NaN screen of the uploaded signal (src/lib.rs:696-698 rejects NaN input in the one-sided modes):
+// done on the device copy, where reading x again costs microseconds, instead of a host scan that
+// would cost as much as the PCIe transfer.  The flag lives in page-locked host memory.
+extern "C++" {
+template <typename T>
+__global__ void nan_screen_kernel(const T *__restrict__ x, size_t count, int *flag) {
+    bool bad = false;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const T v = x[i];
+        bad |= (v != v);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
+}
+}  // extern "C++"
 static size_t esz(const Plan &pl) { return pl.precision == F32 ? 4 : 8; }
+// device row pitch of S in elements: 128-byte rows, so that the TMA paths of the kernels apply
+static int64_t host_ldp(int64_t P, size_t elem_bytes) {
+    // 128-byte rows on the device (pitched 2-D copies measured as fast as 1-D ones over PCIe), so that the
+    // host flavour runs the SAME kernels as the pitch-aligned device path and returns the same bits
+    static const bool packed = [] { const char *e = getenv("VEILS_HOST_LDP_PACKED"); return e && atoi(e) != 0; }();
+    if (packed) return P;
+    const int64_t al = (int64_t)(128 / elem_bytes);
+    return (P + al - 1) / al * al;
+}
+// rows per staged chunk: about 32 MB of S (enough to fill the GPU, small enough to pipeline)
+static int64_t host_chunk_rows(int64_t batch, size_t s_row_bytes) {
+    const size_t target = (size_t)32 << 20;
+    int64_t rows = (int64_t)std::max<size_t>(1, target / std::max<size_t>(1, s_row_bytes));
+    return std::min(rows, batch);
+}
 
 static int32_t forward_host(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
                             const int64_t *p0, const int64_t *p1, int64_t k_offset, void *out,
@@ -541,19 +604,6 @@ static int32_t forward_host(veils_plan *p, const void *x, int64_t n, int64_t bat
     if (!p || !x || !out) return fail(VEILS_ERR_INVALID, "null argument");
     Plan &pl = p->pl;
     if (x_pitch < n) return fail(VEILS_ERR_INVALID, "x_pitch must be >= n");
-    if (pl.mode >= ONESIDED) {                                // src/lib.rs:696-698
-        bool nan = false;
-        for (int64_t b = 0; b < batch && !nan; ++b) {
-            if (pl.precision == F32) {
-                const float *r = (const float *)x + b * x_pitch;
-                for (int64_t i = 0; i < n; ++i) if (std::isnan(r[i])) { nan = true; break; }
-            } else {
-                const double *r = (const double *)x + b * x_pitch;
-                for (int64_t i = 0; i < n; ++i) if (std::isnan(r[i])) { nan = true; break; }
-            }
-        }
-        if (nan) return fail(VEILS_ERR_INVALID, "Complex-valued input not allowed for one-sided FFT modes");
-    }
     const int64_t m2p = pl.N - pl.mid;
     if (n < m2p)
         return fail(VEILS_ERR_INVALID, "Input length " + std::to_string((long long)n) +
@@ -564,25 +614,52 @@ static int32_t forward_host(veils_plan *p, const void *x, int64_t n, int64_t bat
     if (batch <= 0) return VEILS_OK;
     const int64_t P = b - a;
     const size_t es = esz(pl);
-    const size_t in_bytes = (size_t)batch * (size_t)n * es;
-    const size_t out_bytes = (size_t)batch * (size_t)pl.F * (size_t)P * es * (spectrogram ? 1 : 2);
+    const size_t oes = es * (spectrogram ? 1 : 2);                       // output element
+    const int64_t ldp = host_ldp(P, oes);
+    const size_t in_row = (size_t)n * es, out_row = (size_t)pl.F * (size_t)ldp * oes;
+    const int64_t rows = host_chunk_rows(batch, out_row);
     CU(cudaSetDevice(pl.device));
-    void *dx = nullptr, *ds = nullptr;
-    CU(cudaMalloc(&dx, in_bytes));
-    cudaError_t ce = cudaMalloc(&ds, out_bytes);
-    if (ce != cudaSuccess) { cudaFree(dx); return cuda_fail(ce, "cudaMalloc"); }
-    ce = cudaMemcpy2D(dx, (size_t)n * es, x, (size_t)x_pitch * es, (size_t)n * es, (size_t)batch,
-                      cudaMemcpyHostToDevice);
+    HostStage &hs = p->stage;
+    std::lock_guard<std::mutex> lock(hs.mu);
+    CU(hs.streams());
+    *hs.nan_flag = 0;
+    const int slots = rows < batch ? 2 : 1;
+    for (int sl = 0; sl < slots; ++sl) {
+        CU(hs.reserve(2 * sl, (size_t)rows * in_row));
+        CU(hs.reserve(2 * sl + 1, (size_t)rows * out_row));
+    }
+    // rows [r0, r0 + nr) per chunk, alternating between two streams: the upload of one chunk, the
+    // transform of the previous and the download of the one before overlap (when the host buffers
+    // are page-locked; pageable copies are staged by the driver and serialise)
     int32_t rc = VEILS_OK;
-    if (ce != cudaSuccess) rc = cuda_fail(ce, "H2D copy");
-    if (rc == VEILS_OK)
-        rc = forward_impl(p, dx, n, batch, n, &a, &b, k_offset, ds, P, nullptr, spectrogram);
-    if (rc == VEILS_OK) {
-        ce = cudaMemcpy(out, ds, out_bytes, cudaMemcpyDeviceToHost);
+    int64_t c = 0;
+    for (int64_t r0 = 0; r0 < batch && rc == VEILS_OK; r0 += rows, ++c) {
+        const int64_t nr = std::min(rows, batch - r0);
+        const int sl = (int)(c & 1) % slots;
+        cudaStream_t st = hs.st[sl];
+        void *dx = hs.buf[2 * sl], *ds = hs.buf[2 * sl + 1];
+        cudaError_t ce = cudaMemcpy2DAsync(dx, in_row, (const char *)x + (size_t)r0 * (size_t)x_pitch * es,
+                                           (size_t)x_pitch * es, in_row, (size_t)nr, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D copy"); break; }
+        if (pl.mode >= ONESIDED) {
+            const size_t cnt = (size_t)nr * (size_t)n;
+            const int grid = (int)std::min<size_t>(148 * 8, (cnt + 255) / 256);
+            if (pl.precision == F32) nan_screen_kernel<float><<<grid, 256, 0, st>>>((const float *)dx, cnt, hs.nan_flag);
+            else nan_screen_kernel<double><<<grid, 256, 0, st>>>((const double *)dx, cnt, hs.nan_flag);
+            ++g_launch_count;
+        }
+        rc = forward_impl(p, dx, n, nr, n, &a, &b, k_offset, ds, ldp, st, spectrogram);
+        if (rc != VEILS_OK) break;
+        ce = cudaMemcpy2DAsync((char *)out + (size_t)r0 * (size_t)pl.F * (size_t)P * oes, (size_t)P * oes, ds,
+                               (size_t)ldp * oes, (size_t)P * oes, (size_t)(nr * pl.F), cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) rc = cuda_fail(ce, "D2H copy");
     }
-    cudaFree(dx);
-    cudaFree(ds);
+    for (int sl = 0; sl < 2; ++sl) {
+        cudaError_t ce = cudaStreamSynchronize(hs.st[sl]);
+        if (ce != cudaSuccess && rc == VEILS_OK) rc = cuda_fail(ce, "stft (host)");
+    }
+    if (rc == VEILS_OK && *hs.nan_flag)
+        return fail(VEILS_ERR_INVALID, "Complex-valued input not allowed for one-sided FFT modes");
     return rc;
 }
 
@@ -606,23 +683,39 @@ int32_t veils_istft_host(veils_plan *p, const void *S, int64_t P, int64_t batch,
     if (batch <= 0) return VEILS_OK;
     const size_t es = esz(pl);
     const int64_t len = r.k1 - r.k0;
-    const size_t s_bytes = (size_t)batch * (size_t)pl.F * (size_t)P * es * 2;
-    const size_t o_bytes = (size_t)batch * (size_t)len * es;
+    const int64_t ldp = host_ldp(P, 2 * es);
+    const size_t s_row = (size_t)pl.F * (size_t)ldp * es * 2, o_row = (size_t)len * es;
+    const int64_t rows = host_chunk_rows(batch, s_row);
     CU(cudaSetDevice(pl.device));
-    void *ds = nullptr, *dx = nullptr;
-    CU(cudaMalloc(&ds, s_bytes));
-    cudaError_t ce = cudaMalloc(&dx, o_bytes);
-    if (ce != cudaSuccess) { cudaFree(ds); return cuda_fail(ce, "cudaMalloc"); }
+    HostStage &hs = p->stage;
+    std::lock_guard<std::mutex> lock(hs.mu);
+    CU(hs.streams());
+    const int slots = rows < batch ? 2 : 1;
+    for (int sl = 0; sl < slots; ++sl) {
+        CU(hs.reserve(2 * sl + 1, (size_t)rows * s_row));      // the big buffer is slot's [1] in both directions
+        CU(hs.reserve(2 * sl, (size_t)rows * o_row));
+    }
     int32_t rc = VEILS_OK;
-    ce = cudaMemcpy(ds, S, s_bytes, cudaMemcpyHostToDevice);
-    if (ce != cudaSuccess) rc = cuda_fail(ce, "H2D copy");
-    if (rc == VEILS_OK) rc = veils_istft_dev(p, ds, P, batch, P, &r.k0, &r.k1, dx, len, nullptr);
-    if (rc == VEILS_OK) {
-        ce = cudaMemcpy(x_out, dx, o_bytes, cudaMemcpyDeviceToHost);
+    int64_t c = 0;
+    for (int64_t r0 = 0; r0 < batch && rc == VEILS_OK; r0 += rows, ++c) {
+        const int64_t nr = std::min(rows, batch - r0);
+        const int sl = (int)(c & 1) % slots;
+        cudaStream_t st = hs.st[sl];
+        void *ds = hs.buf[2 * sl + 1], *dx = hs.buf[2 * sl];
+        cudaError_t ce = cudaMemcpy2DAsync(ds, (size_t)ldp * es * 2,
+                                           (const char *)S + (size_t)r0 * (size_t)pl.F * (size_t)P * es * 2,
+                                           (size_t)P * es * 2, (size_t)P * es * 2, (size_t)(nr * pl.F),
+                                           cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D copy"); break; }
+        rc = veils_istft_dev(p, ds, P, nr, ldp, &r.k0, &r.k1, dx, len, st);
+        if (rc != VEILS_OK) break;
+        ce = cudaMemcpyAsync((char *)x_out + (size_t)r0 * o_row, dx, (size_t)nr * o_row, cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) rc = cuda_fail(ce, "D2H copy");
     }
-    cudaFree(ds);
-    cudaFree(dx);
+    for (int sl = 0; sl < 2; ++sl) {
+        cudaError_t ce = cudaStreamSynchronize(hs.st[sl]);
+        if (ce != cudaSuccess && rc == VEILS_OK) rc = cuda_fail(ce, "istft (host)");
+    }
     return rc;
 }
 
