@@ -85,9 +85,22 @@ __device__ __forceinline__ void store_5d(const CUtensorMap *m, unsigned src, int
 }
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 // shared -> global, box at coordinates (c0, c1, c2, c3); completion tracked by the bulk group
+#ifndef VEILS_L2_HINT
+#define VEILS_L2_HINT 0          // experiment: 1 = evict_first on tensor stores, 2 = on tensor loads (profiles/r1c_ablation.txt)
+#endif
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 __device__ __forceinline__ void store_4d(const CUtensorMap *m, unsigned src, int c0, int c1, int c2, int c3) {
+#if VEILS_L2_HINT & 1
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+                 ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy_evict_first()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                  ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+#endif
 }
 // shared -> global, 1-D: `bytes` (multiple of 16) from a 16-byte aligned shared address to a
 // 16-byte aligned global address
@@ -105,8 +118,13 @@ __device__ __forceinline__ void prefetch_map(const CUtensorMap *m) {
 }
 // global -> shared, completion on an mbarrier (complete_tx::bytes)
 __device__ __forceinline__ void load_4d(const CUtensorMap *m, unsigned dst, unsigned bar, int c0, int c1, int c2, int c3) {
+#if VEILS_L2_HINT & 2
+    asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy_evict_first()) : "memory");
+#else
     asm volatile("cp.async.bulk.tensor.4d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
