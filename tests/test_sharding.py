@@ -100,7 +100,35 @@ def test_inverse_shards_tile_the_output():
             sh = [sharding.inverse_shard(P, m, hop, p_min, r, world) for r in range(world)]
             assert sh[0].k_a == 0 and sh[-1].k_b == (p_min + P - 1) * hop + m - m // 2
             assert all(sh[r].k_b == sh[r + 1].k_a for r in range(world - 1))
-            assert all(s.halo_cols == (0 if r == 0 else (m + hop - 1) // hop - 1) for r, s in enumerate(sh))
+            assert all(s.halo_cols == (0 if r == 0 else sharding.inverse_halo_cols(m, hop, p_min))
+                       for r, s in enumerate(sh))
+            assert all(s.k0_local >= 0 for s in sh)
+
+
+# hops that do not divide m_num/2 made the local k0 negative with the minimal halo (round-1 advisor
+# finding: max abs error 0.29 for 1024/100 at world 2); the widened halo must be exact everywhere
+ODD_GEOS = [(1024, 100), (18, 4), (20, 4), (26, 6), (34, 8), (15, 4), (33, 7), (512, 128), (400, 160), (16, 4), (8, 3)]
+
+
+@pytest.mark.parametrize("m,hop", ODD_GEOS)
+@pytest.mark.parametrize("world", [2, 3])
+def test_inverse_shards_exact_for_any_hop(m, hop, world):
+    rng = np.random.default_rng(m * 131 + hop)
+    win = np.hanning(m + 2)[1:-1]
+    o = OracleSTFT(win, hop, 1000.0)
+    n = 12 * m + 37
+    x = rng.uniform(-1, 1, n)
+    S = o.stft(x)
+    full = o.istft(S)
+    P = S.shape[1]
+    sh = [sharding.inverse_shard(P, m, hop, o.p_min, r, world) for r in range(world)]
+    parts = []
+    for s in sh:
+        a = s.p_a - o.p_min - s.halo_cols
+        parts.append(o.istft(np.ascontiguousarray(S[:, a:s.p_b - o.p_min]), s.k0_local, s.k1_local))
+    y = np.concatenate(parts)
+    assert y.shape == full.shape
+    assert np.max(np.abs(y - full)) == 0.0
 
 
 @pytest.mark.gpu
@@ -110,8 +138,9 @@ def test_inverse_sharding_cuda_matches_unsharded():
     unsharded istft."""
     from veils_b200 import StandaloneSTFT
     rng = np.random.default_rng(6)
-    for prec, mode, m, hop in (("f32", "onesided", 512, 128), ("f64", "twosided", 256, 64)):
-        win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(m) / m))
+    for prec, mode, m, hop in (("f32", "onesided", 512, 128), ("f64", "twosided", 256, 64),
+                               ("f32", "onesided", 1024, 100), ("f64", "onesided", 18, 4), ("f32", "twosided", 34, 8)):
+        win = 0.5 * (1 - np.cos(2 * np.pi * (np.arange(m) + 0.5) / m))
         st = StandaloneSTFT(win, hop, 16000.0, fft_mode=mode, precision=prec)
         x = rng.uniform(-1, 1, 150000).astype(np.float32 if prec == "f32" else np.float64)
         S = st.stft(x)

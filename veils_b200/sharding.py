@@ -106,6 +106,13 @@ class InverseShard:
     k1_local: int
 
 
+def inverse_halo_cols(m_num: int, hop: int, p_min: int) -> int:
+    """Columns of S a rank needs from its predecessor: the ceil(m_num/hop)-1 overlapping slices, and
+    at least ceil(mid/hop) - p_min so that the local k0 = (halo + p_min)*hop - mid stays >= 0."""
+    mid = m_num // 2
+    return max((m_num + hop - 1) // hop - 1, (mid + hop - 1) // hop - p_min)
+
+
 def inverse_shard(p_total: int, m_num: int, hop: int, p_min: int, rank: int, world: int,
                   k0: int = 0, k1=None) -> InverseShard:
     """Output range and halo of `rank` for the inverse transform of S[F, p_total] sharded by slices.
@@ -115,13 +122,18 @@ def inverse_shard(p_total: int, m_num: int, hop: int, p_min: int, rank: int, wor
     k in [p_a*hop - mid, p_b*hop - mid) (first rank: from k0; last rank: up to k1, default the
     reference's k_max, src/lib.rs:823-824) and needs the ceil(m_num/hop)-1 slices before p_a.
     On the local column block the slice index restarts at p_min, so (k0, k1) shift by
-    (p_a - halo_cols - p_min) * hop."""
+    (p_a - halo_cols - p_min) * hop.
+
+    The halo is widened where needed so that the local k0 is never negative: for k0 < 0 the
+    reference starts at q0 = floor(k0/hop) WITHOUT adding p_min (src/lib.rs:842-846), which on a
+    local block would skip the first halo columns (hops that do not divide m_num/2, e.g. 1024/100).
+    The extra columns lie below the local q0 and contribute nothing."""
     mid = m_num // 2
     a, b = row_range(p_total, rank, world)
     p_a, p_b = p_min + a, p_min + b
     k_max = (p_min + p_total - 1) * hop + m_num - mid
     k1 = k_max if k1 is None else k1
-    halo = 0 if rank == 0 else min((m_num + hop - 1) // hop - 1, a)
+    halo = 0 if rank == 0 else min(inverse_halo_cols(m_num, hop, p_min), a)
     k_a = k0 if rank == 0 else max(k0, p_a * hop - mid)
     k_b = k1 if rank == world - 1 else min(k1, p_b * hop - mid)
     shift = (p_a - halo - p_min) * hop
