@@ -43,6 +43,7 @@ def test_c3_shape_round_trip():
     g = torch.Generator(device="cuda").manual_seed(3)
     x = torch.rand((32, 1440000), generator=g, device="cuda", dtype=torch.float32) * 2 - 1
     st = StandaloneSTFT(hann(4096), 1024, 48000.0, precision="f32")
+    assert st.kernel_name() == "pow2_wide" and st.kernel_name(True) == "pow2_wide"
     S = st.stft(x)
     assert S.shape == (32, 2049, 1410)
     y = st.istft(S)

@@ -29,6 +29,8 @@ struct DeviceTables {
     float *tw_pk_inv = nullptr;
     void *ptab_pk = nullptr;
     void *itab_pk = nullptr;
+    float *wide_fwd = nullptr;    // wide family tables (wide_impl.cuh)
+    float *wide_inv = nullptr;
     void *detr_w = nullptr;       // [2][F] complex: fft_func(win * 1), fft_func(win * i)  (detrending)
 };
 }  // namespace veils
@@ -144,6 +146,11 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 if (e == cudaSuccess) e = cudaMemcpy(d->ptab_pk, pt.data(), pt.size(), cudaMemcpyHostToDevice);
             }
         }
+        if (e == cudaSuccess && pl.wide) {
+            std::vector<double> tw((size_t)wide_table_floats(pl.M));
+            wide_table_fill_host(pl.M, false, pl.win.data(), 0.5, tw.data());
+            e = upload_as<float>(tw, (void **)&d->wide_fwd);
+        }
         if (e == cudaSuccess && !((pl.pow2_fwd || pl.pk_fwd) && (pl.pow2_inv || pl.pk_inv))) {
             std::vector<double> tw((size_t)pl.M * 2);
             for (int64_t m = 0; m < pl.M; ++m) twiddle(m, pl.M, &tw[2 * m], &tw[2 * m + 1]);
@@ -152,26 +159,41 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) {
-            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk);
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk); cudaFree(d->wide_fwd);
             delete d;
             return cuda_fail(e, "upload plan tables");
         }
         pl.dev = d;
     }
     if (need_dual && !pl.dev->dual) {
-        // pow2 inverse folds 1/M (and the 1/2 of the Hermitian part for two-sided layouts) here
+        // pow2 inverse folds 1/M (and the 1/2 of the Hermitian part for two-sided layouts) here.
+        // Everything is uploaded into locals and published only when all of it succeeded.
         const double sc = 1.0 / ((double)pl.M * (pl.mode >= ONESIDED ? 1.0 : 2.0));
-        cudaError_t e = upload_prec(pl, pl.dual, &pl.dev->dual_scaled, sc);
-        if (e == cudaSuccess) e = upload_prec(pl, pl.dual, &pl.dev->dual);
+        void *dual = nullptr, *dual_scaled = nullptr, *itab = nullptr;
+        float *wide_inv = nullptr;
+        cudaError_t e = upload_prec(pl, pl.dual, &dual_scaled, sc);
+        if (e == cudaSuccess) e = upload_prec(pl, pl.dual, &dual);
         if (e == cudaSuccess && pl.pk_inv) {
             std::vector<double> ds(pl.dual);
             for (double &v : ds) v *= sc;
             std::vector<unsigned char> it((size_t)(pl.M / 2) * 16);
             pk_itab_fill_host(pl.M, pl.N, pl.ps, ds.data(), it.data());
-            e = cudaMalloc(&pl.dev->itab_pk, it.size());
-            if (e == cudaSuccess) e = cudaMemcpy(pl.dev->itab_pk, it.data(), it.size(), cudaMemcpyHostToDevice);
+            e = cudaMalloc(&itab, it.size());
+            if (e == cudaSuccess) e = cudaMemcpy(itab, it.data(), it.size(), cudaMemcpyHostToDevice);
         }
-        if (e != cudaSuccess) return cuda_fail(e, "upload dual window");
+        if (e == cudaSuccess && pl.wide) {
+            std::vector<double> tw((size_t)wide_table_floats(pl.M));
+            wide_table_fill_host(pl.M, true, pl.dual.data(), sc, tw.data());
+            e = upload_as<float>(tw, (void **)&wide_inv);
+        }
+        if (e != cudaSuccess) {
+            cudaFree(dual); cudaFree(dual_scaled); cudaFree(itab); cudaFree(wide_inv);
+            return cuda_fail(e, "upload dual window");
+        }
+        pl.dev->dual_scaled = dual_scaled;
+        pl.dev->itab_pk = itab;
+        pl.dev->wide_inv = wide_inv;
+        pl.dev->dual = dual;
     }
     return VEILS_OK;
 }
@@ -189,6 +211,8 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.tw_pk_inv = pl.dev->tw_pk_inv;
     tb.ptab_pk = pl.dev->ptab_pk;
     tb.itab_pk = pl.dev->itab_pk;
+    tb.wide_fwd = pl.dev->wide_fwd;
+    tb.wide_inv = pl.dev->wide_inv;
     return tb;
 }
 
@@ -219,6 +243,9 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && (pl.M <= 1024 || !pl.pow2_fwd || getenv("VEILS_PK_FWD_ALL") != nullptr) &&
                     pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
         pl.pk_inv = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, true);
+        // mfft 1024 / 2048 / 4096 with the default geometry: the wide family (conflict-free swizzled tiles)
+        pl.wide = !force_generic && pl.precision == F32 && getenv("VEILS_NO_WIDE") == nullptr &&
+                  wide_supported(pl.M, pl.N, pl.H, pl.ps);
     }
     *out = p;
     return VEILS_OK;
@@ -239,6 +266,8 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->detr_w);
         cudaFree(p->pl.dev->ptab_pk);
         cudaFree(p->pl.dev->itab_pk);
+        cudaFree(p->pl.dev->wide_fwd);
+        cudaFree(p->pl.dev->wide_inv);
         delete p->pl.dev;
     }
     cudaSetDevice(p->pl.device);
@@ -376,7 +405,8 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
+        ce = pl.wide ? wide_forward((const float *)x, out, prm, tb.wide_fwd, st)
+             : pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
              : pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
                            : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
     } else {
@@ -554,7 +584,8 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
+        ce = pl.wide ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, st)
+             : pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
              : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
                            : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
     } else {
@@ -770,6 +801,7 @@ int32_t veils_stream_sync(void *stream) {
 
 uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
 const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse) {
+    if (p->pl.wide) return "pow2_wide";
     if (inverse ? p->pl.pk_inv : p->pl.pk_fwd) return "pow2_packed";
     return (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) ? "pow2_tile" : "dft_generic";
 }

@@ -41,6 +41,8 @@ struct Tables {
     const float *tw_pk_inv = nullptr;   // packed-f32 inverse twiddles
     const void *ptab_pk = nullptr;      // packed-f32 tile table [M/2] x 16 bytes
     const void *itab_pk = nullptr;      // packed-f32 inverse table [M/2] x 16 bytes
+    const float *wide_fwd = nullptr;    // wide family: forward table (layout: wide_impl.cuh)
+    const float *wide_inv = nullptr;    // wide family: inverse table
 };
 
 extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library
@@ -75,6 +77,15 @@ void pk_itab_fill_host(int64_t M, int64_t N, int64_t ps, const double *dual_scal
 void pk_ptab_fill_host(int64_t M, int64_t N, int64_t H, int64_t ps, const double *win, void *out16);
 cudaError_t pk_forward(const float *x, void *out, const FwdParams &prm, const Tables<float> &tb, cudaStream_t st);
 cudaError_t pk_inverse(const void *S, float *x_out, const InvParams &prm, const Tables<float> &tb, cudaStream_t st);
+
+// ---- wide f32 family: mfft 1024 / 2048 / 4096 with m_num = mfft = 4 hop, phase_shift = 0 (wide_fwd.cu, wide_inv.cu)
+bool wide_supported(int64_t M, int64_t N, int64_t H, int64_t ps);
+int wide_tf(int64_t M);                                   // slices per tile (0: mfft not covered)
+int64_t wide_table_floats(int64_t M);
+// plan table of one direction: window * 0.5 (forward) or dual * scale (inverse) + twiddles, as doubles
+void wide_table_fill_host(int64_t M, bool inverse, const double *vec_n, double scale, double *out);
+cudaError_t wide_forward(const float *x, void *out, const FwdParams &prm, const float *tab, cudaStream_t st);
+cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, const float *tab, cudaStream_t st);
 
 // ---- border extension for the twin's padding modes (pad.cu): mode 0 zeros, 1 edge, 2 even, 3 odd
 template <typename T>
