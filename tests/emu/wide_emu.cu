@@ -121,15 +121,16 @@ struct EmuFwd {
         const WTabOff o = wide_table_offsets(K::M);
         WFwdCtx c;
         c.a.x = x; c.a.out = out;
-        c.a.wtab = tab.data() + o.xtab; c.a.tw1 = tab.data() + o.tw1; c.a.tw2 = tab.data() + o.tw2; c.a.twp = tab.data() + o.twp;
+        c.a.tab = tab.data();
+        c.wtab = tab.data() + o.xtab; c.tw1 = tab.data() + o.tw1; c.tw2 = tab.data() + o.tw2; c.twp = tab.data() + o.twp;
         c.a.n = n; c.a.x_pitch = x_pitch; c.a.ldp = ldp; c.a.p0 = p0; c.a.P = P; c.a.k_offset = k_offset;
         c.a.ptiles = (P + TF - 1) / TF; c.a.F = F; c.a.mode = mode; c.a.spectrogram = spectrogram;
         const int esz = spectrogram ? 4 : 8;
         c.a.vec16 = ((ldp * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         c.a.fac2x = (float)fac2x;
-        std::vector<fl4> smem((size_t)(K::WORK_FLOATS + K::XIN_FLOATS) / 4 + 4);
+        std::vector<fl4> smem((wide_work_floats<LOGMC, TF>() + K::XIN_FLOATS) / 4 + 4);
         c.work = (float *)smem.data();
-        c.xin = c.work + K::WORK_FLOATS;
+        c.xin = c.work + wide_work_floats<LOGMC, TF>();
         g_lo = (const char *)smem.data(); g_hi = g_lo + smem.size() * 16;
         for (int64_t blk = 0; blk < c.a.ptiles * batch; ++blk) {
             c.b = blk / c.a.ptiles; c.pt = blk % c.a.ptiles;
@@ -137,7 +138,7 @@ struct EmuFwd {
             g_tracing = blk == 0;
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
             phase(0, K::NT, [&](int t) { K::pass1(c, t); });
-            emu_pass2<K, false, K::R1, K::R2, K::L2>(1, c.work, c.a.tw2);
+            emu_pass2<K, false, K::R1, K::R2, K::L2>(1, c.work, c.tw2);
             phase(2, K::NT, [&](int t) { K::pass3(c, t); });
         }
         g_tracing = false;
@@ -148,7 +149,7 @@ struct EmuFwd {
 struct EmuInv {
     const void *S; float *xo; const double *dual;
     int64_t P, ldp, batch, out_pitch, p_min, k0, k1, q0, q1, F;
-    int mode, chunk_tiles; double fac2x;
+    int mode, chunk_tiles; double fac2x; int use_land;
     template <int LOGMC, int TF>
     int run() {
         using K = WInv<LOGMC, TF>;
@@ -158,7 +159,8 @@ struct EmuInv {
         WInvCtx c;
         WInvArgs &a = c.a;
         a.S = S; a.xo = xo;
-        a.dtab = tab.data() + o.xtab; a.tw1 = tab.data() + o.tw1; a.tw2 = tab.data() + o.tw2; a.twp = tab.data() + o.twp;
+        a.tab = tab.data();
+        c.dtab = tab.data() + o.xtab; c.tw1 = tab.data() + o.tw1; c.tw2 = tab.data() + o.tw2; c.twp = tab.data() + o.twp;
         a.P = P; a.ldp = ldp; a.out_pitch = out_pitch; a.p_min = p_min; a.k0 = k0; a.k1 = k1; a.q0 = q0; a.q1 = q1; a.F = F;
         a.mode = mode; a.rfac2x = (float)(1.0 / fac2x); a.prefetch = 0;
         a.vec16 = (ldp % 2 == 0 && ((uintptr_t)S % 16) == 0) ? 1 : 0;
@@ -169,9 +171,9 @@ struct EmuInv {
         a.chunk_tiles = chunk_tiles;
         const int64_t lc = (int64_t)TF * chunk_tiles - a.halo, Q = a.qh1 - a.qh0 + 1;
         a.cps = (Q + lc - 1) / lc;
-        std::vector<fl4> smem((size_t)(K::WORK_FLOATS + K::XIN_FLOATS) / 4 + 4);
+        std::vector<fl4> smem((wide_work_floats<LOGMC, TF>() + K::XIN_FLOATS) / 4 + 4);
         c.work = (float *)smem.data();
-        c.acc = c.work + K::WORK_FLOATS;
+        c.acc = c.work + wide_work_floats<LOGMC, TF>();
         g_lo = (const char *)smem.data(); g_hi = g_lo + smem.size() * 16;
         std::vector<typename K::Regs> regs((size_t)K::NT);
         std::vector<typename K::Tail> tails((size_t)K::NT);
@@ -185,8 +187,33 @@ struct EmuInv {
                 c.first = t == 0;
                 c.more = 0;
                 g_tracing = ch == 0 && t == 1;
+                if (use_land && mode >= 2 && a.vec16) {
+                    // what the TMA engine does (wide_inv_kernel): NH column blocks [Mc rows][8 slices] + the
+                    // Nyquist rows land over the work buffer, columns outside [0, P) as zeros
+                    const int64_t col0 = c.qa - p_min;
+                    const float *Sf = (const float *)S;
+                    for (int h = 0; h < K::NH; ++h)
+                        for (int k = 0; k <= K::MC; ++k)
+                            for (int i = 0; i < 8; ++i) {
+                                const int64_t col = col0 + 8 * h + i;
+                                float *dst = k < K::MC ? c.work + h * K::LAND_BLOCK + 16 * k + 2 * i
+                                                       : c.work + K::NH * K::LAND_BLOCK + 16 * h + 2 * i;
+                                const bool ok = col >= 0 && col < P;
+                                const float *src = Sf + 2 * ((c.b * F + k) * ldp + col);
+                                dst[0] = ok ? src[0] : 0.f;
+                                dst[1] = ok ? src[1] : 0.f;
+                            }
+                    std::vector<typename K::P1Regs> pr((size_t)K::NT);
+                    for (int it = 0; it < K::P1_ITERS; ++it) {
+                        phase(3, K::NT, [&](int tt) {
+                            if (mode == 3) K::template land_load<3>(c, tt, it, pr[tt]);
+                            else K::template land_load<2>(c, tt, it, pr[tt]);
+                        });
+                        phase(3, K::NT, [&](int tt) { K::land_rest(c, tt, it, pr[tt]); });
+                    }
+                } else
                 phase(3, K::NT, [&](int tt) { K::pass1(c, tt); });
-                emu_pass2<K, true, K::R1, K::R2, K::L2>(4, c.work, c.a.tw2);
+                emu_pass2<K, true, K::R1, K::R2, K::L2>(4, c.work, c.tw2);
                 phase(5, K::NT, [&](int tt) { K::pass3_load(c, tt, regs[tt]); });
                 if (c.first) for (int tt = 0; tt < K::NT; ++tt) K::zero_head(c, tt);
                 phase(6, K::NT, [&](int tt) { K::template ola<3>(c, tt, regs[tt]); });
@@ -216,10 +243,10 @@ int wide_emu_forward(int64_t M, int tf, const double *win, const float *x, int64
 }
 int wide_emu_inverse(int64_t M, int tf, const double *dual, const void *S, int64_t P, int64_t ldp, int64_t batch,
                      int64_t F, int64_t p_min, int64_t k0, int64_t k1, int64_t q0, int64_t q1, int mode, double fac2x,
-                     int chunk_tiles, float *xo, int64_t out_pitch) {
+                     int chunk_tiles, float *xo, int64_t out_pitch, int use_land) {
     WCfg c;
     if (!wide_cfg_for(M, tf, &c)) return -1;
-    EmuInv e{S, xo, dual, P, ldp, batch, out_pitch, p_min, k0, k1, q0, q1, F, mode, chunk_tiles, fac2x};
+    EmuInv e{S, xo, dual, P, ldp, batch, out_pitch, p_min, k0, k1, q0, q1, F, mode, chunk_tiles, fac2x, use_land};
     return wide_dispatch(c, e);
 }
 void wide_emu_conflicts(long long *wavefronts, long long *ideal) {

@@ -50,7 +50,7 @@ def emu_stft(lib, o, tf, x, p0=None, p1=None, k_offset=0, spectrogram=False, ldp
     return out[:, :, :P]
 
 
-def emu_istft(lib, o, tf, S, k0=None, k1=None, chunk_tiles=3, ldp_align=2):
+def emu_istft(lib, o, tf, S, k0=None, k1=None, chunk_tiles=3, ldp_align=2, land=1):
     S = np.asarray(S, dtype=np.complex64)
     B, F, P = S.shape
     ldp = -(-P // ldp_align) * ldp_align
@@ -63,7 +63,7 @@ def emu_istft(lib, o, tf, S, k0=None, k1=None, chunk_tiles=3, ldp_align=2):
     rc = lib.wide_emu_inverse(C.c_int64(o.mfft), C.c_int(tf), dptr(dual), C.c_void_p(Sp.ctypes.data), C.c_int64(P),
                               C.c_int64(ldp), C.c_int64(B), C.c_int64(F), C.c_int64(o.p_min), C.c_int64(a), C.c_int64(b),
                               C.c_int64(q0), C.c_int64(q1), C.c_int(MODES[o.fft_mode]), C.c_double(fac2x),
-                              C.c_int(chunk_tiles), C.c_void_p(out.ctypes.data), C.c_int64(b - a))
+                              C.c_int(chunk_tiles), C.c_void_p(out.ctypes.data), C.c_int64(b - a), C.c_int(land))
     assert rc == 0
     assert not np.isnan(out).any()
     return out
@@ -127,3 +127,9 @@ def test_inverse_matches_oracle(emu, M, tf, mode):
     # sub-range, dense odd pitch, other chunking: bit-identical where they overlap (same summation order)
     y2 = emu_istft(emu, o, tf, S, k0=M // 4 + 3, k1=n - 5, chunk_tiles=2, ldp_align=1)
     assert np.array_equal(y2, y[:, M // 4 + 3:n - 5])
+    # the direct-load path (no tensor map) gives the same bits as the landed-tile path
+    emu.wide_emu_reset()
+    y3 = emu_istft(emu, o, tf, S, land=0)
+    assert np.array_equal(y3, y)
+    for name, (w, i) in conflicts(emu).items():
+        assert w == i, f"{name}: {w} wavefronts for {i} conflict-free ones"

@@ -29,7 +29,8 @@ struct FwdLaunch {
         const fl2 *t = reinterpret_cast<const fl2 *>(tab);
         WFwdArgs a;
         a.x = x; a.out = out;
-        a.wtab = t + o.xtab; a.tw1 = t + o.tw1; a.tw2 = t + o.tw2; a.twp = t + o.twp;
+        a.tab = t;
+        (void)o;
         a.n = p.n; a.x_pitch = p.x_pitch; a.ldp = p.ldp; a.p0 = p.p0; a.P = p.P; a.k_offset = p.k_offset;
         a.ptiles = (p.P + TF - 1) / TF; a.F = p.F;
         a.mode = p.mode; a.spectrogram = p.spectrogram;

@@ -60,14 +60,10 @@ VHD void stsx(float *p, fl2 v) {
     WD_TRACE(1, p, 8);
     *reinterpret_cast<fl2 *>(p) = v;
 }
+// plan-table entry: the kernels copy the tables to shared memory once per (persistent) CTA
 VHD fl2 ldg2(const fl2 *p) {
-#if defined(__CUDA_ARCH__)
-    const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
-    fl2 r; r.x = v.x; r.y = v.y;
-    return r;
-#else
+    WD_TRACE(0, p, 8);
     return *p;
-#endif
 }
 VHD void syncwarp() {
 #if defined(__CUDA_ARCH__)
@@ -188,10 +184,7 @@ struct WGeo {
 struct WFwdArgs {
     const float *x;
     void *out;
-    const fl2 *wtab;         // [Mc]  0.5 * (w[j0], w[j0 + 1]), j0 = (2m + M/2) mod M  (roll folded in)
-    const fl2 *tw1;          // [F1][L1]   W_Mc^(j c)
-    const fl2 *tw2;          // [F2][L2]   W_L1^(j2 c2)
-    const fl2 *twp;          // [Mc + 1]   W_M^k
+    const fl2 *tab;          // plan table in global memory (layout: wide_table_fill)
     int64_t n, x_pitch, ldp, p0, P, k_offset, ptiles, F;
     int mode;                // 0 twosided, 1 centered, 2 onesided, 3 onesided2X
     int spectrogram;
@@ -200,6 +193,10 @@ struct WFwdArgs {
 };
 struct WFwdCtx {
     WFwdArgs a;
+    const fl2 *wtab;         // [Mc]  0.5 * (w[j0], w[j0 + 1]), j0 = (2m + M/2) mod M  (roll folded in)
+    const fl2 *tw1;          // [F1][L1]   W_Mc^(j c)
+    const fl2 *tw2;          // [F2][L2]   W_L1^(j2 c2)
+    const fl2 *twp;          // [Mc + 1]   W_M^k          (shared-memory copies on the device)
     float *xin;              // staged signal [ROWS][HS]
     float *work;             // [Mc][2][TF], swizzled
     int64_t b, pt;
@@ -246,7 +243,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
             C2 v[R1];
             const float *xa = c.xin + GEO::slice_of(l, 0) * HS + 2 * jg;
             const float *xb = c.xin + GEO::slice_of(l, 1) * HS + 2 * jg;
-            const fl2 *wt = c.a.wtab + jg;
+            const fl2 *wt = c.wtab + jg;
 #pragma unroll
             for (int a = 0; a < R1; ++a) {
                 // FFT slot 2m, m = jg + L1 a, holds sample j0 = (2m + M/2) mod M of the slice (the roll
@@ -261,7 +258,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
             Dft<R1, false, f2>::run(v);
             float *wre = c.work + GEO::off_re(jg) + 2 * l;
             float *wim = c.work + GEO::off_im(jg) + 2 * l;
-            const fl2 *tw = c.a.tw1 + jg;
+            const fl2 *tw = c.tw1 + jg;
             sts2(wre, v[0].x);
             sts2(wim, v[0].y);
 #pragma unroll
@@ -274,7 +271,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
         }
     }
 
-    VHD static void pass2(const WFwdCtx &c, int tid) { GEO::template pass2_t<false, R1, R2, L2>(c.work, c.a.tw2, tid); }
+    VHD static void pass2(const WFwdCtx &c, int tid) { GEO::template pass2_t<false, R1, R2, L2>(c.work, c.tw2, tid); }
 
     // ---- output of one bin for the thread's two slices
     struct Out {
@@ -358,7 +355,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
                 GEO::template ld_grp<RL, L1, L2>(c.work, gB % R1, gB / R1, l, uB);
                 Dft<RL, false, f2>::run(uA);
                 Dft<RL, false, f2>::run(uB);
-                const fl2 *tq = p.twp + gA;
+                const fl2 *tq = c.twp + gA;
 #pragma unroll
                 for (int d = 0; d < RL; ++d)
                     split<MODE, SPEC>(p, o, gA + G * d, ldg2(tq + G * d), uA[d], uB[RL - 1 - d], true);
@@ -368,14 +365,14 @@ struct WFwd : WGeo<LOGMC, TF_> {
                 GEO::template ld_grp<RL, L1, L2>(c.work, 0, R2 / 2, l, uB);
                 Dft<RL, false, f2>::run(uA);
                 Dft<RL, false, f2>::run(uB);
-                split<MODE, SPEC>(p, o, 0, ldg2(p.twp), uA[0], uA[0], true);                 // X[0], X[Mc]
+                split<MODE, SPEC>(p, o, 0, ldg2(c.twp), uA[0], uA[0], true);                 // X[0], X[Mc]
 #pragma unroll
                 for (int d = 1; d < RL / 2; ++d)
-                    split<MODE, SPEC>(p, o, G * d, ldg2(p.twp + G * d), uA[d], uA[RL - d], true);
-                split<MODE, SPEC>(p, o, MC / 2, ldg2(p.twp + MC / 2), uA[RL / 2], uA[RL / 2], false);
+                    split<MODE, SPEC>(p, o, G * d, ldg2(c.twp + G * d), uA[d], uA[RL - d], true);
+                split<MODE, SPEC>(p, o, MC / 2, ldg2(c.twp + MC / 2), uA[RL / 2], uA[RL / 2], false);
 #pragma unroll
                 for (int d = 0; d < RL / 2; ++d)
-                    split<MODE, SPEC>(p, o, G / 2 + G * d, ldg2(p.twp + G / 2 + G * d), uB[d], uB[RL - 1 - d], true);
+                    split<MODE, SPEC>(p, o, G / 2 + G * d, ldg2(c.twp + G / 2 + G * d), uB[d], uB[RL - 1 - d], true);
             }
         }
     }
@@ -399,10 +396,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
 struct WInvArgs {
     const void *S;
     float *xo;
-    const fl2 *dtab;         // [Mc]  scale * (dual[j0], dual[j0 + 1]), j0 = (2m + M/2) mod M
-    const fl2 *tw1;          // [I1][L1]   W_Mc^(j c)
-    const fl2 *tw2;          // [I2][L2]   W_L1^(j2 c2)
-    const fl2 *twp;          // [Mc + 1]   W_M^k
+    const fl2 *tab;          // plan table in global memory (layout: wide_table_fill)
     int64_t P, ldp, out_pitch, p_min, k0, k1, q0, q1, qh0, qh1, cps, F;
     int chunk_tiles, halo;   // streaming overlap-add: tiles per chunk, slices the first tile re-computes
     int mode, vec16, vec_out, prefetch;
@@ -410,6 +404,10 @@ struct WInvArgs {
 };
 struct WInvCtx {
     WInvArgs a;
+    const fl2 *dtab;         // [Mc]  scale * (dual[j0], dual[j0 + 1]), j0 = (2m + M/2) mod M
+    const fl2 *tw1;          // [I1][L1]   W_Mc^(j c)
+    const fl2 *tw2;          // [I2][L2]   W_L1^(j2 c2)
+    const fl2 *twp;          // [Mc + 1]   W_M^k          (shared-memory copies on the device)
     float *work;             // [Mc][2][TF], swizzled
     float *acc;              // [TF + 3][HS] overlap-add accumulator: tile sample u at (u / H) HS + u % H
     int first;               // first tile of a chunk: no carry in the head, owns samples from halo * H on
@@ -535,7 +533,7 @@ struct WInv : WGeo<LOGMC, TF_> {
             C2 vA[R1], vB[R1];
             int jA = w, jB = L1 - w;
             if (w != 0) {
-                const fl2 *tq = p.twp + jA;
+                const fl2 *tq = c.twp + jA;
 #pragma unroll
                 for (int a = 0; a < R1; ++a) {
                     const Raw XA = load_bin<MODE>(p, in, jA + L1 * a, pf);
@@ -553,19 +551,19 @@ struct WInv : WGeo<LOGMC, TF_> {
 #pragma unroll
                 for (int a = 1; a < R1 / 2; ++a) {
                     const Raw XA = load_bin<MODE>(p, in, L1 * a, pf), XB = load_bin<MODE>(p, in, L1 * (R1 - a), pf);
-                    merge(ldg2(p.twp + L1 * a), XA, XB, vA[a], vA[R1 - a]);
+                    merge(ldg2(c.twp + L1 * a), XA, XB, vA[a], vA[R1 - a]);
                 }
                 {
                     const Raw Xh = load_bin<MODE>(p, in, MC / 2, pf);
                     C2 dump;
-                    merge(ldg2(p.twp + MC / 2), Xh, Xh, vA[R1 / 2], dump);
+                    merge(ldg2(c.twp + MC / 2), Xh, Xh, vA[R1 / 2], dump);
                 }
                 // group L1/2: bin L1/2 + L1 a <-> L1/2 + L1 (R1 - 1 - a)
 #pragma unroll
                 for (int a = 0; a < R1 / 2; ++a) {
                     const Raw XA = load_bin<MODE>(p, in, L1 / 2 + L1 * a, pf);
                     const Raw XB = load_bin<MODE>(p, in, L1 / 2 + L1 * (R1 - 1 - a), pf);
-                    merge(ldg2(p.twp + L1 / 2 + L1 * a), XA, XB, vB[a], vB[R1 - 1 - a]);
+                    merge(ldg2(c.twp + L1 / 2 + L1 * a), XA, XB, vB[a], vB[R1 - 1 - a]);
                 }
             }
             Dft<R1, true, f2>::run(vA);
@@ -574,10 +572,96 @@ struct WInv : WGeo<LOGMC, TF_> {
             store_group(c, l, jB, vB);
         }
     }
+    // ================= TMA path (one-sided layouts): the S tile has LANDED over the work buffer ==========
+    // NH = TF / 8 column blocks; block h holds columns [8h, 8h + 8) of the tile as [Mc rows][8 slices][re, im]
+    // (row k at k * 64 bytes -- for consecutive units a wavefront reads 128 contiguous bytes), the NH
+    // Nyquist rows sit behind the blocks.  Columns outside S arrive as zeros (tensor-map bounds).
+    static constexpr int NH = TF / 8;
+    static constexpr int LAND_BLOCK = MC * 16;                           // floats per column block
+    static constexpr int LAND_FLOATS = NH * (MC * 16 + 16);
+    static constexpr unsigned LAND_BYTES = 4u * LAND_FLOATS;
+    struct Live { bool l0, l1; };
+    VHD static Live make_live(const WInvCtx &c, int l) {
+        const WInvArgs &p = c.a;
+        const int64_t qa0 = c.qa + GEO::slice_of(l, 0), qa1 = c.qa + GEO::slice_of(l, 1);
+        const int64_t col0 = qa0 - p.p_min, col1 = qa1 - p.p_min;
+        Live v;
+        v.l0 = qa0 >= p.q0 && qa0 < p.q1 && col0 >= 0 && col0 < p.P;
+        v.l1 = qa1 >= p.q0 && qa1 < p.q1 && col1 >= 0 && col1 < p.P;
+        return v;
+    }
+    template <int MODE>
+    VHD static Raw land_bin(const WInvCtx &c, const Live &lv, int l, int k) {
+        Raw v;
+        const float *rowp = k < MC ? c.work + 16 * k : c.work + NH * LAND_BLOCK;      // Nyquist rows: [NH][16]
+        const int bs = k < MC ? LAND_BLOCK : 16;                                        // block stride
+        if (ADJ) {
+            const float *q = rowp + 4 * l;
+            WD_TRACE(0, q, 16);
+            const fl4 t = *reinterpret_cast<const fl4 *>(q);
+            v.r0 = t.x; v.i0 = t.y; v.r1 = t.z; v.i1 = t.w;
+        } else {
+            const fl2 a = ldsx(rowp + 2 * l), b = ldsx(rowp + bs + 2 * l);
+            v.r0 = a.x; v.i0 = a.y; v.r1 = b.x; v.i1 = b.y;
+        }
+        if (!lv.l0) { v.r0 = 0.f; v.i0 = 0.f; }
+        if (!lv.l1) { v.r1 = 0.f; v.i1 = 0.f; }
+        if (MODE == 3 && k >= 1 && k <= MC - 1) {
+            v.r0 *= c.a.rfac2x; v.i0 *= c.a.rfac2x; v.r1 *= c.a.rfac2x; v.i1 *= c.a.rfac2x;
+        }
+        return v;
+    }
+    // loads of unit w (both groups of the pair, + Nyquist for w = 0) from the landed tile; the caller
+    // synchronises the CTA before land_rest overwrites the buffer
+    struct P1Regs { Raw XA[R1], XB[R1], XN; };
+    static constexpr int P1_ITERS = (L1 / 2 + NSUB - 1) / NSUB;
+    template <int MODE>
+    VHD static void land_load(const WInvCtx &c, int tid, int it, P1Regs &r) {
+        const int l = tid % LN, w = tid / LN + it * NSUB;
+        if (w >= L1 / 2) return;
+        const Live lv = make_live(c, l);
+        const int jA = w, jB = w == 0 ? L1 / 2 : L1 - w;
+#pragma unroll
+        for (int a = 0; a < R1; ++a) {
+            r.XA[a] = land_bin<MODE>(c, lv, l, jA + L1 * a);
+            r.XB[a] = land_bin<MODE>(c, lv, l, jB + L1 * a);
+        }
+        r.XN = r.XA[0];
+        if (w == 0) r.XN = land_bin<MODE>(c, lv, l, MC);
+    }
+    VHD static void land_rest(const WInvCtx &c, int tid, int it, const P1Regs &r) {
+        const int l = tid % LN, w = tid / LN + it * NSUB;
+        if (w >= L1 / 2) return;
+        C2 vA[R1], vB[R1];
+        int jA = w, jB = L1 - w;
+        if (w != 0) {
+            const fl2 *tq = c.twp + jA;
+#pragma unroll
+            for (int a = 0; a < R1; ++a) merge(ldg2(tq + L1 * a), r.XA[a], r.XB[R1 - 1 - a], vA[a], vB[R1 - 1 - a]);
+        } else {
+            jB = L1 / 2;
+            vA[0].x = mk2(r.XA[0].r0 + r.XN.r0, r.XA[0].r1 + r.XN.r1);       // DC, Nyquist: imaginary parts ignored
+            vA[0].y = mk2(r.XA[0].r0 - r.XN.r0, r.XA[0].r1 - r.XN.r1);
+#pragma unroll
+            for (int a = 1; a < R1 / 2; ++a) merge(ldg2(c.twp + L1 * a), r.XA[a], r.XA[R1 - a], vA[a], vA[R1 - a]);
+            {
+                C2 dump;
+                merge(ldg2(c.twp + MC / 2), r.XA[R1 / 2], r.XA[R1 / 2], vA[R1 / 2], dump);
+            }
+#pragma unroll
+            for (int a = 0; a < R1 / 2; ++a)
+                merge(ldg2(c.twp + L1 / 2 + L1 * a), r.XB[a], r.XB[R1 - 1 - a], vB[a], vB[R1 - 1 - a]);
+        }
+        Dft<R1, true, f2>::run(vA);
+        Dft<R1, true, f2>::run(vB);
+        store_group(c, l, jA, vA);
+        store_group(c, l, jB, vB);
+    }
+
     VHD static void store_group(const WInvCtx &c, int l, int j, const C2 (&v)[R1]) {
         float *wre = c.work + GEO::off_re(j) + 2 * l;
         float *wim = c.work + GEO::off_im(j) + 2 * l;
-        const fl2 *tw = c.a.tw1 + j;
+        const fl2 *tw = c.tw1 + j;
         sts2(wre, v[0].x);
         sts2(wim, v[0].y);
 #pragma unroll
@@ -595,7 +679,7 @@ struct WInv : WGeo<LOGMC, TF_> {
         else if (m == 1) pass1_t<1>(c, tid);
         else pass1_t<0>(c, tid);
     }
-    VHD static void pass2(const WInvCtx &c, int tid) { GEO::template pass2_t<true, R1, R2, L2>(c.work, c.a.tw2, tid); }
+    VHD static void pass2(const WInvCtx &c, int tid) { GEO::template pass2_t<true, R1, R2, L2>(c.work, c.tw2, tid); }
 
     // ---- pass 3: warp unit = (c2, run of SUBW consecutive cb): the thread's group g = cb + R1 c2 yields
     //      z'[m], m = g + G d, i.e. the time samples 2m, 2m+1 of its two slices.  NIT units per thread.
@@ -631,7 +715,7 @@ struct WInv : WGeo<LOGMC, TF_> {
             const int g = cb + R1 * c2;
             float *a0 = c.acc + (GEO::slice_of(l, 0) + Q) * HS + 2 * g;
             float *a1 = c.acc + (GEO::slice_of(l, 1) + Q) * HS + 2 * g;
-            const fl2 *dq = c.a.dtab + g;
+            const fl2 *dq = c.dtab + g;
 #pragma unroll
             for (int dd = 0; dd < DQ; ++dd) {
                 const int d = (((Q + 2) & 3) * DQ + dd);                     // j0 / H = (d / DQ + 2) mod 4 = Q
@@ -733,11 +817,12 @@ inline auto wide_dispatch(const WCfg &c, FN &fn) -> decltype(fn.template run<9, 
 //   [xtab: Mc][tw1: R1 L1 = Mc][tw2: R2 L2 = L1][twp: Mc + 1]
 // xtab = window * 0.5 (forward, the 1/2 of the real-FFT split) or dual * scale (inverse), permuted so
 // that entry m holds the samples j0, j0 + 1 with j0 = (2m + M/2) mod M of FFT slots 2m, 2m + 1.
-inline int64_t wide_table_entries(int64_t M) { const int64_t mc = M / 2; return mc + mc + mc + (mc + 1); }   // tw2 <= Mc
+// (tw2 gets Mc / 8 >= L1 entries: R1 >= 8 in every plan)
+inline int64_t wide_table_entries(int64_t M) { const int64_t mc = M / 2; return mc + mc + mc / 8 + (mc + 1) + 1; }
 struct WTabOff { int64_t xtab, tw1, tw2, twp; };
 inline WTabOff wide_table_offsets(int64_t M) {
     const int64_t mc = M / 2;
-    return WTabOff{0, mc, 2 * mc, 3 * mc};
+    return WTabOff{0, mc, 2 * mc, 2 * mc + mc / 8};
 }
 inline void wide_table_fill(int64_t M, int r1, int r2, const double *vec_n, double scale, double *out2) {
     const int64_t mc = M / 2, l1 = mc / r1, l2 = l1 / r2;
@@ -754,16 +839,19 @@ inline void wide_table_fill(int64_t M, int r1, int r2, const double *vec_n, doub
         for (int64_t j = 0; j < l2; ++j) tw_exact(j * cc, l1, &out2[2 * (o.tw2 + cc * l2 + j)], &out2[2 * (o.tw2 + cc * l2 + j) + 1]);
     for (int64_t k = 0; k <= mc; ++k) tw_exact(k, M, &out2[2 * (o.twp + k)], &out2[2 * (o.twp + k) + 1]);
 }
+// shared memory: [work (+ the landed Nyquist rows)][staged signal | accumulator][plan table][mbarrier]
 template <int LOGMC, int TF>
-inline size_t wide_fwd_smem_bytes() {
+inline size_t wide_work_floats() {
     using G = WGeo<LOGMC, TF>;
-    return 4 * ((size_t)G::WORK_FLOATS + (size_t)G::XIN_FLOATS);
+    return (size_t)G::WORK_FLOATS + 32;               // + NH Nyquist rows of the landed tile (inverse, TMA path)
 }
 template <int LOGMC, int TF>
-inline size_t wide_inv_smem_bytes() {
+inline size_t wide_smem_bytes() {
     using G = WGeo<LOGMC, TF>;
-    return 4 * ((size_t)G::WORK_FLOATS + (size_t)G::XIN_FLOATS);
+    return 4 * (wide_work_floats<LOGMC, TF>() + (size_t)G::XIN_FLOATS) + 8 * (size_t)wide_table_entries(G::M) + 16;
 }
+template <int LOGMC, int TF> inline size_t wide_fwd_smem_bytes() { return wide_smem_bytes<LOGMC, TF>(); }
+template <int LOGMC, int TF> inline size_t wide_inv_smem_bytes() { return wide_smem_bytes<LOGMC, TF>(); }
 
 }  // namespace wd
 }  // namespace veils

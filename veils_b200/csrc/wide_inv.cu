@@ -11,7 +11,17 @@ struct InvLaunch {
     template <int LOGMC, int TF, int MODE>
     cudaError_t go(WInvArgs &a) {
         using K = WInv<LOGMC, TF>;
-        auto kern = wide_inv_kernel<LOGMC, TF, MODE>;
+        // one-sided layouts: the S tiles land through the TMA engine when S can be described by a tensor map
+        // (16-byte aligned base and row pitch); P1_ITERS > 1 would overwrite the landed tile between iterations
+        CUtensorMap smap, smap_nyq;
+        memset(&smap, 0, sizeof(smap));
+        memset(&smap_nyq, 0, sizeof(smap_nyq));
+        const bool land = MODE >= 2 && K::P1_ITERS == 1 && a.vec16 && !env_int("VEILS_WIDE_NO_TMA", 0) &&
+                          tma::make_land_map(&smap, S, a.P, a.ldp, a.F, prm->batch, K::L1, K::R1, K::L1, K::R1) &&
+                          tma::make_land_map(&smap_nyq, S, a.P, a.ldp, a.F, prm->batch, K::L1, K::R1, 1, 1);
+        using KernT = void (*)(const WInvArgs, const int64_t, const CUtensorMap, const CUtensorMap);
+        KernT kern = wide_inv_kernel<LOGMC, TF, MODE, false>;
+        if (MODE >= 2 && land) kern = wide_inv_kernel<LOGMC, TF, (MODE >= 2 ? MODE : 2), true>;
         const size_t smem = wide_inv_smem_bytes<LOGMC, TF>();
         int cap = 0;
         cudaError_t e = wide_prepare(kern, K::NT, smem, &cap);
@@ -25,7 +35,7 @@ struct InvLaunch {
         a.chunk_tiles = ct;
         a.cps = cps(ct);
         const int64_t total = a.cps * prm->batch;
-        kern<<<(unsigned)(total < cap ? total : cap), K::NT, smem, st>>>(a, total);
+        kern<<<(unsigned)(total < cap ? total : cap), K::NT, smem, st>>>(a, total, smap, smap_nyq);
         ++g_launch_count;
         return cudaGetLastError();
     }
@@ -37,7 +47,8 @@ struct InvLaunch {
         const fl2 *t = reinterpret_cast<const fl2 *>(tab);
         WInvArgs a;
         a.S = S; a.xo = xo;
-        a.dtab = t + o.xtab; a.tw1 = t + o.tw1; a.tw2 = t + o.tw2; a.twp = t + o.twp;
+        a.tab = t;
+        (void)o;
         a.P = p.P; a.ldp = p.ldp; a.out_pitch = p.out_pitch; a.p_min = p.p_min;
         a.k0 = p.k0; a.k1 = p.k1; a.q0 = p.q0; a.q1 = p.q1; a.F = p.F;
         a.mode = p.mode;

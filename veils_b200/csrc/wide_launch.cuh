@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "wide_impl.cuh"
+#include "tma.cuh"
 
 namespace veils {
 namespace wd {
@@ -30,6 +31,20 @@ inline const DevInfo &dev_info() {
     return info;
 }
 
+// plan table -> shared memory, once per persistent CTA (offsets: wide_table_offsets)
+#define TAB_ENTRIES(M) ((M) / 2 * 3 + (M) / 16 + 2)
+#define TAB_XTAB(M) 0
+#define TAB_TW1(M) ((M) / 2)
+#define TAB_TW2(M) (M)
+#define TAB_TWP(M) ((M) + (M) / 16)
+__device__ __forceinline__ void copy_table(fl2 *dst, const fl2 *src, int n, int tid, int nt) {
+    for (int i = tid; i < n; i += nt) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(src + i));
+        fl2 r; r.x = v.x; r.y = v.y;
+        dst[i] = r;
+    }
+}
+
 // ---- forward: persistent CTAs walk the (signal, tile) list; the next tile's samples are staged
 //      (cp.async) while passes 2 and 3 of the current tile run
 template <int LOGMC, int TF, int MODE, bool SPEC>
@@ -41,7 +56,12 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
     WFwdCtx c;
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
-    c.xin = c.work + K::WORK_FLOATS;
+    c.xin = c.work + (K::WORK_FLOATS + 32);
+    {
+        fl2 *tab = reinterpret_cast<fl2 *>(c.xin + K::XIN_FLOATS);
+        copy_table(tab, args.tab, TAB_ENTRIES(K::M), tid, K::NT);
+        c.wtab = tab + TAB_XTAB(K::M); c.tw1 = tab + TAB_TW1(K::M); c.tw2 = tab + TAB_TW2(K::M); c.twp = tab + TAB_TWP(K::M);
+    }
     int64_t w = blockIdx.x;
     if (w >= total) return;
     int64_t cb = w / args.ptiles, cpt = w - cb * args.ptiles;
@@ -75,50 +95,123 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
 }
 
 // ---- inverse: a CTA walks the tiles of one chunk of one signal in order (streaming overlap-add:
-//      the accumulator rows TF .. TF+2 carry over to the next tile)
-template <int LOGMC, int TF, int MODE>
+//      the accumulator rows TF .. TF+2 carry over to the next tile).
+//      LAND (one-sided layouts, S describable by a tensor map): the S tile of the NEXT work item is
+//      requested from the TMA engine as soon as the last pass has read the work buffer and lands over
+//      it while the overlap-add and the output of the current tile run; pass 1 then reads shared
+//      memory.  Otherwise pass 1 loads S straight from global memory.
+struct WTile {
+    int64_t ch, b, qa;
+    int t;
+    bool valid;
+};
+template <int TF>
+__device__ __forceinline__ WTile wide_first_tile(const WInvArgs &a, int64_t total, int64_t lc) {
+    WTile w;
+    w.ch = blockIdx.x;
+    w.t = 0;
+    w.valid = w.ch < total;
+    w.b = w.valid ? w.ch / a.cps : 0;
+    w.qa = a.qh0 + (w.ch - w.b * a.cps) * lc - a.halo;
+    return w;
+}
+template <int TF>
+__device__ __forceinline__ WTile wide_next_tile(const WInvArgs &a, const WTile &c, int64_t total, int64_t lc) {
+    WTile w = c;
+    if (c.t + 1 < a.chunk_tiles && c.qa + TF <= a.qh1) {
+        w.t = c.t + 1;
+        w.qa = c.qa + TF;
+        return w;
+    }
+    w.ch = c.ch + gridDim.x;
+    w.t = 0;
+    w.valid = w.ch < total;
+    w.b = w.valid ? w.ch / a.cps : 0;
+    w.qa = a.qh0 + (w.ch - w.b * a.cps) * lc - a.halo;
+    return w;
+}
+
+template <int LOGMC, int TF, int MODE, bool LAND>
 __global__ void __launch_bounds__(WGeo<LOGMC, TF>::NT, wide_min_ctas<WGeo<LOGMC, TF>::NT>())
-wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total) {
+wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, const __grid_constant__ CUtensorMap smap,
+                const __grid_constant__ CUtensorMap smap_nyq) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using K = WInv<LOGMC, TF>;
     const int tid = threadIdx.x;
     WInvCtx c;
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
-    c.acc = c.work + K::WORK_FLOATS;
+    c.acc = c.work + (K::WORK_FLOATS + 32);
+    fl2 *tab = reinterpret_cast<fl2 *>(c.acc + K::XIN_FLOATS);
+    copy_table(tab, args.tab, TAB_ENTRIES(K::M), tid, K::NT);
+    c.dtab = tab + TAB_XTAB(K::M); c.tw1 = tab + TAB_TW1(K::M); c.tw2 = tab + TAB_TW2(K::M); c.twp = tab + TAB_TWP(K::M);
+    const unsigned land_bar = tma::smem_u32(tab + TAB_ENTRIES(K::M));
+    if (LAND && tid == 0) {
+        tma::mbar_init(land_bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
     const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
-    for (int64_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        c.b = ch / args.cps;
-        const int64_t a0 = args.qh0 + (ch - c.b * args.cps) * lc;      // first owned slice
-#pragma unroll 1
-        for (int t = 0; t < args.chunk_tiles; ++t) {
-            c.qa = a0 - args.halo + (int64_t)t * TF;
-            if (c.qa > args.qh1) break;
-            c.first = t == 0;
-            c.more = (t + 1 < args.chunk_tiles && c.qa + TF <= args.qh1) ? 1 : 0;
-            K::template pass1_t<MODE>(c, tid);
-            __syncthreads();
-            K::pass2(c, tid);
-            __syncthreads();
-            {
-                typename K::Regs r;
-                K::pass3_load(c, tid, r);
-                if (c.first) K::zero_head(c, tid);
-                K::template ola<3>(c, tid, r);
-                __syncthreads();
-                K::template ola<2>(c, tid, r);
-                __syncthreads();
-                K::template ola<1>(c, tid, r);
-                __syncthreads();
-                K::template ola<0>(c, tid, r);
-            }
-            __syncthreads();
-            K::out(c, tid);
-            typename K::Tail tail;
-            K::take_tail(c, tid, tail);
-            __syncthreads();
-            K::keep_tail(c, tid, tail);
+    auto land = [&](const WTile &w) {
+        if (tid != 0) return;
+        tma::fence_async_smem();               // earlier generic-proxy accesses to the buffer are ordered first
+        const unsigned wbase = tma::smem_u32(c.work);
+        const int col0 = (int)(w.qa - args.p_min);
+        tma::mbar_expect_tx(land_bar, K::LAND_BYTES);
+#pragma unroll
+        for (int h = 0; h < K::NH; ++h) {
+            tma::load_4d(&smap, wbase + 4u * h * K::LAND_BLOCK, land_bar, col0 + 8 * h, 0, 0, (int)w.b);
+            tma::load_4d(&smap_nyq, wbase + 4u * (K::NH * K::LAND_BLOCK + 16 * h), land_bar, col0 + 8 * h, 0, K::R1, (int)w.b);
         }
+    };
+    WTile cur = wide_first_tile<TF>(args, total, lc);
+    unsigned phase = 0;
+    if (LAND && cur.valid) land(cur);
+    while (cur.valid) {
+        const WTile nxt = wide_next_tile<TF>(args, cur, total, lc);
+        c.b = cur.b;
+        c.qa = cur.qa;
+        c.first = cur.t == 0;
+        c.more = (nxt.valid && nxt.ch == cur.ch) ? 1 : 0;
+        if (LAND) {
+            tma::mbar_wait(land_bar, phase);
+            phase ^= 1;
+#pragma unroll 1
+            for (int it = 0; it < K::P1_ITERS; ++it) {
+                typename K::P1Regs r;
+                K::template land_load<MODE>(c, tid, it, r);
+                __syncthreads();               // every thread holds its bins before anyone overwrites the tile
+                K::land_rest(c, tid, it, r);
+            }
+        } else {
+            K::template pass1_t<MODE>(c, tid);
+        }
+        __syncthreads();
+        K::pass2(c, tid);
+        __syncthreads();
+        {
+            typename K::Regs r;
+            K::pass3_load(c, tid, r);
+            if (LAND) {
+                __syncthreads();               // the work buffer is free: the next tile lands during what follows
+                if (nxt.valid) land(nxt);
+            }
+            if (c.first) K::zero_head(c, tid);
+            K::template ola<3>(c, tid, r);
+            __syncthreads();
+            K::template ola<2>(c, tid, r);
+            __syncthreads();
+            K::template ola<1>(c, tid, r);
+            __syncthreads();
+            K::template ola<0>(c, tid, r);
+        }
+        __syncthreads();
+        K::out(c, tid);
+        typename K::Tail tail;
+        K::take_tail(c, tid, tail);
+        __syncthreads();
+        K::keep_tail(c, tid, tail);
+        cur = nxt;
     }
 }
 
