@@ -167,9 +167,8 @@ struct EmuInv {
         a.vec_out = ((uintptr_t)xo % 16) == 0 ? 1 : 0;
         a.qh0 = fdiv64(k0 + K::MID, K::H);
         a.qh1 = fdiv64(k1 - 1 + K::MID, K::H);
-        a.halo = 3 + (int)((a.qh0 - 3 - p_min) & 1);            // even first column: 16-byte loads of slice pairs
         a.chunk_tiles = chunk_tiles;
-        const int64_t lc = (int64_t)TF * chunk_tiles - a.halo, Q = a.qh1 - a.qh0 + 1;
+        const int64_t lc = (int64_t)TF * chunk_tiles - 4, Q = a.qh1 - a.qh0 + 1;
         a.cps = (Q + lc - 1) / lc;
         std::vector<fl4> smem((wide_work_floats<LOGMC, TF>() + K::XIN_FLOATS) / 4 + 4);
         c.work = (float *)smem.data();
@@ -178,12 +177,13 @@ struct EmuInv {
         std::vector<typename K::Regs> regs((size_t)K::NT);
         std::vector<typename K::Tail> tails((size_t)K::NT);
         for (int64_t ch = 0; ch < a.cps * batch; ++ch) {
-            c.b = ch / a.cps;
-            const int64_t a0 = a.qh0 + (ch - c.b * a.cps) * lc;
+            const WChunk wc = wide_chunk(a, ch, TF, K::H, K::MID);
+            c.b = wc.b; c.halo = wc.halo; c.kend = wc.kend;
             for (size_t i = 0; i < smem.size() * 4; ++i) c.work[i] = std::nanf("");    // poison
             for (int t = 0; t < chunk_tiles; ++t) {
-                c.qa = a0 - a.halo + (int64_t)t * TF;
+                c.qa = wc.qa0 + (int64_t)t * TF;
                 if (c.qa > a.qh1) break;
+                if (((c.qa - p_min) & 1) != 0) return -7;                              // tiles start on even columns
                 c.first = t == 0;
                 c.more = 0;
                 g_tracing = ch == 0 && t == 1;
@@ -197,7 +197,7 @@ struct EmuInv {
                             for (int i = 0; i < 8; ++i) {
                                 const int64_t col = col0 + 8 * h + i;
                                 float *dst = k < K::MC ? c.work + h * K::LAND_BLOCK + 16 * k + 2 * i
-                                                       : c.work + K::NH * K::LAND_BLOCK + 16 * h + 2 * i;
+                                                       : c.work + K::NH * K::LAND_BLOCK + K::NYQ_STRIDE * h + 2 * i;
                                 const bool ok = col >= 0 && col < P;
                                 const float *src = Sf + 2 * ((c.b * F + k) * ldp + col);
                                 dst[0] = ok ? src[0] : 0.f;

@@ -78,31 +78,35 @@ inline bool make_s_map5(CUtensorMap *m, const void *base, int esz, int64_t P, in
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// Tensor map for LANDING a tile of S[b][f][p] (8-byte elements) in shared memory (wide_inv_kernel):
-//   dim0 = p (size P), dim1 = j (size L1, stride ldp), dim2 = a (size R1 + 1, stride L1 ldp), dim3 = b:
-//   row f = j + L1 a; (j = 0, a = R1) is the Nyquist row, the other (j, R1) are never touched.
-// Box = [8 slices][box_j][box_a][1].  Needs a 16-byte aligned base and row pitch.
-inline bool make_land_map(CUtensorMap *m, const void *base, int64_t P, int64_t ldp, int64_t F, int64_t B, int L1, int R1,
-                          int box_j, int box_a) {
+// Tensor map for LANDING a tile of S[b][f][p] (8-byte elements) in shared memory (wide_inv_kernel): the plain
+// 3-D view dim0 = p (size P), dim1 = f (size F, stride ldp), dim2 = b (stride F ldp); box = [8 slices][rows][1].
+// Needs a 16-byte aligned base and row pitch.  (4-D views with the smaller row stride in dim1 trap as
+// "illegal instruction" in the load direction on this driver -- see make_s_map.)
+inline bool make_land_map(CUtensorMap *m, const void *base, int64_t P, int64_t ldp, int64_t F, int64_t B, int box_rows) {
     EncodeFn fn = encode_fn();
     if (!fn) return false;
     if (((uintptr_t)base & 15) != 0 || (ldp * 8) % 16 != 0) return false;
-    if (P <= 0 || B <= 0 || P >= (1LL << 31) || B >= (1LL << 31) || box_j > 256 || box_a > 256) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)P, (cuuint64_t)L1, (cuuint64_t)(R1 + 1), (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)(ldp * 8), (cuuint64_t)(L1 * ldp * 8), (cuuint64_t)(F * ldp * 8)};
-    for (int i = 0; i < 3; ++i)
+    if (P <= 0 || B <= 0 || P >= (1LL << 31) || B >= (1LL << 31) || box_rows > 256) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)F, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)(ldp * 8), (cuuint64_t)(F * ldp * 8)};
+    for (int i = 0; i < 2; ++i)
         if (strides[i] >= (1ULL << 40) || strides[i] % 16 != 0) return false;
-    const cuuint32_t box[4] = {8, (cuuint32_t)box_j, (cuuint32_t)box_a, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void *>(base), dims, strides, box, estr,
+    const cuuint32_t box[3] = {8, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 #if defined(__CUDACC__)
-__device__ __forceinline__ void prefetch_l2_4d(const CUtensorMap *m, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];"
-                 ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+__device__ __forceinline__ void prefetch_l2_3d(const CUtensorMap *m, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];"
+                 ::"l"(m), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// global -> shared, 3-D box, completion on an mbarrier (complete_tx::bytes)
+__device__ __forceinline__ void load_3d(const CUtensorMap *m, unsigned dst, unsigned bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void store_5d(const CUtensorMap *m, unsigned src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"

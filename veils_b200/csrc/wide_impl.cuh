@@ -398,7 +398,7 @@ struct WInvArgs {
     float *xo;
     const fl2 *tab;          // plan table in global memory (layout: wide_table_fill)
     int64_t P, ldp, out_pitch, p_min, k0, k1, q0, q1, qh0, qh1, cps, F;
-    int chunk_tiles, halo;   // streaming overlap-add: tiles per chunk, slices the first tile re-computes
+    int chunk_tiles;         // streaming overlap-add: tiles per chunk (a chunk owns TF * chunk_tiles - 4 slices)
     int mode, vec16, vec_out, prefetch;
     float rfac2x;
 };
@@ -411,9 +411,25 @@ struct WInvCtx {
     float *work;             // [Mc][2][TF], swizzled
     float *acc;              // [TF + 3][HS] overlap-add accumulator: tile sample u at (u / H) HS + u % H
     int first;               // first tile of a chunk: no carry in the head, owns samples from halo * H on
+    int halo;                // slices the first tile of this chunk re-computes (3 or 4: even first column)
     int more;                // another tile of this chunk follows (L2 prefetch of its S columns)
     int64_t b, qa;
+    int64_t kend;            // first sample the NEXT chunk owns
 };
+// Chunk ch of the launch: signal b, first owned slice a0, first computed slice qa0 = a0 - halo.  The halo is 3
+// slices (75 % overlap) or 4, whichever puts the tile on an even column of S: the slice pairs of a lane
+// are then one aligned 16-byte access and the tile can be described to the TMA engine.
+struct WChunk { int64_t b, qa0, kend; int halo; };
+VHD WChunk wide_chunk(const WInvArgs &a, int64_t ch, int tf, int H, int mid) {
+    const int64_t lc = (int64_t)tf * a.chunk_tiles - 4;
+    WChunk c;
+    c.b = ch / a.cps;
+    const int64_t a0 = a.qh0 + (ch - c.b * a.cps) * lc;
+    c.halo = 3 + (int)((a0 - 3 - a.p_min) & 1);
+    c.qa0 = a0 - c.halo;
+    c.kend = (a0 + lc) * (int64_t)H - mid;
+    return c;
+}
 
 template <int LOGMC, int TF_>
 struct WInv : WGeo<LOGMC, TF_> {
@@ -578,8 +594,9 @@ struct WInv : WGeo<LOGMC, TF_> {
     // Nyquist rows sit behind the blocks.  Columns outside S arrive as zeros (tensor-map bounds).
     static constexpr int NH = TF / 8;
     static constexpr int LAND_BLOCK = MC * 16;                           // floats per column block
-    static constexpr int LAND_FLOATS = NH * (MC * 16 + 16);
-    static constexpr unsigned LAND_BYTES = 4u * LAND_FLOATS;
+    static constexpr int NYQ_STRIDE = 32;                                // Nyquist rows: 128 bytes apart (TMA alignment)
+    static constexpr int LAND_ROWS = MC < 256 ? MC : 256;                // rows per tensor box
+    static constexpr unsigned LAND_BYTES = 4u * NH * (MC * 16 + 16);     // bytes one tile brings in
     struct Live { bool l0, l1; };
     VHD static Live make_live(const WInvCtx &c, int l) {
         const WInvArgs &p = c.a;
@@ -593,8 +610,8 @@ struct WInv : WGeo<LOGMC, TF_> {
     template <int MODE>
     VHD static Raw land_bin(const WInvCtx &c, const Live &lv, int l, int k) {
         Raw v;
-        const float *rowp = k < MC ? c.work + 16 * k : c.work + NH * LAND_BLOCK;      // Nyquist rows: [NH][16]
-        const int bs = k < MC ? LAND_BLOCK : 16;                                        // block stride
+        const float *rowp = k < MC ? c.work + 16 * k : c.work + NH * LAND_BLOCK;      // Nyquist rows: [NH][32]
+        const int bs = k < MC ? LAND_BLOCK : NYQ_STRIDE;                                // block stride
         if (ADJ) {
             const float *q = rowp + 4 * l;
             WD_TRACE(0, q, 16);
@@ -747,9 +764,10 @@ struct WInv : WGeo<LOGMC, TF_> {
         constexpr int TFH = TF * H;
         const int64_t base = c.qa * (int64_t)H - MID;                       // k = base + u
         float *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
-        int64_t ka = base + (c.first ? (int64_t)p.halo * H : 0), kb = base + TFH;
+        int64_t ka = base + (c.first ? (int64_t)c.halo * H : 0), kb = base + TFH;
         if (ka < p.k0) ka = p.k0;
         if (kb > p.k1) kb = p.k1;
+        if (kb > c.kend) kb = c.kend;
         const int ua = (int)(ka - base), ub = (int)(kb - base);
         if (ub <= ua) return;
         const bool al = p.vec_out && ((((c.b * p.out_pitch - p.k0 + base)) & 3) == 0);
@@ -843,7 +861,7 @@ inline void wide_table_fill(int64_t M, int r1, int r2, const double *vec_n, doub
 template <int LOGMC, int TF>
 inline size_t wide_work_floats() {
     using G = WGeo<LOGMC, TF>;
-    return (size_t)G::WORK_FLOATS + 32;               // + NH Nyquist rows of the landed tile (inverse, TMA path)
+    return (size_t)G::WORK_FLOATS + 64;               // + NH Nyquist rows of the landed tile (inverse, TMA path)
 }
 template <int LOGMC, int TF>
 inline size_t wide_smem_bytes() {

@@ -17,8 +17,8 @@ struct InvLaunch {
         memset(&smap, 0, sizeof(smap));
         memset(&smap_nyq, 0, sizeof(smap_nyq));
         const bool land = MODE >= 2 && K::P1_ITERS == 1 && a.vec16 && !env_int("VEILS_WIDE_NO_TMA", 0) &&
-                          tma::make_land_map(&smap, S, a.P, a.ldp, a.F, prm->batch, K::L1, K::R1, K::L1, K::R1) &&
-                          tma::make_land_map(&smap_nyq, S, a.P, a.ldp, a.F, prm->batch, K::L1, K::R1, 1, 1);
+                          tma::make_land_map(&smap, S, a.P, a.ldp, a.F, prm->batch, K::LAND_ROWS) &&
+                          tma::make_land_map(&smap_nyq, S, a.P, a.ldp, a.F, prm->batch, 1);
         using KernT = void (*)(const WInvArgs, const int64_t, const CUtensorMap, const CUtensorMap);
         KernT kern = wide_inv_kernel<LOGMC, TF, MODE, false>;
         if (MODE >= 2 && land) kern = wide_inv_kernel<LOGMC, TF, (MODE >= 2 ? MODE : 2), true>;
@@ -28,9 +28,9 @@ struct InvLaunch {
         if (e != cudaSuccess) return e;
         // streaming overlap-add: chunks of `ct` tiles; the first tile of a chunk re-computes `halo` slices
         const int64_t Q = a.qh1 - a.qh0 + 1;
-        int ct = (50 * a.halo + TF - 1) / TF;              // halo re-computation <= ~2 % of a chunk
+        int ct = (50 * 4 + TF - 1) / TF;                   // halo re-computation <= ~2 % of a chunk
         if (ct > 64) ct = 64;
-        auto cps = [&](int c) { const int64_t lc = (int64_t)TF * c - a.halo; return (Q + lc - 1) / lc; };
+        auto cps = [&](int c) { const int64_t lc = (int64_t)TF * c - 4; return (Q + lc - 1) / lc; };
         while (ct > 2 && prm->batch * cps(ct) < 4 * (int64_t)cap) --ct;   // enough chunks to balance the CTAs
         a.chunk_tiles = ct;
         a.cps = cps(ct);
@@ -58,8 +58,6 @@ struct InvLaunch {
         a.prefetch = env_int("VEILS_WIDE_PREFETCH", 1);
         a.qh0 = fdiv64(p.k0 + K::MID, K::H);
         a.qh1 = fdiv64(p.k1 - 1 + K::MID, K::H);
-        // the first column of every tile is even: the slice pairs of a lane load as one 16-byte access
-        a.halo = 3 + (int)((a.qh0 - 3 - p.p_min) & 1);
         a.chunk_tiles = 0; a.cps = 0;
         switch (p.mode) {
             case 0: return go<LOGMC, TF, 0>(a);

@@ -56,7 +56,7 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
     WFwdCtx c;
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
-    c.xin = c.work + (K::WORK_FLOATS + 32);
+    c.xin = c.work + (K::WORK_FLOATS + 64);
     {
         fl2 *tab = reinterpret_cast<fl2 *>(c.xin + K::XIN_FLOATS);
         copy_table(tab, args.tab, TAB_ENTRIES(K::M), tid, K::NT);
@@ -101,34 +101,29 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
 //      it while the overlap-add and the output of the current tile run; pass 1 then reads shared
 //      memory.  Otherwise pass 1 loads S straight from global memory.
 struct WTile {
-    int64_t ch, b, qa;
-    int t;
+    int64_t ch, b, qa, kend;
+    int t, halo;
     bool valid;
 };
-template <int TF>
-__device__ __forceinline__ WTile wide_first_tile(const WInvArgs &a, int64_t total, int64_t lc) {
+template <int TF, int H, int MID>
+__device__ __forceinline__ WTile wide_tile_of_chunk(const WInvArgs &a, int64_t ch, int64_t total) {
     WTile w;
-    w.ch = blockIdx.x;
+    w.ch = ch;
     w.t = 0;
-    w.valid = w.ch < total;
-    w.b = w.valid ? w.ch / a.cps : 0;
-    w.qa = a.qh0 + (w.ch - w.b * a.cps) * lc - a.halo;
+    w.valid = ch < total;
+    const WChunk c = wide_chunk(a, w.valid ? ch : 0, TF, H, MID);
+    w.b = c.b; w.qa = c.qa0; w.kend = c.kend; w.halo = c.halo;
     return w;
 }
-template <int TF>
-__device__ __forceinline__ WTile wide_next_tile(const WInvArgs &a, const WTile &c, int64_t total, int64_t lc) {
-    WTile w = c;
+template <int TF, int H, int MID>
+__device__ __forceinline__ WTile wide_next_tile(const WInvArgs &a, const WTile &c, int64_t total) {
     if (c.t + 1 < a.chunk_tiles && c.qa + TF <= a.qh1) {
+        WTile w = c;
         w.t = c.t + 1;
         w.qa = c.qa + TF;
         return w;
     }
-    w.ch = c.ch + gridDim.x;
-    w.t = 0;
-    w.valid = w.ch < total;
-    w.b = w.valid ? w.ch / a.cps : 0;
-    w.qa = a.qh0 + (w.ch - w.b * a.cps) * lc - a.halo;
-    return w;
+    return wide_tile_of_chunk<TF, H, MID>(a, c.ch + gridDim.x, total);
 }
 
 template <int LOGMC, int TF, int MODE, bool LAND>
@@ -141,7 +136,7 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
     WInvCtx c;
     c.a = args;
     c.work = reinterpret_cast<float *>(smem);
-    c.acc = c.work + (K::WORK_FLOATS + 32);
+    c.acc = c.work + (K::WORK_FLOATS + 64);
     fl2 *tab = reinterpret_cast<fl2 *>(c.acc + K::XIN_FLOATS);
     copy_table(tab, args.tab, TAB_ENTRIES(K::M), tid, K::NT);
     c.dtab = tab + TAB_XTAB(K::M); c.tw1 = tab + TAB_TW1(K::M); c.tw2 = tab + TAB_TW2(K::M); c.twp = tab + TAB_TWP(K::M);
@@ -151,7 +146,6 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
         tma::fence_mbar_init();
     }
     __syncthreads();
-    const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;      // owned slices per chunk
     auto land = [&](const WTile &w) {
         if (tid != 0) return;
         tma::fence_async_smem();               // earlier generic-proxy accesses to the buffer are ordered first
@@ -160,17 +154,21 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
         tma::mbar_expect_tx(land_bar, K::LAND_BYTES);
 #pragma unroll
         for (int h = 0; h < K::NH; ++h) {
-            tma::load_4d(&smap, wbase + 4u * h * K::LAND_BLOCK, land_bar, col0 + 8 * h, 0, 0, (int)w.b);
-            tma::load_4d(&smap_nyq, wbase + 4u * (K::NH * K::LAND_BLOCK + 16 * h), land_bar, col0 + 8 * h, 0, K::R1, (int)w.b);
+#pragma unroll
+            for (int r = 0; r < K::MC; r += K::LAND_ROWS)
+                tma::load_3d(&smap, wbase + 4u * (h * K::LAND_BLOCK + 16 * r), land_bar, col0 + 8 * h, r, (int)w.b);
+            tma::load_3d(&smap_nyq, wbase + 4u * (K::NH * K::LAND_BLOCK + K::NYQ_STRIDE * h), land_bar, col0 + 8 * h, K::MC, (int)w.b);
         }
     };
-    WTile cur = wide_first_tile<TF>(args, total, lc);
+    WTile cur = wide_tile_of_chunk<TF, K::H, K::MID>(args, blockIdx.x, total);
     unsigned phase = 0;
     if (LAND && cur.valid) land(cur);
     while (cur.valid) {
-        const WTile nxt = wide_next_tile<TF>(args, cur, total, lc);
+        const WTile nxt = wide_next_tile<TF, K::H, K::MID>(args, cur, total);
         c.b = cur.b;
         c.qa = cur.qa;
+        c.kend = cur.kend;
+        c.halo = cur.halo;
         c.first = cur.t == 0;
         c.more = (nxt.valid && nxt.ch == cur.ch) ? 1 : 0;
         if (LAND) {
