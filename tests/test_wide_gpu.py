@@ -22,7 +22,8 @@ def hann(m):
 def test_wide_matches_oracle(M, mode):
     rng = np.random.default_rng(M + len(mode))
     st = StandaloneSTFT(hann(M), M // 4, 16000.0, fft_mode=mode, precision="f32")
-    assert st.kernel_name() == "pow2_wide" and st.kernel_name(True) == "pow2_wide"
+    assert st.kernel_name() == "pow2_wide"
+    assert st.kernel_name(True) == ("pow2_wide" if mode.startswith("onesided") else "pow2_packed")
     o = OracleSTFT(hann(M), M // 4, 16000.0, fft_mode=mode)
     n = 37 * (M // 4) + 123
     x = rng.uniform(-1, 1, (3, n)).astype(np.float32)
@@ -114,6 +115,22 @@ def test_wide_sharded_inverse_is_bit_identical():
             a = s.p_a - st.p_min - s.halo_cols
             parts.append(st.istft(np.ascontiguousarray(S[:, a:s.p_b - st.p_min]), s.k0_local, s.k1_local))
         assert np.array_equal(np.concatenate(parts), full)
+
+
+@pytest.mark.parametrize("mode", ["twosided", "centered"])
+def test_wide_inverse_two_sided_forced(monkeypatch, mode):
+    """the wide inverse of the two-sided layouts (direct loads) is kept correct although the dispatcher
+    prefers the packed family there"""
+    monkeypatch.setenv("VEILS_WIDE_INV_ALL", "1")
+    rng = np.random.default_rng(10)
+    M = 1024
+    st = StandaloneSTFT(hann(M), M // 4, 16000.0, fft_mode=mode, precision="f32")
+    assert st.kernel_name(True) == "pow2_wide"
+    o = OracleSTFT(hann(M), M // 4, 16000.0, fft_mode=mode)
+    x = rng.uniform(-1, 1, (2, 61 * 256 + 9))
+    S = np.stack([o.stft(r) for r in x]).astype(np.complex64)
+    y = st.istft(S)
+    assert rel_err(y, np.stack([o.istft(s.astype(np.complex128)) for s in S])) <= 1e-5
 
 
 def test_wide_tf8_variant_for_2048(monkeypatch):

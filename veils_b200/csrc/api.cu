@@ -181,7 +181,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
             e = cudaMalloc(&itab, it.size());
             if (e == cudaSuccess) e = cudaMemcpy(itab, it.data(), it.size(), cudaMemcpyHostToDevice);
         }
-        if (e == cudaSuccess && pl.wide) {
+        if (e == cudaSuccess && pl.wide_inv) {
             std::vector<double> tw((size_t)wide_table_floats(pl.M));
             wide_table_fill_host(pl.M, true, pl.dual.data(), sc, tw.data());
             e = upload_as<float>(tw, (void **)&wide_inv);
@@ -246,6 +246,9 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         // mfft 1024 / 2048 / 4096 with the default geometry: the wide family (conflict-free swizzled tiles)
         pl.wide = !force_generic && pl.precision == F32 && getenv("VEILS_NO_WIDE") == nullptr &&
                   wide_supported(pl.M, pl.N, pl.H, pl.ps);
+        // two-sided inverse: two rows per bin, no tensor-map landing yet -> the packed family is faster there
+        // (measured c4: 49 % vs 27 % of the roofline); VEILS_WIDE_INV_ALL=1 forces the wide kernels
+        pl.wide_inv = pl.wide && (pl.mode >= ONESIDED || !pl.pk_inv || getenv("VEILS_WIDE_INV_ALL") != nullptr);
     }
     *out = p;
     return VEILS_OK;
@@ -584,7 +587,7 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.wide ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, st)
+        ce = pl.wide_inv ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, st)
              : pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
              : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
                            : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
@@ -801,7 +804,7 @@ int32_t veils_stream_sync(void *stream) {
 
 uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(); }
 const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse) {
-    if (p->pl.wide) return "pow2_wide";
+    if (inverse ? p->pl.wide_inv : p->pl.wide) return "pow2_wide";
     if (inverse ? p->pl.pk_inv : p->pl.pk_fwd) return "pow2_packed";
     return (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) ? "pow2_tile" : "dft_generic";
 }

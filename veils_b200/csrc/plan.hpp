@@ -51,7 +51,8 @@ struct Plan {
     bool pow2_inv = false;
     bool pk_fwd = false;      // packed f32 family (preferred over pow2 when available)
     bool pk_inv = false;
-    bool wide = false;        // wide f32 family (mfft 1024 / 2048 / 4096, default geometry): both directions
+    bool wide = false;        // wide f32 family (mfft 1024 / 2048 / 4096, default geometry): forward
+    bool wide_inv = false;    // ... and inverse (one-sided layouts; two-sided ones stay with the packed family)
 };
 
 // Each returns "" on success or the reference's error text.

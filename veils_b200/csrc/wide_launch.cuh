@@ -160,6 +160,17 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
             tma::load_3d(&smap_nyq, wbase + 4u * (K::NH * K::LAND_BLOCK + K::NYQ_STRIDE * h), land_bar, col0 + 8 * h, K::MC, (int)w.b);
         }
     };
+    // the tile after the next one is pulled into L2 while the current one is transformed
+    auto prefetch = [&](const WTile &w) {
+        if (tid != 32) return;
+        const int col0 = (int)(w.qa - args.p_min);
+#pragma unroll
+        for (int h = 0; h < K::NH; ++h) {
+#pragma unroll
+            for (int r = 0; r < K::MC; r += K::LAND_ROWS) tma::prefetch_l2_3d(&smap, col0 + 8 * h, r, (int)w.b);
+            tma::prefetch_l2_3d(&smap_nyq, col0 + 8 * h, K::MC, (int)w.b);
+        }
+    };
     WTile cur = wide_tile_of_chunk<TF, K::H, K::MID>(args, blockIdx.x, total);
     unsigned phase = 0;
     if (LAND && cur.valid) land(cur);
@@ -172,6 +183,7 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
         c.first = cur.t == 0;
         c.more = (nxt.valid && nxt.ch == cur.ch) ? 1 : 0;
         if (LAND) {
+            if (args.prefetch && nxt.valid) prefetch(nxt);
             tma::mbar_wait(land_bar, phase);
             phase ^= 1;
 #pragma unroll 1
