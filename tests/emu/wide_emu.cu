@@ -128,6 +128,7 @@ struct EmuFwd {
         const int esz = spectrogram ? 4 : 8;
         c.a.vec16 = ((ldp * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         c.a.fac2x = (float)fac2x;
+        c.a.no_bulk = 1;
         std::vector<fl4> smem((wide_work_floats<LOGMC, TF>() + K::XIN_FLOATS) / 4 + 4);
         c.work = (float *)smem.data();
         c.xin = c.work + wide_work_floats<LOGMC, TF>();

@@ -133,8 +133,8 @@ def test_wide_inverse_two_sided_forced(monkeypatch, mode):
     assert rel_err(y, np.stack([o.istft(s.astype(np.complex128)) for s in S])) <= 1e-5
 
 
-def test_wide_tf8_variant_for_2048(monkeypatch):
-    monkeypatch.setenv("VEILS_WIDE_TF", "8")
+def test_wide_tf16_variant_for_2048(monkeypatch):
+    monkeypatch.setenv("VEILS_WIDE_TF", "16")
     rng = np.random.default_rng(9)
     st = StandaloneSTFT(hann(2048), 512, 16000.0, precision="f32")
     o = OracleSTFT(hann(2048), 512, 16000.0)

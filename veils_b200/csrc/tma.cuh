@@ -136,6 +136,11 @@ __device__ __forceinline__ void store_4d(const CUtensorMap *m, unsigned src, int
 __device__ __forceinline__ void store_bulk(void *dst, unsigned src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
+// global -> shared, 1-D: `bytes` (multiple of 16), 16-byte aligned addresses; completion on an mbarrier
+__device__ __forceinline__ void load_bulk(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all bulk stores of this thread have finished READING shared memory
 __device__ __forceinline__ void wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

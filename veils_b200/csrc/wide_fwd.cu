@@ -37,6 +37,7 @@ struct FwdLaunch {
         const int esz = p.spectrogram ? 4 : 8;
         a.vec16 = ((p.ldp * esz) % 16 == 0 && ((uintptr_t)out % 16) == 0) ? 1 : 0;
         a.fac2x = p.mode == 3 ? (float)p.fac2x : 1.f;
+        a.no_bulk = env_int("VEILS_WIDE_NO_BULK", 0);
         (void)sizeof(K);
         if (p.spectrogram) {
             switch (p.mode) {

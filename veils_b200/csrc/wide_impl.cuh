@@ -189,6 +189,7 @@ struct WFwdArgs {
     int mode;                // 0 twosided, 1 centered, 2 onesided, 3 onesided2X
     int spectrogram;
     int vec16;               // S base and row pitch allow 16-byte stores
+    int no_bulk;             // debug: stage every tile through cp.async
     float fac2x;
 };
 struct WFwdCtx {
@@ -279,51 +280,53 @@ struct WFwd : WGeo<LOGMC, TF_> {
         int64_t rb;          // row pitch in bytes
         bool live0, live1, vec;
     };
-    template <bool SPEC>
-    VHD static void put(const Out &o, int64_t row, float r0, float i0, float r1, float i1) {
-        char *q = o.base + row * o.rb;
+    // FULL: both slices of the lane are inside [0, P) (and, adjacent pairing, the pair is one aligned
+    // 16-byte store): no predication.  q = pointer of (row, column of slice h = 0).
+    template <bool SPEC, bool FULL>
+    VHD static void put(const Out &o, char *q, float r0, float i0, float r1, float i1) {
         if (SPEC) {
             const float v0 = r0 * r0 + i0 * i0, v1 = r1 * r1 + i1 * i1;   // scipy _short_time_fft.py:1398-1400
-            if (ADJ && o.vec && o.live1) {
+            if (ADJ && FULL) {
                 fl2 t; t.x = v0; t.y = v1;
                 *reinterpret_cast<fl2 *>(q) = t;
             } else {
-                if (o.live0) *reinterpret_cast<float *>(q) = v0;
-                if (o.live1) *reinterpret_cast<float *>(q + (ADJ ? 4 : 4 * LN)) = v1;
+                if (FULL || o.live0) *reinterpret_cast<float *>(q) = v0;
+                if (FULL || o.live1) *reinterpret_cast<float *>(q + (ADJ ? 4 : 4 * LN)) = v1;
             }
         } else {
-            if (ADJ && o.vec && o.live1) {
+            if (ADJ && FULL) {
                 fl4 t; t.x = r0; t.y = i0; t.z = r1; t.w = i1;
                 *reinterpret_cast<fl4 *>(q) = t;
             } else {
-                if (o.live0) { fl2 t; t.x = r0; t.y = i0; *reinterpret_cast<fl2 *>(q) = t; }
-                if (o.live1) { fl2 t; t.x = r1; t.y = i1; *reinterpret_cast<fl2 *>(q + (ADJ ? 8 : 8 * LN)) = t; }
+                if (FULL || o.live0) { fl2 t; t.x = r0; t.y = i0; *reinterpret_cast<fl2 *>(q) = t; }
+                if (FULL || o.live1) { fl2 t; t.x = r1; t.y = i1; *reinterpret_cast<fl2 *>(q + (ADJ ? 8 : 8 * LN)) = t; }
             }
         }
     }
-    // mode epilogue of one-sided bin k (src/lib.rs:354-408)
-    template <int MODE, bool SPEC>
-    VHD static void emit(const WFwdArgs &p, const Out &o, int k, float r0, float i0, float r1, float i1) {
+    // mode epilogue of one-sided bin k (src/lib.rs:354-408); q = pointer of row k (one-sided layouts)
+    template <int MODE, bool SPEC, bool FULL>
+    VHD static void emit(const WFwdArgs &p, const Out &o, int k, char *q, float r0, float i0, float r1, float i1) {
         const bool edge = k == 0 || k == MC;
         if (edge) { i0 = 0.f; i1 = 0.f; }                                  // :378-384
         if (MODE >= 2) {
             if (MODE == 3 && !edge) { r0 *= p.fac2x; i0 *= p.fac2x; r1 *= p.fac2x; i1 *= p.fac2x; }   // :397-403
-            put<SPEC>(o, k, r0, i0, r1, i1);
+            put<SPEC, FULL>(o, q, r0, i0, r1, i1);
             return;
         }
         const int sh = MODE == 1 ? MC : 0;                                  // fftshift :360-366
-        put<SPEC>(o, (k + sh) & (M - 1), r0, i0, r1, i1);
-        if (!edge) put<SPEC>(o, (M - k + sh) & (M - 1), r0, -i0, r1, -i1);
+        put<SPEC, FULL>(o, o.base + (int64_t)((k + sh) & (M - 1)) * o.rb, r0, i0, r1, i1);
+        if (!edge) put<SPEC, FULL>(o, o.base + (int64_t)((M - k + sh) & (M - 1)) * o.rb, r0, -i0, r1, -i1);
     }
-    // A = Z[k] / 2, B = Z[Mc - k] / 2 of both slices, t = W_M^k:  X[k] and (both) X[Mc - k]
-    template <int MODE, bool SPEC>
-    VHD static void split(const WFwdArgs &p, const Out &o, int k, fl2 t, C2 A, C2 B, bool both) {
+    // A = Z[k] / 2, B = Z[Mc - k] / 2 of both slices, t = W_M^k:  X[k] -> row pointer qk and (both)
+    // X[Mc - k] -> qm
+    template <int MODE, bool SPEC, bool FULL>
+    VHD static void split(const WFwdArgs &p, const Out &o, int k, char *qk, char *qm, fl2 t, C2 A, C2 B, bool both) {
         const f2 Ex = A.x + B.x, Oy = A.y + B.y, ey = A.y - B.y, ox = A.x - B.x;
         const f2 P = vfma(bc(t.y), ox, bc(t.x) * Oy);                       // wi ox + wr Oy
         const f2 Q = vfma(bc(t.y), Oy, bc(-t.x) * ox);                      // wi Oy - wr ox
         // the last adds are scalar: they place (re, im) of each slice in store order for free
-        emit<MODE, SPEC>(p, o, k, lo(Ex) + lo(P), lo(ey) + lo(Q), hi(Ex) + hi(P), hi(ey) + hi(Q));
-        if (both) emit<MODE, SPEC>(p, o, MC - k, lo(Ex) - lo(P), lo(Q) - lo(ey), hi(Ex) - hi(P), hi(Q) - hi(ey));
+        emit<MODE, SPEC, FULL>(p, o, k, qk, lo(Ex) + lo(P), lo(ey) + lo(Q), hi(Ex) + hi(P), hi(ey) + hi(Q));
+        if (both) emit<MODE, SPEC, FULL>(p, o, MC - k, qm, lo(Ex) - lo(P), lo(Q) - lo(ey), hi(Ex) - hi(P), hi(Q) - hi(ey));
     }
 
     // ---- pass 3: warp unit = (c2 < R2/2, run of SUBW consecutive cb): the thread holds last-pass group
@@ -333,7 +336,7 @@ struct WFwd : WGeo<LOGMC, TF_> {
     template <int MODE, bool SPEC>
     VHD static void pass3_t(const WFwdCtx &c, int tid) {
         const WFwdArgs &p = c.a;
-        const int l = tid % LN, sub = tid / LN, warp = sub / SUBW, sw = sub % SUBW;
+        const int l = tid % LN;
         Out o;
         {
             const int64_t col0 = c.pt * TF + GEO::slice_of(l, 0), col1 = c.pt * TF + GEO::slice_of(l, 1);
@@ -344,6 +347,13 @@ struct WFwd : WGeo<LOGMC, TF_> {
             o.rb = p.ldp * esz;
             o.base = reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + col0) * esz;
         }
+        if (o.live0 && o.live1 && (!ADJ || o.vec)) pass3_f<MODE, SPEC, true>(c, tid, o);
+        else pass3_f<MODE, SPEC, false>(c, tid, o);
+    }
+    template <int MODE, bool SPEC, bool FULL>
+    VHD static void pass3_f(const WFwdCtx &c, int tid, const Out &o) {
+        const WFwdArgs &p = c.a;
+        const int l = tid % LN, sub = tid / LN, warp = sub / SUBW, sw = sub % SUBW;
 #pragma unroll 1
         for (int unit = warp; unit < NU3; unit += NWARP) {
             const int c2 = unit / CBR, cb = (unit - c2 * CBR) * SUBW + sw;
@@ -356,23 +366,30 @@ struct WFwd : WGeo<LOGMC, TF_> {
                 Dft<RL, false, f2>::run(uA);
                 Dft<RL, false, f2>::run(uB);
                 const fl2 *tq = c.twp + gA;
+                char *qk = o.base + gA * o.rb, *qm = o.base + (MC - gA) * o.rb;     // rows k and Mc - k
+                const int64_t st = G * o.rb;
 #pragma unroll
-                for (int d = 0; d < RL; ++d)
-                    split<MODE, SPEC>(p, o, gA + G * d, ldg2(tq + G * d), uA[d], uB[RL - 1 - d], true);
+                for (int d = 0; d < RL; ++d) {
+                    split<MODE, SPEC, FULL>(p, o, gA + G * d, qk, qm, ldg2(tq + G * d), uA[d], uB[RL - 1 - d], true);
+                    qk += st;
+                    qm -= st;
+                }
             } else {
                 // self-mirrored groups 0 (bins G d <-> G (RL - d), DC <-> Nyquist) and G/2
                 GEO::template ld_grp<RL, L1, L2>(c.work, 0, 0, l, uA);
                 GEO::template ld_grp<RL, L1, L2>(c.work, 0, R2 / 2, l, uB);
                 Dft<RL, false, f2>::run(uA);
                 Dft<RL, false, f2>::run(uB);
-                split<MODE, SPEC>(p, o, 0, ldg2(c.twp), uA[0], uA[0], true);                 // X[0], X[Mc]
+                auto row = [&](int k) { return o.base + (int64_t)k * o.rb; };
+                split<MODE, SPEC, FULL>(p, o, 0, row(0), row(MC), ldg2(c.twp), uA[0], uA[0], true);      // X[0], X[Mc]
 #pragma unroll
                 for (int d = 1; d < RL / 2; ++d)
-                    split<MODE, SPEC>(p, o, G * d, ldg2(c.twp + G * d), uA[d], uA[RL - d], true);
-                split<MODE, SPEC>(p, o, MC / 2, ldg2(c.twp + MC / 2), uA[RL / 2], uA[RL / 2], false);
+                    split<MODE, SPEC, FULL>(p, o, G * d, row(G * d), row(MC - G * d), ldg2(c.twp + G * d), uA[d], uA[RL - d], true);
+                split<MODE, SPEC, FULL>(p, o, MC / 2, row(MC / 2), row(MC / 2), ldg2(c.twp + MC / 2), uA[RL / 2], uA[RL / 2], false);
 #pragma unroll
                 for (int d = 0; d < RL / 2; ++d)
-                    split<MODE, SPEC>(p, o, G / 2 + G * d, ldg2(c.twp + G / 2 + G * d), uB[d], uB[RL - 1 - d], true);
+                    split<MODE, SPEC, FULL>(p, o, G / 2 + G * d, row(G / 2 + G * d), row(MC - G / 2 - G * d),
+                                            ldg2(c.twp + G / 2 + G * d), uB[d], uB[RL - 1 - d], true);
             }
         }
     }
@@ -815,7 +832,7 @@ struct WInv : WGeo<LOGMC, TF_> {
 struct WCfg { int logmc, tf; };
 inline bool wide_cfg_for(int64_t M, int tf_pref, WCfg *c) {
     if (M == 1024) { c->logmc = 9; c->tf = 16; return true; }
-    if (M == 2048) { c->logmc = 10; c->tf = tf_pref == 8 ? 8 : 16; return true; }
+    if (M == 2048) { c->logmc = 10; c->tf = tf_pref == 16 ? 16 : 8; return true; }   // 2 CTAs / SM: 52.7 vs 49.3 %
     if (M == 4096) { c->logmc = 11; c->tf = 8; return true; }
     return false;
 }

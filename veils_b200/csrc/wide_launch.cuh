@@ -62,16 +62,48 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
         copy_table(tab, args.tab, TAB_ENTRIES(K::M), tid, K::NT);
         c.wtab = tab + TAB_XTAB(K::M); c.tw1 = tab + TAB_TW1(K::M); c.tw2 = tab + TAB_TW2(K::M); c.twp = tab + TAB_TWP(K::M);
     }
+    // staging of a tile: interior tiles whose first sample is 16-byte aligned come in as ROWS bulk copies
+    // (one thread each, completion on an mbarrier); border / unaligned tiles through cp.async with zero fill
+    const unsigned fill_bar = tma::smem_u32(reinterpret_cast<fl2 *>(c.xin + K::XIN_FLOATS) + TAB_ENTRIES(K::M));
+    if (tid == 0) {
+        tma::mbar_init(fill_bar, 1);
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+    const bool x_al = ((((size_t)args.x) & 15) == 0) && !args.no_bulk;
+    auto stage = [&](int64_t b, int64_t pt) -> bool {
+        const int64_t s0 = (args.p0 + pt * TF) * (int64_t)K::H + args.k_offset - K::MID;
+        const bool bulk = x_al && s0 >= 0 && s0 + (int64_t)K::ROWS * K::H <= args.n && (((b * args.x_pitch + s0) & 3) == 0);
+        if (bulk) {
+            if (tid < K::ROWS) {
+                tma::fence_async_smem();
+                if (tid == 0) tma::mbar_expect_tx(fill_bar, 4u * K::ROWS * K::H);
+                __syncwarp((1u << K::ROWS) - 1u);
+                tma::load_bulk(tma::smem_u32(c.xin + tid * K::HS), args.x + b * args.x_pitch + s0 + (int64_t)tid * K::H,
+                               4u * K::H, fill_bar);
+            }
+        } else {
+            WFwdCtx cn = c;
+            cn.b = b;
+            cn.pt = pt;
+            K::fill(cn, tid);
+            cp_async_commit();
+        }
+        return bulk;
+    };
     int64_t w = blockIdx.x;
     if (w >= total) return;
     int64_t cb = w / args.ptiles, cpt = w - cb * args.ptiles;
     const int64_t gb = gridDim.x / args.ptiles, gr = gridDim.x - gb * args.ptiles;
-    c.b = cb;
-    c.pt = cpt;
-    K::fill(c, tid);
-    cp_async_commit();
+    bool bulk_cur = stage(cb, cpt);
+    unsigned phase = 0;
     for (; w < total; w += gridDim.x) {
-        cp_async_wait_all();
+        if (bulk_cur) {
+            tma::mbar_wait(fill_bar, phase);
+            phase ^= 1;
+        } else {
+            cp_async_wait_all();
+        }
         __syncthreads();                       // the tile is staged; pass 3 of the previous tile has read `work`
         c.b = cb;
         c.pt = cpt;
@@ -79,13 +111,7 @@ wide_fwd_kernel(const __grid_constant__ WFwdArgs args, const int64_t total) {
         __syncthreads();
         int64_t nb = cb + gb, npt = cpt + gr;
         if (npt >= args.ptiles) { npt -= args.ptiles; ++nb; }
-        if (w + gridDim.x < total) {
-            WFwdCtx cn = c;
-            cn.b = nb;
-            cn.pt = npt;
-            K::fill(cn, tid);
-            cp_async_commit();
-        }
+        if (w + gridDim.x < total) bulk_cur = stage(nb, npt);
         K::pass2(c, tid);
         __syncthreads();
         K::template pass3_t<MODE, SPEC>(c, tid);
