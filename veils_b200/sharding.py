@@ -114,7 +114,7 @@ def inverse_halo_cols(m_num: int, hop: int, p_min: int) -> int:
 
 
 def inverse_shard(p_total: int, m_num: int, hop: int, p_min: int, rank: int, world: int,
-                  k0: int = 0, k1=None) -> InverseShard:
+                  k0: int = 0, k1=None, halo_align: int = 1) -> InverseShard:
     """Output range and halo of `rank` for the inverse transform of S[F, p_total] sharded by slices.
 
     Slice q adds to samples [q*hop - mid, q*hop - mid + m_num) (src/lib.rs:876-910).  A sample's
@@ -127,13 +127,15 @@ def inverse_shard(p_total: int, m_num: int, hop: int, p_min: int, rank: int, wor
     The halo is widened where needed so that the local k0 is never negative: for k0 < 0 the
     reference starts at q0 = floor(k0/hop) WITHOUT adding p_min (src/lib.rs:842-846), which on a
     local block would skip the first halo columns (hops that do not divide m_num/2, e.g. 1024/100).
-    The extra columns lie below the local q0 and contribute nothing."""
+    The extra columns lie below the local q0 and contribute nothing.  `halo_align` rounds the halo up
+    to a multiple (2 keeps the [halo | own] block of a pitch-aligned S buffer 16-byte aligned)."""
     mid = m_num // 2
     a, b = row_range(p_total, rank, world)
     p_a, p_b = p_min + a, p_min + b
     k_max = (p_min + p_total - 1) * hop + m_num - mid
     k1 = k_max if k1 is None else k1
-    halo = 0 if rank == 0 else min(inverse_halo_cols(m_num, hop, p_min), a)
+    need = -(-inverse_halo_cols(m_num, hop, p_min) // halo_align) * halo_align
+    halo = 0 if rank == 0 else min(need, a)
     k_a = k0 if rank == 0 else max(k0, p_a * hop - mid)
     k_b = k1 if rank == world - 1 else min(k1, p_b * hop - mid)
     shift = (p_a - halo - p_min) * hop
