@@ -558,13 +558,15 @@ def side_c4(e, args):
     me = shards[e.rank]
     halo_next = shards[e.rank + 1].halo_cols if e.rank + 1 < e.world else 0
     P_r = fs_.p_b - fs_.p_a
-    ldp = -(-(me.halo_cols + P_r) // 16) * 16
+    off = 16 if me.halo_cols else 0       # own columns start on a 128-byte line; the halo block sits right before them
+    ldp = -(-(off + P_r) // 16) * 16
     free, _ = torch.cuda.mem_get_info()
     need = (fs_.s_b - fs_.s_a) * 4 + F * ldp * 8 + (me.k_b - me.k_a) * 4 + (3 << 30)
     if need > free:
         return {"skipped": f"needs {need / 2**30:.0f} GiB of device memory, {free / 2**30:.0f} free"}
     x = hash_noise_torch(torch, e.dev, fs_.s_a, fs_.s_b)                 # this rank's samples + halo, generated in place
-    S = torch.empty((F, ldp), dtype=torch.complex64, device=e.dev)       # [halo | own] columns
+    Sbuf = torch.empty((F, ldp), dtype=torch.complex64, device=e.dev)
+    S = Sbuf[:, off - me.halo_cols:]                                     # [halo | own] columns
     y = torch.empty((me.k_b - me.k_a,), dtype=torch.float32, device=e.dev)
     stream = torch.cuda.current_stream(e.dev).cuda_stream
     n_loc = fs_.s_b - fs_.s_a
