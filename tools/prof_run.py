@@ -16,9 +16,18 @@ ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--config", default="c2")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--ldp-align", type=int, default=1)
+ap.add_argument("--m", type=int, default=0, help="override m_num = mfft (hop = m / 4)")
+ap.add_argument("--n", type=int, default=0)
+ap.add_argument("--mode", default="")
 args = ap.parse_args()
 cfg = dict(bench.CONFIGS[args.config])
 cfg["batch"] = args.batch
+if args.m:
+    cfg["m"], cfg["hop"] = args.m, args.m // 4
+if args.n:
+    cfg["n"] = args.n
+if args.mode:
+    cfg["mode"] = args.mode
 dev = torch.device("cuda", 0)
 st = StandaloneSTFT(bench.make_window(cfg), cfg["hop"], cfg["fs"], fft_mode=cfg["mode"], precision=cfg["prec"])
 x = bench.synth_device(cfg, torch, dev, 1)
