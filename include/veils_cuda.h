@@ -131,6 +131,14 @@ int32_t veils_stft_dev(veils_plan *p, const void *x, int64_t n, int64_t batch, i
 int32_t veils_spectrogram_dev(veils_plan *p, const void *x, int64_t n, int64_t batch,
                               int64_t x_pitch, const int64_t *p0, const int64_t *p1,
                               int64_t k_offset, void *Sxx, int64_t ldp, void *stream);
+/* The same with the reference's NaN screen (src/lib.rs:696-698: "Complex-valued input not allowed for
+ * one-sided FFT modes"): *nan_flag -- device memory or page-locked host memory, zeroed by the caller --
+ * is set to 1 when a NaN sample went into a one-sided transform (a < 1 % pass over the DC row of S behind
+ * the transform; slices whose DC bin is not finite are re-read and tested exactly).  spectrogram != 0:
+ * Sxx is the real |X|^2 array.  The host-pointer entry points always screen and return the error. */
+int32_t veils_stft_dev_checked(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                               const int64_t *p0, const int64_t *p1, int64_t k_offset, void *S, int64_t ldp,
+                               void *stream, int32_t spectrogram, int32_t *nan_flag);
 /* istft (src/lib.rs:792-914): S[batch][f_pts][ldp] with P valid slices -> x_out[batch][k1-k0] */
 int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,
                         const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
@@ -161,6 +169,11 @@ int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t 
  * Sx <- Sx * conj(Sy), element-wise over [batch][f_pts][P] (row pitches ldx, ldy), after two stft calls. */
 int32_t veils_cross_multiply_dev(veils_plan *p, void *Sx, const void *Sy, int64_t P, int64_t batch,
                                  int64_t ldx, int64_t ldy, void *stream);
+/* Helpers for the twin's complex signals in the two-sided layouts (python/standalone_stft.py:349, 404, 424; the
+ * Rust crate is real-only): over batch * f_pts rows of P complex elements, op 1: A += i B -- stft(x) of a
+ * complex x is stft(Re x) + i stft(Im x); op 2: A = -i B -- Im(istft(S)) = istft_real(-i S). */
+int32_t veils_complex_op_dev(veils_plan *p, int32_t op, void *A, const void *B, int64_t P, int64_t batch, int64_t lda,
+                             int64_t ldb, void *stream);
 
 /* ---- compute: host pointers (drop-in for the Vec API; copies inside) ------------------- */
 /* Also performs the reference's NaN scan for one-sided modes (src/lib.rs:696-698).

@@ -56,6 +56,9 @@ PROTOTYPES = {
     "veils_stft_detrend_dev": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P, C.c_int64,
                                             C.c_char_p, C.c_char_p, _P, C.c_int64, _P, _P, C.c_int64, _P]),
     "veils_cross_multiply_dev": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "veils_complex_op_dev": (C.c_int32, [_P, C.c_int32, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
+    "veils_stft_dev_checked": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,
+                                            C.c_int64, _P, C.c_int64, _P, C.c_int32, _P]),
     "veils_stft_host": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,
                                      C.c_int64, _P]),
     "veils_spectrogram_host": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,

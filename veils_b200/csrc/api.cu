@@ -41,7 +41,7 @@ struct HostStage {
     size_t cap[4] = {0, 0, 0, 0};
     cudaStream_t st[2] = {nullptr, nullptr};
     std::mutex mu;                                         // host-pointer calls on one plan serialise
-    int *nan_flag = nullptr;                               // page-locked, written by nan_screen_kernel
+    int *nan_flag = nullptr;                               // page-locked, written by nan_dc_check_kernel
     cudaError_t reserve(int i, size_t bytes) {
         if (cap[i] >= bytes) return cudaSuccess;
         if (buf[i]) cudaFree(buf[i]);
@@ -433,6 +433,23 @@ int32_t veils_spectrogram_dev(veils_plan *p, const void *x, int64_t n, int64_t b
     return forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, Sxx, ldp, stream, 1);
 }
 
+static int32_t nan_check_launch(const Plan &pl, const void *x, int64_t n, int64_t batch, int64_t x_pitch, int64_t a,
+                                int64_t P, int64_t k_offset, const void *S, int64_t ldp, int spectrogram, int *flag,
+                                cudaStream_t st);
+// device-pointer flavour with the reference's NaN screen (src/lib.rs:696-698): *nan_flag (device memory or
+// page-locked host memory, zeroed by the caller) becomes 1 when a NaN sample went into a one-sided transform
+int32_t veils_stft_dev_checked(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
+                               const int64_t *p0, const int64_t *p1, int64_t k_offset, void *S, int64_t ldp,
+                               void *stream, int32_t spectrogram, int32_t *nan_flag) {
+    int32_t rc = forward_impl(p, x, n, batch, x_pitch, p0, p1, k_offset, S, ldp, stream, spectrogram ? 1 : 0);
+    if (rc != VEILS_OK || !nan_flag) return rc;
+    int64_t a, b;
+    std::string e = plan_p_range(p->pl, n, p0, p1, &a, &b);
+    if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
+    return nan_check_launch(p->pl, x, n, batch, x_pitch, a, b - a, k_offset, S, ldp, spectrogram ? 1 : 0, nan_flag,
+                            (cudaStream_t)stream);
+}
+
 static int padding_mode(const char *padding) {
     if (!padding || !strcmp(padding, "zeros")) return 0;
     if (!strcmp(padding, "edge")) return 1;
@@ -564,6 +581,21 @@ int32_t veils_cross_multiply_dev(veils_plan *p, void *Sx, const void *Sy, int64_
     return VEILS_OK;
 }
 
+int32_t veils_complex_op_dev(veils_plan *p, int32_t op, void *A, const void *B, int64_t P, int64_t batch, int64_t lda,
+                             int64_t ldb, void *stream) {
+    if (!p || !A || !B) return fail(VEILS_ERR_INVALID, "null argument");
+    if (op != 1 && op != 2) return fail(VEILS_ERR_INVALID, "op must be 1 (A += i B) or 2 (A = -i B)");
+    if (P < 0 || batch < 0 || lda < P || ldb < P) return fail(VEILS_ERR_INVALID, "lda, ldb must be >= P >= 0");
+    Plan &pl = p->pl;
+    int32_t rc = ensure_device(pl, false);
+    if (rc != VEILS_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = pl.precision == F32 ? complex_op<float>((float *)A, (const float *)B, batch * pl.F, P, lda, ldb, op, st)
+                                         : complex_op<double>((double *)A, (const double *)B, batch * pl.F, P, lda, ldb, op, st);
+    if (ce != cudaSuccess) return cuda_fail(ce, "complex op launch");
+    return VEILS_OK;
+}
+
 int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, int64_t ldp,
                         const int64_t *k0, const int64_t *k1, void *x_out, int64_t out_pitch,
                         void *stream) {
@@ -600,21 +632,56 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     return VEILS_OK;
 }
 
-// ---- host-pointer flavour ------------------------------------------------------------------
-// NaN screen of the uploaded signal (src/lib.rs:696-698 rejects NaN input in the one-sided modes):
-// done on the device copy, where reading x again costs microseconds, instead of a host scan that
-// would cost as much as the PCIe transfer.  The flag lives in page-locked host memory.
+// ---- NaN screen (src/lib.rs:696-698 rejects NaN input in the one-sided modes) ----------------
+// A NaN sample makes EVERY bin of the slices it touches NaN, and bin 0 is a plain sum of the
+// windowed samples (no twiddle can hide it).  So the screen reads only the DC row of the finished
+// S -- 1 / f_pts of the output, < 1 % of the transform's traffic, any kernel family -- and where
+// that value is not finite (NaN or Inf input, or overflow) a thread re-reads the slice's samples and
+// tests them exactly for NaN.  The flag may live in device memory or in page-locked host memory.
 extern "C++" {
 template <typename T>
-__global__ void nan_screen_kernel(const T *__restrict__ x, size_t count, int *flag) {
-    bool bad = false;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
-        const T v = x[i];
-        bad |= (v != v);
+__global__ void nan_dc_check_kernel(const T *__restrict__ x, int64_t n, int64_t x_pitch, int64_t batch, int64_t p0,
+                                    int64_t P, int64_t H, int64_t N, int64_t mid, int64_t k_offset,
+                                    const T *__restrict__ S, int64_t row_elems, int64_t sig_elems, int esz_mul,
+                                    int *flag) {
+    const int64_t total = batch * P;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / P, p = i - b * P;
+        const T v = S[b * sig_elems + p * esz_mul];                  // Re(S[b][0][p]) (or |X|^2 of the spectrogram)
+        (void)row_elems;
+        if (v - v == (T)0) continue;                                 // finite: no NaN went into this slice
+        const int64_t s0 = (p0 + p) * H + k_offset - mid;
+        const T *xb = x + b * x_pitch;
+        bool bad = false;
+        for (int64_t j = 0; j < N; ++j) {
+            const int64_t s = s0 + j;
+            if (s >= 0 && s < n) { const T w = xb[s]; bad |= (w != w); }
+        }
+        if (bad) *flag = 1;
     }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) *flag = 1;
 }
 }  // extern "C++"
+// enqueue the screen behind a forward transform (one-sided modes only; no-op otherwise)
+static int32_t nan_check_launch(const Plan &pl, const void *x, int64_t n, int64_t batch, int64_t x_pitch, int64_t a,
+                                int64_t P, int64_t k_offset, const void *S, int64_t ldp, int spectrogram, int *flag,
+                                cudaStream_t st) {
+    if (pl.mode < ONESIDED || !flag || batch <= 0 || P <= 0) return VEILS_OK;
+    const int64_t total = batch * P;
+    const int grid = (int)std::min<int64_t>(148 * 8, (total + 255) / 256);
+    const int mul = spectrogram ? 1 : 2;
+    if (pl.precision == F32)
+        nan_dc_check_kernel<float><<<grid, 256, 0, st>>>((const float *)x, n, x_pitch, batch, a, P, pl.H, pl.N, pl.mid,
+                                                         k_offset, (const float *)S, ldp * mul, pl.F * ldp * mul, mul, flag);
+    else
+        nan_dc_check_kernel<double><<<grid, 256, 0, st>>>((const double *)x, n, x_pitch, batch, a, P, pl.H, pl.N, pl.mid,
+                                                          k_offset, (const double *)S, ldp * mul, pl.F * ldp * mul, mul, flag);
+    ++g_launch_count;
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) return cuda_fail(ce, "NaN screen launch");
+    return VEILS_OK;
+}
+
+// ---- host-pointer flavour ------------------------------------------------------------------
 static size_t esz(const Plan &pl) { return pl.precision == F32 ? 4 : 8; }
 // device row pitch of S in elements: 128-byte rows, so that the TMA paths of the kernels apply
 static int64_t host_ldp(int64_t P, size_t elem_bytes) {
@@ -675,14 +742,9 @@ static int32_t forward_host(veils_plan *p, const void *x, int64_t n, int64_t bat
         cudaError_t ce = cudaMemcpy2DAsync(dx, in_row, (const char *)x + (size_t)r0 * (size_t)x_pitch * es,
                                            (size_t)x_pitch * es, in_row, (size_t)nr, cudaMemcpyHostToDevice, st);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "H2D copy"); break; }
-        if (pl.mode >= ONESIDED) {
-            const size_t cnt = (size_t)nr * (size_t)n;
-            const int grid = (int)std::min<size_t>(148 * 8, (cnt + 255) / 256);
-            if (pl.precision == F32) nan_screen_kernel<float><<<grid, 256, 0, st>>>((const float *)dx, cnt, hs.nan_flag);
-            else nan_screen_kernel<double><<<grid, 256, 0, st>>>((const double *)dx, cnt, hs.nan_flag);
-            ++g_launch_count;
-        }
         rc = forward_impl(p, dx, n, nr, n, &a, &b, k_offset, ds, ldp, st, spectrogram);
+        if (rc != VEILS_OK) break;
+        rc = nan_check_launch(pl, dx, n, nr, n, a, P, k_offset, ds, ldp, spectrogram, hs.nan_flag, st);
         if (rc != VEILS_OK) break;
         ce = cudaMemcpy2DAsync((char *)out + (size_t)r0 * (size_t)pl.F * (size_t)P * oes, (size_t)P * oes, ds,
                                (size_t)ldp * oes, (size_t)P * oes, (size_t)(nr * pl.F), cudaMemcpyDeviceToHost, st);

@@ -78,7 +78,35 @@ __global__ void cross_kernel(T *__restrict__ Sx, const T *__restrict__ Sy, int64
     }
 }
 
+// op 1: A += i B (complex-input stft of a two-sided layout = stft(Re x) + i stft(Im x), the transform is linear);
+// op 2: A = -i B (Im(istft(S)) = Re(istft(-i S)): the imaginary part of the twin's complex istft)
+template <typename T>
+__global__ void complex_op_kernel(T *__restrict__ A, const T *__restrict__ B, int64_t rows, int64_t P, int64_t lda,
+                                  int64_t ldb, int op) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) {
+        T *a = A + 2 * (r * lda + p);
+        const T *b = B + 2 * (r * ldb + p);
+        const T br = b[0], bi = b[1];
+        if (op == 1) { a[0] -= bi; a[1] += br; }
+        else { a[0] = bi; a[1] = -br; }
+    }
+}
+
 }  // namespace
+
+template <typename T>
+cudaError_t complex_op(T *A, const T *B, int64_t rows, int64_t P, int64_t lda, int64_t ldb, int op, cudaStream_t st) {
+    if (rows <= 0 || P <= 0) return cudaSuccess;
+    const int threads = 128;
+    dim3 grid((unsigned)((P + threads - 1) / threads), (unsigned)(rows < 4096 ? rows : 4096));
+    complex_op_kernel<T><<<grid, threads, 0, st>>>(A, B, rows, P, lda, ldb, op);
+    ++g_launch_count;
+    return cudaGetLastError();
+}
+template cudaError_t complex_op<float>(float *, const float *, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
+template cudaError_t complex_op<double>(double *, const double *, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
 
 template <typename T>
 cudaError_t cross_multiply(T *Sx, const T *Sy, int64_t rows, int64_t P, int64_t ldx, int64_t ldy, cudaStream_t st) {

@@ -102,4 +102,9 @@ cudaError_t detrend_correct(const T *x, int64_t n, int64_t batch, int64_t x_pitc
 template <typename T>
 cudaError_t cross_multiply(T *Sx, const T *Sy, int64_t rows, int64_t P, int64_t ldx, int64_t ldy, cudaStream_t st);
 
+// A += i B (op 1) / A = -i B (op 2) over rows x P complex elements (complex input / complex istft of the
+// two-sided layouts, python/standalone_stft.py:349, 404, 424; detrend.cu)
+template <typename T>
+cudaError_t complex_op(T *A, const T *B, int64_t rows, int64_t P, int64_t lda, int64_t ldb, int op, cudaStream_t st);
+
 }  // namespace veils

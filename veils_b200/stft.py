@@ -40,8 +40,14 @@ def _dptr(a):
 class StandaloneSTFT:
     """Drop-in for veils::StandaloneSTFT backed by the sm_100a kernels."""
 
+    NAN_TEXT = "Complex-valued input not allowed for one-sided FFT modes"      # src/lib.rs:697
+
     def __init__(self, win, hop, fs, *, fft_mode="onesided", mfft=None, dual_win=None,
-                 scale_to=None, phase_shift=0, precision="f64", device=0):
+                 scale_to=None, phase_shift=0, precision="f64", device=0, nan_check="deferred"):
+        """phase_shift=None (scipy): no roll of the zero-padded slice, i.e. phase_shift = -m_num_mid.
+        nan_check (device tensors, one-sided modes; src/lib.rs:696-698): 'deferred' -- the screen runs behind
+        the transform and the error is raised by the next call on this object or by check_input();
+        'sync' -- stft() waits for it and raises like the reference; 'off'.  Host arrays always raise."""
         L = lib()
         win = np.ascontiguousarray(np.asarray(win, dtype=np.float64).ravel())
         dual = None if dual_win is None else np.ascontiguousarray(
@@ -61,7 +67,12 @@ class StandaloneSTFT:
         d.mfft = 0 if mfft is None else int(mfft)
         d.dual_win = None if dual is None else _dptr(dual)
         d.scale_to = None if scale_to is None else str(scale_to).encode()
-        d.phase_shift = 0 if phase_shift is None else int(phase_shift)
+        self._phase_none = phase_shift is None
+        d.phase_shift = -(win.size // 2) if phase_shift is None else int(phase_shift)
+        if nan_check not in ("deferred", "sync", "off"):
+            raise ValueError("nan_check must be 'deferred', 'sync' or 'off'")
+        self.nan_check = nan_check
+        self._nanflag = None
         d.precision = _lib.F32 if precision == "f32" else _lib.F64
         d.device = int(device)
         if mfft is not None and int(mfft) <= 0:
@@ -104,7 +115,7 @@ class StandaloneSTFT:
     m_num = property(lambda s: s._L.veils_m_num(s._h))
     m_num_mid = property(lambda s: s._L.veils_m_num_mid(s._h))
     f_pts = property(lambda s: s._L.veils_f_pts(s._h))
-    phase_shift = property(lambda s: s._L.veils_phase_shift(s._h))
+    phase_shift = property(lambda s: None if s._phase_none else s._L.veils_phase_shift(s._h))
     delta_t = property(lambda s: s._L.veils_delta_t(s._h))
     delta_f = property(lambda s: s._L.veils_delta_f(s._h))
     T = property(lambda s: 1.0 / s.fs)
@@ -215,9 +226,59 @@ class StandaloneSTFT:
 
     PADDINGS = ("zeros", "edge", "even", "odd")
 
+    @classmethod
+    def _is_complex(cls, x):
+        if cls._is_tensor(x):
+            return x.is_complex()
+        return np.iscomplexobj(x)
+
+    def _fwd_complex(self, x, p0, p1, k_offset, spectrogram, padding, detr):
+        """The twin accepts complex x in the two-sided layouts (python/standalone_stft.py:349; the Rust crate
+        is real-only).  The transform is linear: stft(x) = stft(Re x) + i stft(Im x) -- two real transforms
+        and one A += i B pass (veils_complex_op_dev)."""
+        if self.onesided_fft:
+            raise VeilsError(_lib.ERR_INVALID, f"Complex-valued `x` not allowed for fft_mode='{self.fft_mode}'! "
+                                               "Set fft_mode to 'twosided' or 'centered'.")
+        if spectrogram or detr is not None:
+            raise VeilsError(_lib.ERR_INVALID, "complex input: only stft() is supported")
+        import torch
+        tdt = torch.float32 if self.precision == "f32" else torch.float64
+        was_numpy = not self._is_tensor(x)
+        xt = torch.from_numpy(np.ascontiguousarray(x)).cuda(self.device) if was_numpy else x
+        Sr = self._fwd_tensor(xt.real.to(tdt).contiguous(), p0, p1, k_offset, False, padding)
+        Si = self._fwd_tensor(xt.imag.to(tdt).contiguous(), p0, p1, k_offset, False, padding)
+        S3, T3 = (Sr[None], Si[None]) if Sr.dim() == 2 else (Sr, Si)
+        batch, F, P = S3.shape
+        st = torch.cuda.current_stream(Sr.device).cuda_stream
+        _check(self._L.veils_complex_op_dev(self._h, 1, S3.data_ptr(), T3.data_ptr(), P, batch,
+                                            S3.stride(1) if F > 1 else P, T3.stride(1) if F > 1 else P, st))
+        return Sr.cpu().numpy() if was_numpy else Sr
+
+    # ---- NaN screen of device tensors (the flag lives in page-locked host memory the kernel writes to)
+    def _flag(self):
+        if self._nanflag is None:
+            import torch
+            self._nanflag = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        return self._nanflag
+
+    def _raise_if_nan(self):
+        if self._nanflag is not None and int(self._nanflag[0]) != 0:
+            self._nanflag[0] = 0
+            raise VeilsError(_lib.ERR_INVALID, self.NAN_TEXT)
+
+    def check_input(self):
+        """Waits for the transforms issued on this device and raises if a NaN went into a one-sided stft."""
+        if self._nanflag is not None:
+            import torch
+            torch.cuda.synchronize(self.device)
+        self._raise_if_nan()
+
     def _fwd(self, x, p0, p1, k_offset, spectrogram, padding="zeros", detr=None):
         if padding not in self.PADDINGS:
             raise VeilsError(_lib.ERR_INVALID, f"Parameter padding='{padding}' not in {list(self.PADDINGS)}!")
+        self._raise_if_nan()
+        if self._is_complex(x):
+            return self._fwd_complex(x, p0, p1, k_offset, spectrogram, padding, detr)
         if self._is_tensor(x):
             return self._fwd_tensor(x, p0, p1, k_offset, spectrogram, padding, detr)
         x = np.asarray(x)
@@ -290,9 +351,17 @@ class StandaloneSTFT:
                                                  out.data_ptr(), ldp, st, 1 if spectrogram else 0))
             out = out[:, :, :P]
             return out[0] if squeeze else out
-        fn = self._L.veils_spectrogram_dev if spectrogram else self._L.veils_stft_dev
-        _check(fn(self._h, x2.data_ptr(), n, batch, x2.stride(0) if batch > 1 else n, opt_i64(a),
-                  opt_i64(b), int(k_offset), out.data_ptr(), ldp, st))
+        if self.onesided_fft and self.nan_check != "off":
+            _check(self._L.veils_stft_dev_checked(self._h, x2.data_ptr(), n, batch, x2.stride(0) if batch > 1 else n,
+                                                  opt_i64(a), opt_i64(b), int(k_offset), out.data_ptr(), ldp, st,
+                                                  1 if spectrogram else 0, self._flag().data_ptr()))
+            if self.nan_check == "sync":
+                torch.cuda.current_stream(x.device).synchronize()
+                self._raise_if_nan()
+        else:
+            fn = self._L.veils_spectrogram_dev if spectrogram else self._L.veils_stft_dev
+            _check(fn(self._h, x2.data_ptr(), n, batch, x2.stride(0) if batch > 1 else n, opt_i64(a),
+                      opt_i64(b), int(k_offset), out.data_ptr(), ldp, st))
         out = out[:, :, :P]
         return out[0] if squeeze else out
 
@@ -338,8 +407,13 @@ class StandaloneSTFT:
                                                 Sx3.stride(1) if F > 1 else P, Sy3.stride(1) if F > 1 else P, st))
         return Sx.cpu().numpy() if was_numpy else Sx
 
-    def istft(self, S, k0=None, k1=None):
-        """src/lib.rs:792-914 -> real signal of length k1-k0 (default k0=0, k1=k_max of S)."""
+    def istft(self, S, k0=None, k1=None, *, complex_output=False):
+        """src/lib.rs:792-914 -> real signal of length k1-k0 (default k0=0, k1=k_max of S).
+        complex_output=True (two-sided layouts): the twin's complex result (python/standalone_stft.py:404, 424;
+        the Rust crate keeps the real part, src/lib.rs:903-907): Re from S, Im = istft_real(-i S)."""
+        self._raise_if_nan()
+        if complex_output:
+            return self._istft_complex(S, k0, k1)
         if self._is_tensor(S):
             return self._istft_tensor(S, k0, k1)
         S = np.asarray(S)
@@ -356,6 +430,22 @@ class StandaloneSTFT:
         _check(self._L.veils_istft_host(self._h, S3.ctypes.data, P, batch, opt_i64(a), opt_i64(b),
                                         out.ctypes.data))
         return out[0] if squeeze else out
+
+    def _istft_complex(self, S, k0, k1):
+        if self.onesided_fft:
+            raise VeilsError(_lib.ERR_INVALID, "complex_output needs fft_mode 'twosided' or 'centered'")
+        import torch
+        was_numpy = not self._is_tensor(S)
+        cdt = torch.complex64 if self.precision == "f32" else torch.complex128
+        St = torch.from_numpy(np.ascontiguousarray(S)).to(cdt).cuda(self.device) if was_numpy else S
+        S3 = (St[None] if St.dim() == 2 else St).contiguous()
+        batch, F, P = S3.shape
+        T3 = torch.empty_like(S3)
+        st = torch.cuda.current_stream(S3.device).cuda_stream
+        _check(self._L.veils_complex_op_dev(self._h, 2, T3.data_ptr(), S3.data_ptr(), P, batch, P, P, st))
+        y = torch.complex(self._istft_tensor(S3, k0, k1), self._istft_tensor(T3, k0, k1))   # packaging of the two results
+        y = y[0] if St.dim() == 2 else y
+        return y.cpu().numpy() if was_numpy else y
 
     def _istft_tensor(self, S, k0, k1):
         import torch
