@@ -119,6 +119,9 @@ int32_t veils_t(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t
                 int64_t k_offset, double *out);
 /* f() (src/lib.rs:930-949; centered follows scipy): writes f_pts doubles */
 int32_t veils_f(const veils_plan *p, double *out);
+/* StandaloneSTFT::debug_ifft_func (src/lib.rs:952-954): ifft_func (:414-505) of ONE slice, evaluated on the
+ * host in f64 (debug helper, O(mfft^2)).  X: f_pts complex {re, im}; out: m_num complex {re, im}. */
+int32_t veils_debug_ifft_func(const veils_plan *p, const double *X, double *out);
 
 /* ---- compute: device pointers + stream (the measured path) ---------------------------- */
 /* stft (src/lib.rs:689-749) for `batch` signals of n samples.  x, S are device pointers of

@@ -8,8 +8,45 @@ use std::ffi::{CStr, CString};
 use std::os::raw::c_void;
 use std::ptr;
 
+/// reference src/lib.rs:54-84
+#[derive(Debug, Clone, PartialEq)]
+pub enum FftMode {
+    TwoSided,
+    Centered,
+    OneSided,
+    OneSided2X,
+}
+
+impl std::str::FromStr for FftMode {
+    type Err = String;
+    fn from_str(s: &str) -> Result<Self, Self::Err> {
+        match s {
+            "twosided" => Ok(FftMode::TwoSided),
+            "centered" => Ok(FftMode::Centered),
+            "onesided" => Ok(FftMode::OneSided),
+            "onesided2X" => Ok(FftMode::OneSided2X),
+            _ => Err(format!("Unknown fft_mode: {}", s)),
+        }
+    }
+}
+
+impl FftMode {
+    pub fn is_onesided(&self) -> bool {
+        matches!(self, FftMode::OneSided | FftMode::OneSided2X)
+    }
+    fn from_code(c: i32) -> FftMode {
+        match c {
+            ffi::VEILS_TWOSIDED => FftMode::TwoSided,
+            ffi::VEILS_CENTERED => FftMode::Centered,
+            ffi::VEILS_ONESIDED2X => FftMode::OneSided2X,
+            _ => FftMode::OneSided,
+        }
+    }
+}
+
 pub struct StandaloneSTFT {
     plan: *mut ffi::veils_plan,
+    fft_mode: FftMode,
 }
 
 unsafe impl Send for StandaloneSTFT {}
@@ -57,9 +94,12 @@ impl StandaloneSTFT {
         };
         let mut plan = ptr::null_mut();
         check(unsafe { ffi::veils_plan_create(&desc, &mut plan) })?;
-        Ok(StandaloneSTFT { plan })
+        let fft_mode = FftMode::from_code(unsafe { ffi::veils_fft_mode(plan) });
+        Ok(StandaloneSTFT { plan, fft_mode })
     }
 
+    /// reference src/lib.rs:239
+    pub fn fft_mode(&self) -> &FftMode { &self.fft_mode }
     pub fn hop(&self) -> usize { unsafe { ffi::veils_hop(self.plan) as usize } }
     pub fn fs(&self) -> f64 { unsafe { ffi::veils_fs(self.plan) } }
     pub fn mfft(&self) -> usize { unsafe { ffi::veils_mfft(self.plan) as usize } }
@@ -158,6 +198,14 @@ impl StandaloneSTFT {
         check(unsafe { ffi::veils_t(self.plan, n as i64, opt(&a64), opt(&b64),
                                     k_offset.unwrap_or(0) as i64, out.as_mut_ptr()) })?;
         Ok(out)
+    }
+    /// reference src/lib.rs:952-954: ifft_func of one slice (f_pts bins -> m_num samples)
+    pub fn debug_ifft_func(&self, x: Vec<Complex<f64>>) -> Vec<Complex<f64>> {
+        let mut out = vec![Complex::new(0.0f64, 0.0); self.m_num()];
+        if x.len() == self.f_pts() {
+            unsafe { ffi::veils_debug_ifft_func(self.plan, x.as_ptr() as *const f64, out.as_mut_ptr() as *mut f64) };
+        }
+        out
     }
     pub fn f(&self) -> Vec<f64> {
         let mut out = vec![0.0f64; self.f_pts()];

@@ -30,6 +30,42 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().veils_abi_version() == 1
 
 
+def test_rust_ffi_mirrors_the_header():
+    """rust/src/ffi.rs is generated from include/veils_cuda.h (tools/gen_rust_ffi.py): every declaration of the
+    header -- and nothing else -- has its `extern "C"` item, and the crate shell keeps the reference's accessors."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_rust_ffi", os.path.join(root, "tools", "gen_rust_ffi.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
+    assert text == gen.generate(), "rust/src/ffi.rs is stale: run python tools/gen_rust_ffi.py"
+    fns = set(re.findall(r"pub fn (veils_[a-z0-9_]+)\(", text))
+    assert fns == set(_header_symbols())
+    shell = open(os.path.join(root, "rust", "src", "lib.rs")).read()
+    for item in ("pub fn fft_mode(&self) -> &FftMode", "pub fn debug_ifft_func(", "pub enum FftMode", "fn is_onesided",
+                 "pub fn stft(", "pub fn istft(", "pub fn spectrogram(", "pub fn p_range(", "pub fn dual_win("):
+        assert item in shell, item
+
+
+def test_debug_ifft_func_matches_the_oracle():
+    """src/lib.rs:952-954 -- host-only, no GPU needed"""
+    from oracle.stft_oracle import OracleSTFT
+    rng = np.random.default_rng(2)
+    for mode in ("onesided", "onesided2X", "twosided", "centered"):
+        for m, mfft, ps in ((16, 16, 0), (15, 20, 3), (8, 8, -2)):
+            win = rng.uniform(0.2, 1.0, m)
+            o = OracleSTFT(win, 4, 1.0, fft_mode=mode, mfft=mfft, phase_shift=ps)
+            s = StandaloneSTFT(win, 4, 1.0, fft_mode=mode, mfft=mfft, phase_shift=ps)
+            X = rng.standard_normal(o.f_pts) + 1j * rng.standard_normal(o.f_pts)
+            if mode.startswith("onesided"):
+                X[0] = X[0].real
+                if mfft % 2 == 0:
+                    X[-1] = X[-1].real
+            assert rel_err(s.debug_ifft_func(X), o._ifft_func(X[None, :])[0]) <= 1e-13
+
+
 def _mk(r, **kw):
     return StandaloneSTFT(r["win"], int(r["hop"]), float(r["fs"]), fft_mode=str(r["mode"]),
                           mfft=int(r["mfft"]), phase_shift=int(r.get("phase_shift", 0)), **kw)

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "veils_istft_range": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P]),
     "veils_t": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, C.c_int64, _DP]),
     "veils_f": (C.c_int32, [_P, _DP]),
+    "veils_debug_ifft_func": (C.c_int32, [_P, _DP, _DP]),
     "veils_stft_dev": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,
                                     C.c_int64, _P, C.c_int64, _P]),
     "veils_spectrogram_dev": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,

@@ -115,11 +115,20 @@ static cudaError_t upload_prec(const Plan &pl, const std::vector<double> &src, v
 
 // Create the device tables on first use.  need_dual: also resolve + upload the dual window.
 static int32_t ensure_device(Plan &pl, bool need_dual) {
+    const int want = need_dual ? 3 : 1;
+    if ((pl.dev_ready.load(std::memory_order_acquire) & want) == want) return VEILS_OK;   // no lock, no CUDA call
     if (need_dual) {
         std::string e = plan_dual(pl);
         if (!e.empty()) return fail(VEILS_ERR_NOT_INVERTIBLE, e);
     }
     std::lock_guard<std::mutex> g(pl.mu);
+    if (pl.dev && (!need_dual || pl.dev->dual)) return VEILS_OK;      // another thread was faster
+    // first use: build the tables on the plan's device without disturbing the caller's current device
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
+    cudaGetDevice(&guard.prev);
     CU(cudaSetDevice(pl.device));
     if (!pl.dev) {
         DeviceTables *d = new (std::nothrow) DeviceTables();
@@ -148,7 +157,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
         }
         if (e == cudaSuccess && pl.wide) {
             std::vector<double> tw((size_t)wide_table_floats(pl.M));
-            wide_table_fill_host(pl.M, false, pl.win.data(), 0.5, tw.data());
+            wide_table_fill_host(pl.M, pl.wide_tf, false, pl.win.data(), 0.5, tw.data());
             e = upload_as<float>(tw, (void **)&d->wide_fwd);
         }
         if (e == cudaSuccess && !((pl.pow2_fwd || pl.pk_fwd) && (pl.pow2_inv || pl.pk_inv))) {
@@ -164,6 +173,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
             return cuda_fail(e, "upload plan tables");
         }
         pl.dev = d;
+        pl.dev_ready.fetch_or(1, std::memory_order_release);
     }
     if (need_dual && !pl.dev->dual) {
         // pow2 inverse folds 1/M (and the 1/2 of the Hermitian part for two-sided layouts) here.
@@ -183,7 +193,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
         }
         if (e == cudaSuccess && pl.wide_inv) {
             std::vector<double> tw((size_t)wide_table_floats(pl.M));
-            wide_table_fill_host(pl.M, true, pl.dual.data(), sc, tw.data());
+            wide_table_fill_host(pl.M, pl.wide_tf, true, pl.dual.data(), sc, tw.data());
             e = upload_as<float>(tw, (void **)&wide_inv);
         }
         if (e != cudaSuccess) {
@@ -194,9 +204,20 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
         pl.dev->itab_pk = itab;
         pl.dev->wide_inv = wide_inv;
         pl.dev->dual = dual;
+        pl.dev_ready.fetch_or(2, std::memory_order_release);
     }
     return VEILS_OK;
 }
+
+// kernels are launched on the plan's device; the caller's current device is restored afterwards
+struct PlanDeviceScope {
+    int prev = -1;
+    explicit PlanDeviceScope(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev) { prev = cur; cudaSetDevice(dev); }
+    }
+    ~PlanDeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
 
 template <typename T>
 static Tables<T> tables_of(const Plan &pl) {
@@ -238,14 +259,15 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         pl.pow2_fwd = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, false);
         pl.pow2_inv = !force_generic && pow2_supported(pl.M, pl.N, pl.H, pl.ps, pl.precision, true);
         const bool no_pk = getenv("VEILS_NO_PACKED") != nullptr;
-        // measured on B200 (profiles/r1_config_sweep.txt): the packed forward wins for 2-pass plans
-        // (mfft <= 512); for the 3-pass plans its 255-register build loses to the scalar family
+        // measured on B200 (profiles/r1_config_sweep.txt): the packed forward wins up to mfft = 1024;
+        // beyond, its 255-register 3-pass build loses to the scalar family (and both to the wide family)
         pl.pk_fwd = !force_generic && !no_pk && pl.precision == F32 && (pl.M <= 1024 || !pl.pow2_fwd || getenv("VEILS_PK_FWD_ALL") != nullptr) &&
                     pk_supported(pl.M, pl.N, pl.H, pl.ps, false);
         pl.pk_inv = !force_generic && !no_pk && pl.precision == F32 && pk_supported(pl.M, pl.N, pl.H, pl.ps, true);
         // mfft 1024 / 2048 / 4096 with the default geometry: the wide family (conflict-free swizzled tiles)
         pl.wide = !force_generic && pl.precision == F32 && getenv("VEILS_NO_WIDE") == nullptr &&
                   wide_supported(pl.M, pl.N, pl.H, pl.ps);
+        pl.wide_tf = pl.wide ? wide_tf(pl.M) : 0;
         // two-sided inverse: two rows per bin, no tensor-map landing yet -> the packed family is faster there
         // (measured c4: 49 % vs 27 % of the roofline); VEILS_WIDE_INV_ALL=1 forces the wide kernels
         pl.wide_inv = pl.wide && (pl.mode >= ONESIDED || !pl.pk_inv || getenv("VEILS_WIDE_INV_ALL") != nullptr);
@@ -380,6 +402,48 @@ int32_t veils_f(const veils_plan *p, double *out) {
     return VEILS_OK;
 }
 
+// StandaloneSTFT::debug_ifft_func (src/lib.rs:952-954 -> ifft_func :414-505) of ONE slice, on the host:
+// mode prologue, direct O(M^2) inverse DFT in f64 (a debug helper, not a compute path), 1/M, roll right by
+// p_s over mfft, first m_num samples.  X: f_pts complex {re, im}; out: m_num complex.  One-sided layouts
+// follow irfft semantics (imaginary parts of DC / Nyquist ignored), so the result is real.
+int32_t veils_debug_ifft_func(const veils_plan *p, const double *X, double *out) {
+    if (!p || !X || !out) return fail(VEILS_ERR_INVALID, "null argument");
+    const Plan &pl = p->pl;
+    const int64_t M = pl.M, N = pl.N, F = pl.F;
+    std::vector<double> fr((size_t)M), fi((size_t)M);
+    if (pl.mode >= ONESIDED) {
+        const double c = pl.mode == ONESIDED2X ? 1.0 / pl.fac2x : 1.0;
+        for (int64_t k = 0; k < F; ++k) {
+            const bool paired = k >= 1 && (M % 2 == 0 ? k <= F - 2 : k <= F - 1);
+            const double sc = paired ? c : 1.0;
+            fr[k] = X[2 * k] * sc;
+            fi[k] = (k == 0 || (M % 2 == 0 && k == M / 2)) ? 0.0 : X[2 * k + 1] * sc;
+        }
+        for (int64_t k = F; k < M; ++k) { fr[k] = fr[M - k]; fi[k] = -fi[M - k]; }
+    } else {
+        const int64_t sh = pl.mode == CENTERED ? M / 2 : 0;          // ifftshift = rotate_left(floor(M/2)) :516-521
+        for (int64_t k = 0; k < M; ++k) { fr[k] = X[2 * ((k + sh) % M)]; fi[k] = X[2 * ((k + sh) % M) + 1]; }
+    }
+    std::vector<double> yr((size_t)M), yi((size_t)M);
+    for (int64_t nn = 0; nn < M; ++nn) {
+        long double ar = 0, ai = 0;
+        for (int64_t k = 0; k < M; ++k) {
+            double wr, wi;
+            twiddle(-(k * nn), M, &wr, &wi);                          // exp(+2 pi i k n / M)
+            ar += (long double)fr[k] * wr - (long double)fi[k] * wi;
+            ai += (long double)fr[k] * wi + (long double)fi[k] * wr;
+        }
+        yr[nn] = (double)(ar / M);
+        yi[nn] = (double)(ai / M);
+    }
+    for (int64_t j = 0; j < N; ++j) {                                 // roll right by ps: out[j] = y[(j - ps) mod M]
+        const int64_t i = ((j - pl.ps) % M + M) % M;
+        out[2 * j] = yr[i];
+        out[2 * j + 1] = yi[i];
+    }
+    return VEILS_OK;
+}
+
 // ---- compute -----------------------------------------------------------------------------
 static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch,
                             const int64_t *p0, const int64_t *p1, int64_t k_offset, void *out,
@@ -399,6 +463,7 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
     if (batch == 0) return VEILS_OK;
     int32_t rc = ensure_device(pl, false);
     if (rc != VEILS_OK) return rc;
+    PlanDeviceScope scope(pl.device);
     FwdParams prm;
     prm.n = n; prm.x_pitch = x_pitch; prm.batch = batch;
     prm.N = pl.N; prm.H = pl.H; prm.M = pl.M; prm.F = pl.F; prm.mid = pl.mid; prm.ps = pl.ps;
@@ -408,7 +473,7 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.wide ? wide_forward((const float *)x, out, prm, tb.wide_fwd, st)
+        ce = pl.wide ? wide_forward((const float *)x, out, prm, tb.wide_fwd, pl.wide_tf, st)
              : pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
              : pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
                            : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
@@ -495,6 +560,7 @@ int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t b
     if (batch <= 0) return batch == 0 ? VEILS_OK : fail(VEILS_ERR_INVALID, "batch must be >= 0");
     rc = ensure_device(pl, false);
     if (rc != VEILS_OK) return rc;
+    PlanDeviceScope scope(pl.device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce = pl.precision == F32
                          ? pad_signal<float>((const float *)x, (float *)x_ext, n, batch, x_pitch, left, n_ext, ext_pitch, mode, st)
@@ -574,6 +640,7 @@ int32_t veils_cross_multiply_dev(veils_plan *p, void *Sx, const void *Sy, int64_
     Plan &pl = p->pl;
     int32_t rc = ensure_device(pl, false);
     if (rc != VEILS_OK) return rc;
+    PlanDeviceScope scope(pl.device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce = pl.precision == F32 ? cross_multiply<float>((float *)Sx, (const float *)Sy, batch * pl.F, P, ldx, ldy, st)
                                          : cross_multiply<double>((double *)Sx, (const double *)Sy, batch * pl.F, P, ldx, ldy, st);
@@ -589,6 +656,7 @@ int32_t veils_complex_op_dev(veils_plan *p, int32_t op, void *A, const void *B, 
     Plan &pl = p->pl;
     int32_t rc = ensure_device(pl, false);
     if (rc != VEILS_OK) return rc;
+    PlanDeviceScope scope(pl.device);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce = pl.precision == F32 ? complex_op<float>((float *)A, (const float *)B, batch * pl.F, P, lda, ldb, op, st)
                                          : complex_op<double>((double *)A, (const double *)B, batch * pl.F, P, lda, ldb, op, st);
@@ -610,6 +678,7 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     if (batch == 0) return VEILS_OK;
     int32_t rc = ensure_device(pl, true);                    // dual_win()? (src/lib.rs:849)
     if (rc != VEILS_OK) return rc;
+    PlanDeviceScope scope(pl.device);
     InvParams prm;
     prm.P = P; prm.ldp = ldp; prm.batch = batch;
     prm.N = pl.N; prm.H = pl.H; prm.M = pl.M; prm.F = pl.F; prm.mid = pl.mid; prm.ps = pl.ps;
@@ -619,7 +688,7 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
     cudaError_t ce;
     if (pl.precision == F32) {
         Tables<float> tb = tables_of<float>(pl);
-        ce = pl.wide_inv ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, st)
+        ce = pl.wide_inv ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, pl.wide_tf, st)
              : pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
              : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
                            : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
@@ -666,6 +735,7 @@ static int32_t nan_check_launch(const Plan &pl, const void *x, int64_t n, int64_
                                 int64_t P, int64_t k_offset, const void *S, int64_t ldp, int spectrogram, int *flag,
                                 cudaStream_t st) {
     if (pl.mode < ONESIDED || !flag || batch <= 0 || P <= 0) return VEILS_OK;
+    PlanDeviceScope scope(pl.device);
     const int64_t total = batch * P;
     const int grid = (int)std::min<int64_t>(148 * 8, (total + 255) / 256);
     const int mul = spectrogram ? 1 : 2;

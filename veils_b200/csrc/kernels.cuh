@@ -83,9 +83,9 @@ bool wide_supported(int64_t M, int64_t N, int64_t H, int64_t ps);
 int wide_tf(int64_t M);                                   // slices per tile (0: mfft not covered)
 int64_t wide_table_floats(int64_t M);
 // plan table of one direction: window * 0.5 (forward) or dual * scale (inverse) + twiddles, as doubles
-void wide_table_fill_host(int64_t M, bool inverse, const double *vec_n, double scale, double *out);
-cudaError_t wide_forward(const float *x, void *out, const FwdParams &prm, const float *tab, cudaStream_t st);
-cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, const float *tab, cudaStream_t st);
+void wide_table_fill_host(int64_t M, int tf, bool inverse, const double *vec_n, double scale, double *out);
+cudaError_t wide_forward(const float *x, void *out, const FwdParams &prm, const float *tab, int tf, cudaStream_t st);
+cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, const float *tab, int tf, cudaStream_t st);
 
 // ---- border extension for the twin's padding modes (pad.cu): mode 0 zeros, 1 edge, 2 even, 3 odd
 template <typename T>

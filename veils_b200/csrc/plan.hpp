@@ -4,6 +4,7 @@
 // reference recomputes on every call (pre/post padding, src/lib.rs:524-585) and what the CUDA
 // kernels need (device tables, dispatch decision).  Pure host C++: usable without a GPU.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <mutex>
 #include <string>
@@ -47,11 +48,13 @@ struct Plan {
 
     // device side, created lazily by the first compute call
     DeviceTables *dev = nullptr;
+    std::atomic<int> dev_ready{0};   // bit 0: forward tables uploaded, bit 1: dual-window tables too (lock-free fast path)
     bool pow2_fwd = false;    // dispatch decisions (see api.cu)
     bool pow2_inv = false;
     bool pk_fwd = false;      // packed f32 family (preferred over pow2 when available)
     bool pk_inv = false;
     bool wide = false;        // wide f32 family (mfft 1024 / 2048 / 4096, default geometry): forward
+    int wide_tf = 0;          // slices per tile of the wide kernels, fixed at plan creation
     bool wide_inv = false;    // ... and inverse (one-sided layouts; two-sided ones stay with the packed family)
 };
 

@@ -7,6 +7,7 @@
 
 #include "pow2_pk_cfg.hpp"
 #include "tma.cuh"
+#include "launch_cache.cuh"
 
 namespace veils {
 
@@ -414,25 +415,10 @@ pk_inv_kernel(const __grid_constant__ InvArgs<float> args, const ITab *__restric
     }
 }
 
-int pk_env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-int pk_num_sms();
+#define pk_env_int(name, dflt) VEILS_ENV_ONCE(name, dflt)      // environment switches: read once per process
 int pk_cta_cap(int per_sm) {
-    const char *e = getenv("VEILS_PK_CTAS_PER_SM");
-    if (e && atoi(e) > 0 && atoi(e) < per_sm) return atoi(e);
-    return per_sm;
-}
-
-int pk_num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
+    const int e = VEILS_ENV_ONCE("VEILS_PK_CTAS_PER_SM", 0);
+    return (e > 0 && e < per_sm) ? e : per_sm;
 }
 
 struct PkFwdLaunch {
@@ -453,23 +439,33 @@ struct PkFwdLaunch {
         CUtensorMap smap, smap_tile;
         memset(&smap, 0, sizeof(smap));
         memset(&smap_tile, 0, sizeof(smap_tile));
-        const bool stage = ones && p.batch < (1LL << 31) && !pk_env_int("VEILS_PK_NO_TMA", 0) &&
-                           tma::make_s_map(&smap, out, spec ? 4 : 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL) &&
-                           (spec || (K::NP == 2 ? tma::make_s_map(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL, K::G)
-                                                : tma::make_s_map5(&smap_tile, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, K::R1, TF)));
+        bool stage = ones && p.batch < (1LL << 31) && !pk_env_int("VEILS_PK_NO_TMA", 0);
+        if (stage) {
+            const int esz = spec ? 4 : 8;
+            const MapKey k1{out, {esz, p.P, p.ldp, p.F, p.batch, K::G * 1000 + K::RL, TF, 101}};
+            stage = cached_map(&smap, k1, [&](CUtensorMap *m) {
+                return tma::make_s_map(m, out, esz, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL);
+            });
+            if (stage && !spec) {
+                const MapKey k2{out, {8, p.P, p.ldp, p.F, p.batch, K::G * 1000 + K::RL, TF, 102 + K::NP}};
+                stage = cached_map(&smap_tile, k2, [&](CUtensorMap *m) {
+                    return K::NP == 2 ? tma::make_s_map(m, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, TF, K::RL, K::G)
+                                      : tma::make_s_map5(m, out, 8, p.P, p.ldp, p.F, p.batch, K::G, K::RL, K::R1, TF);
+                });
+            }
+        }
         KernT kern = stage ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, true> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, true>)
                    : ones  ? (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, true, false, false>)
                            : (spec ? (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, true, false> : (KernT)pk_fwd_kernel<LOGMC, TF, NSUB, false, false, false>);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static KernelSlot slots[6];
+        int per_sm = 0, dev = 0;
+        cudaError_t e = prepare_kernel(slots[(stage ? 0 : (ones ? 2 : 4)) + (spec ? 1 : 0)], kern, (TF / 2) * NSUB, smem, &per_sm, &dev);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorInvalidConfiguration;
+        const int sms = device_sms(dev);
         const int64_t total = a.ptiles * p.batch;
-        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
+        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * sms;
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem, st>>>(
-            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), pk_num_sms(), smap, smap_tile);
+            a, ptab, total, xin_elems, pk_zero_off(p.N, p.H, TF), pk_env_int("VEILS_PK_STAGGER_NS", 0), sms, smap, smap_tile);
         ++g_launch_count;
         return cudaGetLastError();
     }
@@ -506,12 +502,21 @@ struct PkInvLaunch {
         // mfft 2048 1.32 -> 1.14 ms, mfft 4096 2.66 -> 2.55 ms (mfft 1024 has two group pairs per thread)
         const bool acc_size = (LOGMC == 7 || LOGMC == 8 || LOGMC == 10 || LOGMC == 11) &&
                               pk_inv_acc_smem_bytes<LOGMC, TF>(p.N) + 1024 <= SMEM_LIMIT;
-        const int use_tma = (LOGMC == 8 || (acc_geo && acc_size)) && (K::R1 * K::LTF * 8) % 128 == 0 &&
-                            p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
-                            !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) &&
-                            K::L1 <= 256 &&
-                            tma::make_s_map(&smap, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1, K::L1) &&
-                            tma::make_s_map(&smap_nyq, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
+        bool use_tma = (LOGMC == 8 || (acc_geo && acc_size)) && (K::R1 * K::LTF * 8) % 128 == 0 &&
+                       p.mode >= 2 && K::WPT2 == 1 && p.batch < (1LL << 31) && p.P < (1LL << 31) &&
+                       !pk_env_int("VEILS_PK_NO_TMA", 0) && !pk_env_int("VEILS_PK_NO_TMA_LOAD", 0) && K::L1 <= 256;
+        if (use_tma) {
+            const MapKey k1{S, {8, p.P, p.ldp, p.F, p.batch, K::L1 * 1000 + K::R1, K::LTF, 201}};
+            use_tma = cached_map(&smap, k1, [&](CUtensorMap *m) {
+                return tma::make_s_map(m, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, K::R1, K::L1);
+            });
+            if (use_tma) {
+                const MapKey k2{S, {8, p.P, p.ldp, p.F, p.batch, K::L1 * 1000 + K::R1, K::LTF, 202}};
+                use_tma = cached_map(&smap_nyq, k2, [&](CUtensorMap *m) {
+                    return tma::make_s_map(m, S, 8, p.P, p.ldp, p.F, p.batch, K::L1, K::R1, K::LTF, 1);
+                });
+            }
+        }
         // accumulator overlap-add: 75 % overlap with the default roll, 8-byte aligned output pairs.
         // 2 = its own shared-memory layout (no carry buffers); the plain TMA path keeps the base layout
         const int acc_path = (use_tma && acc_geo && acc_size) ? 2 : 0;
@@ -522,13 +527,11 @@ struct PkInvLaunch {
             smem_l = pk_inv_acc_smem_bytes<LOGMC, TF>(p.N);
         }
         const int use_tma_l = use_tma && (acc_path || (size_t)work_bytes >= K::LAND_BYTES);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l);
+        static KernelSlot slots[2];
+        int per_sm = 0, dev = 0;
+        cudaError_t e = prepare_kernel(slots[p.mode >= 2 ? 1 : 0], kern, (TF / 2) * NSUB, smem_l, &per_sm, &dev);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (TF / 2) * NSUB, smem_l);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorInvalidConfiguration;
-        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * pk_num_sms();
+        const int64_t cap = (int64_t)pk_cta_cap(per_sm) * device_sms(dev);
         pk_inv_chunks(a, p, TF, p.batch, cap);
         const int64_t total = a.cps * p.batch;
         kern<<<(unsigned)(total < cap ? total : cap), (TF / 2) * NSUB, smem_l, st>>>(a, itab, total, work_bytes_l, use_tma_l, acc_path, smap, smap_nyq);

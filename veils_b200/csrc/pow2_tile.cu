@@ -5,6 +5,7 @@
 
 #include "pow2_cfg.hpp"
 #include "tma.cuh"
+#include "launch_cache.cuh"
 
 namespace veils {
 
@@ -159,16 +160,6 @@ pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, co
     }
 }
 
-static int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    return sms;
-}
-
 struct FwdLaunch {
     const void *x; void *out; const FwdParams *prm; const void *win; const void *tw; cudaStream_t st;
     template <typename T, int LOGMC, int TF, int NSUB>
@@ -180,25 +171,25 @@ struct FwdLaunch {
         const size_t smem = fwd_smem_bytes_t<T, LOGMC, TF>(p.N, xin_elems);
         CUtensorMap smap;
         memset(&smap, 0, sizeof(smap));
-        const char *no_tma = getenv("VEILS_PK_NO_TMA");
         // measured (profiles/r1c_ablation.txt): +3 % for f64; the f32 tile kernels (mfft >= 2048 here) are
         // 5 % faster with their plain stores, so only f64 takes the staged path
-        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !(no_tma && atoi(no_tma));
+        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !VEILS_ENV_ONCE("VEILS_PK_NO_TMA", 0);
         if (stage) {
             // complex f64 elements are 16 bytes: described as pairs of 8-byte elements
             const int mul = (!p.spectrogram && sizeof(T) == 8) ? 2 : 1;
             const int esz = p.spectrogram ? (int)sizeof(T) : (sizeof(T) == 8 ? 8 : 8);
-            stage = tma::make_s_map(&smap, out, esz, p.P * mul, p.ldp * mul, p.F, p.batch, K::G, K::RL, TF * mul, K::RL);
+            const MapKey key{out, {esz, p.P * mul, p.ldp * mul, p.F, p.batch, K::G * 1000 + K::RL, TF * mul, 1}};
+            stage = cached_map(&smap, key, [&](CUtensorMap *m) {
+                return tma::make_s_map(m, out, esz, p.P * mul, p.ldp * mul, p.F, p.batch, K::G, K::RL, TF * mul, K::RL);
+            });
         }
         auto kern = stage ? pow2_fwd_kernel<T, LOGMC, TF, NSUB, true> : pow2_fwd_kernel<T, LOGMC, TF, NSUB, false>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static KernelSlot slots[2];
+        int per_sm = 0, dev = 0;
+        cudaError_t e = prepare_kernel(slots[stage ? 1 : 0], kern, TF * NSUB, smem, &per_sm, &dev);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TF * NSUB, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ptiles * p.batch;
-        const int64_t cap = (int64_t)per_sm * num_sms();
+        const int64_t cap = (int64_t)per_sm * device_sms(dev);
         const unsigned grid = (unsigned)(total < cap ? total : cap);
         (void)sizeof(K);
         kern<<<grid, TF * NSUB, smem, st>>>(a, total, xin_elems, smap);
@@ -217,14 +208,12 @@ struct InvLaunch {
         const int work_bytes = (int)inv_work_bytes_t<T, LOGMC, TF>(p.N);
         const size_t smem = inv_smem_bytes_t<T, LOGMC, TF>(p.N);
         auto kern = pow2_inv_kernel<T, LOGMC, TF, NSUB>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        static KernelSlot slot;
+        int per_sm = 0, dev = 0;
+        cudaError_t e = prepare_kernel(slot, kern, TF * NSUB, smem, &per_sm, &dev);
         if (e != cudaSuccess) return e;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TF * NSUB, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorInvalidConfiguration;
         const int64_t total = a.ntiles * p.batch;
-        const int64_t cap = (int64_t)per_sm * num_sms();
+        const int64_t cap = (int64_t)per_sm * device_sms(dev);
         const unsigned grid = (unsigned)(total < cap ? total : cap);
         kern<<<grid, TF * NSUB, smem, st>>>(a, total, work_bytes);
         ++g_launch_count;

@@ -14,7 +14,8 @@ struct FwdLaunch {
         auto kern = wide_fwd_kernel<LOGMC, TF, MODE, SPEC>;
         const size_t smem = wide_fwd_smem_bytes<LOGMC, TF>();
         int cap = 0;
-        cudaError_t e = wide_prepare(kern, K::NT, smem, &cap);
+        static KernelSlot slot;
+        cudaError_t e = wide_prepare(slot, kern, K::NT, smem, &cap);
         if (e != cudaSuccess) return e;
         const int64_t total = a.ptiles * prm->batch;
         kern<<<(unsigned)(total < cap ? total : cap), K::NT, smem, st>>>(a, total);
@@ -59,15 +60,17 @@ struct FwdLaunch {
 
 bool wide_supported(int64_t M, int64_t N, int64_t H, int64_t ps) { return wd::wide_geometry_ok(M, N, H, ps); }
 int64_t wide_table_floats(int64_t M) { return 2 * wd::wide_table_entries(M); }
+// slices per tile of the plan (VEILS_WIDE_TF is a tuning switch, read at PLAN creation)
 int wide_tf(int64_t M) {
     wd::WCfg c;
-    if (!wd::wide_cfg_for(M, wd::env_int("VEILS_WIDE_TF", 0), &c)) return 0;
+    const char *e = getenv("VEILS_WIDE_TF");
+    if (!wd::wide_cfg_for(M, e ? atoi(e) : 0, &c)) return 0;
     return c.tf;
 }
 // forward: window * 0.5; inverse: dual * scale.  `out` receives wide_table_floats(M) doubles.
-void wide_table_fill_host(int64_t M, bool inverse, const double *vec_n, double scale, double *out) {
+void wide_table_fill_host(int64_t M, int tf, bool inverse, const double *vec_n, double scale, double *out) {
     wd::WCfg c;
-    if (!wd::wide_cfg_for(M, wd::env_int("VEILS_WIDE_TF", 0), &c)) return;
+    if (!wd::wide_cfg_for(M, tf, &c)) return;
     int r1 = 0, r2 = 0;
     if (c.logmc == 9) { r1 = 8; r2 = 8; }
     else if (c.logmc == 10 && c.tf == 16) { r1 = inverse ? 8 : 16; r2 = 8; }
@@ -76,10 +79,10 @@ void wide_table_fill_host(int64_t M, bool inverse, const double *vec_n, double s
     wd::wide_table_fill(M, r1, r2, vec_n, scale, out);
 }
 
-cudaError_t wide_forward(const float *x, void *out, const FwdParams &prm, const float *tab, cudaStream_t st) {
+cudaError_t wide_forward(const float *x, void *out, const FwdParams &prm, const float *tab, int tf, cudaStream_t st) {
     if (prm.P <= 0 || prm.batch <= 0) return cudaSuccess;
     wd::WCfg c;
-    if (!wd::wide_cfg_for(prm.M, wd::env_int("VEILS_WIDE_TF", 0), &c)) return cudaErrorNotSupported;
+    if (!wd::wide_cfg_for(prm.M, tf, &c)) return cudaErrorNotSupported;
     FwdLaunch l{x, out, &prm, tab, st};
     return wd::wide_dispatch(c, l);
 }

@@ -16,15 +16,22 @@ struct InvLaunch {
         CUtensorMap smap, smap_nyq;
         memset(&smap, 0, sizeof(smap));
         memset(&smap_nyq, 0, sizeof(smap_nyq));
-        const bool land = MODE >= 2 && K::P1_ITERS == 1 && a.vec16 && !env_int("VEILS_WIDE_NO_TMA", 0) &&
-                          tma::make_land_map(&smap, S, a.P, a.ldp, a.F, prm->batch, K::LAND_ROWS) &&
-                          tma::make_land_map(&smap_nyq, S, a.P, a.ldp, a.F, prm->batch, 1);
+        bool land = MODE >= 2 && K::P1_ITERS == 1 && a.vec16 && !env_int("VEILS_WIDE_NO_TMA", 0);
+        if (land) {
+            const MapKey k1{S, {a.P, a.ldp, a.F, prm->batch, K::LAND_ROWS, 301, 0, 0}};
+            land = cached_map(&smap, k1, [&](CUtensorMap *m) { return tma::make_land_map(m, S, a.P, a.ldp, a.F, prm->batch, K::LAND_ROWS); });
+        }
+        if (land) {
+            const MapKey k2{S, {a.P, a.ldp, a.F, prm->batch, 1, 302, 0, 0}};
+            land = cached_map(&smap_nyq, k2, [&](CUtensorMap *m) { return tma::make_land_map(m, S, a.P, a.ldp, a.F, prm->batch, 1); });
+        }
         using KernT = void (*)(const WInvArgs, const int64_t, const CUtensorMap, const CUtensorMap);
         KernT kern = wide_inv_kernel<LOGMC, TF, MODE, false>;
         if (MODE >= 2 && land) kern = wide_inv_kernel<LOGMC, TF, (MODE >= 2 ? MODE : 2), true>;
         const size_t smem = wide_inv_smem_bytes<LOGMC, TF>();
         int cap = 0;
-        cudaError_t e = wide_prepare(kern, K::NT, smem, &cap);
+        static KernelSlot slots[2];
+        cudaError_t e = wide_prepare(slots[(MODE >= 2 && land) ? 1 : 0], kern, K::NT, smem, &cap);
         if (e != cudaSuccess) return e;
         // streaming overlap-add: chunks of `ct` tiles; the first tile of a chunk re-computes `halo` slices
         const int64_t Q = a.qh1 - a.qh0 + 1;
@@ -69,10 +76,10 @@ struct InvLaunch {
 };
 }  // namespace
 
-cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, const float *tab, cudaStream_t st) {
+cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, const float *tab, int tf, cudaStream_t st) {
     if (prm.batch <= 0 || prm.k1 <= prm.k0) return cudaSuccess;
     wd::WCfg c;
-    if (!wd::wide_cfg_for(prm.M, wd::env_int("VEILS_WIDE_TF", 0), &c)) return cudaErrorNotSupported;
+    if (!wd::wide_cfg_for(prm.M, tf, &c)) return cudaErrorNotSupported;
     InvLaunch l{S, x_out, &prm, tab, st};
     return wd::wide_dispatch(c, l);
 }

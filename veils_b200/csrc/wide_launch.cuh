@@ -7,29 +7,14 @@
 
 #include "wide_impl.cuh"
 #include "tma.cuh"
+#include "launch_cache.cuh"
 
 namespace veils {
 namespace wd {
 
 template <int NT> constexpr int wide_min_ctas() { return NT <= 256 ? 2 : 1; }
 
-inline int env_int(const char *name, int dflt) {
-    const char *e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-// per-device attributes, read once
-struct DevInfo { int sms = 0; };
-inline const DevInfo &dev_info() {
-    static thread_local int cached_dev = -1;
-    static thread_local DevInfo info;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev != cached_dev) {
-        cudaDeviceGetAttribute(&info.sms, cudaDevAttrMultiProcessorCount, dev);
-        cached_dev = dev;
-    }
-    return info;
-}
+#define env_int(name, dflt) VEILS_ENV_ONCE(name, dflt)          // environment switches: read once per process
 
 // plan table -> shared memory, once per persistent CTA (offsets: wide_table_offsets)
 #define TAB_ENTRIES(M) ((M) / 2 * 3 + (M) / 16 + 2)
@@ -252,16 +237,13 @@ wide_inv_kernel(const __grid_constant__ WInvArgs args, const int64_t total, cons
 }
 
 template <typename KernT>
-inline cudaError_t wide_prepare(KernT kern, int nt, size_t smem, int *grid_cap) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+inline cudaError_t wide_prepare(KernelSlot &slot, KernT kern, int nt, size_t smem, int *grid_cap) {
+    int per_sm = 0, dev = 0;
+    cudaError_t e = prepare_kernel(slot, kern, nt, smem, &per_sm, &dev);
     if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nt, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int cap = env_int("VEILS_WIDE_CTAS_PER_SM", 0);
     if (cap > 0 && cap < per_sm) per_sm = cap;
-    *grid_cap = per_sm * dev_info().sms;
+    *grid_cap = per_sm * device_sms(dev);
     return cudaSuccess;
 }
 

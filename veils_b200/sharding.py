@@ -13,7 +13,7 @@ NO collective:
     overlap-add is local and in the same increasing-q order as the unsharded transform
     (src/lib.rs:853), hence bit-identical (exchanging partial sums instead would change the order);
   * gathering the per-rank results into one array is the only place a collective
-    (`torch.distributed.all_gather` / `gather`, NCCL on GPUs, gloo in the CPU tests) is used.
+    (`torch.distributed.gather` to the destination rank only; NCCL on GPUs, gloo in the CPU tests) is used.
 
 The compute callables are injected (`stft_fn`), so the CPU tests can drive the very same
 partitioning / gathering logic with the oracle standing in for the CUDA kernels.
@@ -59,15 +59,27 @@ def sharded_stft_rows(x_rows, stft_fn):
     return stft_fn(x_rows)
 
 
+def _gather_to(pad, dist, rank, world, dst):
+    """dist.gather of equal-shape tensors to `dst` only; complex tensors travel as (re, im) pairs
+    (the gloo backend has no complex gather)."""
+    import torch
+    cplx = pad.is_complex()
+    t = torch.view_as_real(pad).contiguous() if cplx else pad
+    parts = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, parts, dst=dst)
+    if rank != dst:
+        return None
+    return [torch.view_as_complex(p) for p in parts] if cplx else parts
+
+
 def gather_rows(local, batch: int, dist, rank: int, world: int, dst: int = 0):
     """Gather row shards (torch tensors [rows_r, ...]) to `dst` in rank order -> [batch, ...] or None.
-    Uses all_gather on equal-size padded shards (works with both NCCL and gloo)."""
+    dist.gather of equal-size padded shards: only `dst` receives (NCCL and gloo)."""
     import torch
     rows_max = -(-batch // world)
     pad = torch.zeros((rows_max,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
+    parts = _gather_to(pad, dist, rank, world, dst)
     if rank != dst:
         return None
     out = []
@@ -84,8 +96,7 @@ def gather_frames(local, p_total: int, dist, rank: int, world: int, dst: int = 0
     F = local.shape[0]
     pad = torch.zeros((F, p_maxr), dtype=local.dtype, device=local.device)
     pad[:, : local.shape[1]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
+    parts = _gather_to(pad, dist, rank, world, dst)
     if rank != dst:
         return None
     out = []
@@ -167,8 +178,7 @@ def gather_samples(local, k0: int, k1: int, shards, dist, rank: int, world: int,
     n_max = max(s.k_b - s.k_a for s in shards)
     pad = torch.zeros((n_max,), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
-    parts = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(parts, pad)
+    parts = _gather_to(pad, dist, rank, world, dst)
     if rank != dst:
         return None
     return torch.cat([parts[r][: shards[r].k_b - shards[r].k_a] for r in range(world)], dim=0)

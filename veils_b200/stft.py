@@ -127,6 +127,16 @@ class StandaloneSTFT:
     k_min = property(lambda s: s._L.veils_k_min(s._h))
     device = property(lambda s: s._L.veils_device(s._h))
 
+    def debug_ifft_func(self, X):
+        """src/lib.rs:952-954: ifft_func of one slice (f_pts complex -> m_num complex), host-side f64."""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.complex128).ravel())
+        if X.size != self.f_pts:
+            raise VeilsError(_lib.ERR_INVALID, f"expected {self.f_pts} bins")
+        out = np.empty(self.m_num, dtype=np.complex128)
+        _check(self._L.veils_debug_ifft_func(self._h, X.view(np.float64).ctypes.data_as(C.POINTER(C.c_double)),
+                                             out.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     def kernel_name(self, inverse=False):
         return self._L.veils_plan_kernel_name(self._h, int(inverse)).decode()
 
@@ -310,6 +320,8 @@ class StandaloneSTFT:
         tdt = torch.float32 if self.precision == "f32" else torch.float64
         if not x.is_cuda or x.dtype != tdt:
             raise ValueError(f"expected a CUDA tensor of dtype {tdt}")
+        if x.device.index != self.device:
+            raise ValueError(f"tensor on cuda:{x.device.index}, plan on cuda:{self.device}")
         squeeze = x.dim() == 1
         x2 = x.reshape(1, -1) if squeeze else x
         if x2.stride(-1) != 1:
@@ -452,6 +464,8 @@ class StandaloneSTFT:
         cdt = torch.complex64 if self.precision == "f32" else torch.complex128
         if not S.is_cuda or S.dtype != cdt:
             raise ValueError(f"expected a CUDA tensor of dtype {cdt}")
+        if S.device.index != self.device:
+            raise ValueError(f"tensor on cuda:{S.device.index}, plan on cuda:{self.device}")
         squeeze = S.dim() == 2
         S3 = S[None] if squeeze else S
         batch, F, P = S3.shape
