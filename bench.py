@@ -430,6 +430,33 @@ def side_c1(e):
         fwd()
     host_us = (time.perf_counter() - t0) / 1000 * 1e6
     torch.cuda.synchronize()
+    import ctypes
+    us_c = ctypes.c_double(0.0)
+    assert L.veils_debug_launch_cost_us(st._h, x.data_ptr(), n, 1, n, S.data_ptr(), ldp, stream, 1000, ctypes.byref(us_c)) == 0
+    torch.cuda.synchronize()
+    # the round trip as a CUDA graph (both launches captured once, replayed): what a latency-bound caller would do
+    graph_us = None
+    try:
+        gs = torch.cuda.Stream(e.dev)
+        with torch.cuda.stream(gs):
+            gstream = gs.cuda_stream
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=gs):
+                assert L.veils_stft_dev(st._h, x.data_ptr(), n, 1, n, None, None, 0, S.data_ptr(), ldp, gstream) == 0
+                assert L.veils_istft_dev(st._h, S.data_ptr(), P, 1, ldp, None, None, y.data_ptr(), k1 - k0, gstream) == 0
+            for _ in range(5):
+                g.replay()
+            gs.synchronize()
+            gl = []
+            for _ in range(50):
+                t0 = time.perf_counter()
+                g.replay()
+                gs.synchronize()
+                gl.append(time.perf_counter() - t0)
+            graph_us = {"median": 1e6 * float(np.median(gl)), "min": 1e6 * float(np.min(gl))}
+    except Exception as ex:                         # noqa: BLE001
+        graph_us = {"error": str(ex)[:120]}
+    torch.cuda.synchronize()
     # wall latency of one synchronous round trip
     lat = []
     for _ in range(50):
@@ -444,8 +471,11 @@ def side_c1(e):
     ey = rel_err(y[0].cpu().numpy(), o.istft(Sref))
     bf, bi = algorithmic_bytes(cfg, 1, n, P, F, k1 - k0)
     return {"workload": "c1: 1 x 44100 @ 44.1 kHz, Hann 2048 / 512 onesided, f64 (latency-bound, 1.8 MB)",
-            "kernel_us": {"stft": us_f, "istft": us_i}, "host_us_per_launch": host_us,
+            "kernel_us": {"stft": us_f, "istft": us_i},
+            "host_us_per_launch": {"inside_library": us_c.value, "through_python_ctypes": host_us,
+                                   "how": "1000 back-to-back veils_stft_dev calls, wall clock / 1000, no sync"},
             "roundtrip_wall_us": {"median": 1e6 * float(np.median(lat)), "min": 1e6 * float(np.min(lat))},
+            "roundtrip_cuda_graph_wall_us": graph_us,
             "roofline": {"bound": "latency", "stft": roof_entry(e, bf, us_f * 1e-3), "istft": roof_entry(e, bi, us_i * 1e-3)},
             "parity": {"stft_rel_err_vs_oracle": es, "istft_rel_err_vs_oracle": ey, "tolerance": 1e-12,
                        "recon_max_abs_err": float(np.max(np.abs(y[0, :n].cpu().numpy() - xh)))},

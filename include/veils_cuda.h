@@ -203,6 +203,9 @@ int32_t veils_stream_sync(void *stream);
 
 /* ---- introspection used by bench.py / the tests ---------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
+/* host-side cost of one veils_stft_dev call in microseconds: `reps` back-to-back calls timed inside the library */
+int32_t veils_debug_launch_cost_us(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch, void *S,
+                                   int64_t ldp, void *stream, int32_t reps, double *us_per_call);
 uint64_t veils_kernel_launch_count(void);
 /* Name of the kernel family the plan dispatches to for forward / inverse
  * ("pow2_tile" | "dft_generic"); static storage. */

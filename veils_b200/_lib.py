@@ -75,6 +75,7 @@ PROTOTYPES = {
     "veils_stream_create": (C.c_int32, [C.c_int32, C.POINTER(_P)]),
     "veils_stream_destroy": (C.c_int32, [_P]),
     "veils_stream_sync": (C.c_int32, [_P]),
+    "veils_debug_launch_cost_us": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.c_int32, _DP]),
     "veils_kernel_launch_count": (C.c_uint64, []),
     "veils_plan_kernel_name": (C.c_char_p, [_P, C.c_int32]),
 }

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -513,6 +514,22 @@ int32_t veils_stft_dev_checked(veils_plan *p, const void *x, int64_t n, int64_t 
     if (!e.empty()) return fail(VEILS_ERR_INVALID, e);
     return nan_check_launch(p->pl, x, n, batch, x_pitch, a, b - a, k_offset, S, ldp, spectrogram ? 1 : 0, nan_flag,
                             (cudaStream_t)stream);
+}
+
+// Host-side cost of one veils_stft_dev call: `reps` back-to-back calls, wall clock / reps, measured inside the
+// library (no binding overhead).  The stream is not synchronised: this is what the caller's thread pays per launch.
+int32_t veils_debug_launch_cost_us(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch, void *S,
+                                   int64_t ldp, void *stream, int32_t reps, double *us_per_call) {
+    if (!us_per_call || reps <= 0) return fail(VEILS_ERR_INVALID, "null argument");
+    int32_t rc = forward_impl(p, x, n, batch, x_pitch, nullptr, nullptr, 0, S, ldp, stream, 0);    // warm: tables, caches
+    if (rc != VEILS_OK) return rc;
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int32_t i = 0; i < reps && rc == VEILS_OK; ++i)
+        rc = forward_impl(p, x, n, batch, x_pitch, nullptr, nullptr, 0, S, ldp, stream, 0);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    *us_per_call = ((double)(t1.tv_sec - t0.tv_sec) * 1e6 + (double)(t1.tv_nsec - t0.tv_nsec) * 1e-3) / reps;
+    return rc;
 }
 
 static int padding_mode(const char *padding) {
