@@ -1,0 +1,62 @@
+"""GPU parity of the mixed-radix kernel family (non-power-of-two mfft with prime factors <= 13) through the
+C ABI, against the oracle: the reference's own 15-point golden geometry, the Hann 400 / hop 160 speech front
+end, mfft > m_num, odd hops, phase shifts, all layouts, f32 and f64; lengths with a larger prime factor
+still run the O(M^2) kernels."""
+import numpy as np
+import pytest
+
+from golden_util import rel_err
+from oracle.stft_oracle import OracleSTFT
+from veils_b200 import StandaloneSTFT
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(15, 8, 15, 0), (400, 160, 400, 0), (50, 10, 60, 3), (21, 4, 63, -5), (9, 3, 441, 2), (30, 6, 1000, 0),
+         (600, 150, 600, 0), (33, 7, 33, 0)]
+
+
+@pytest.mark.parametrize("m,hop,mfft,ps", CASES)
+@pytest.mark.parametrize("mode", ["onesided", "twosided", "centered", "onesided2X"])
+@pytest.mark.parametrize("prec,tol", [("f64", 1e-12), ("f32", 2e-5)])
+def test_mixed_radix_matches_oracle(m, hop, mfft, ps, mode, prec, tol):
+    rng = np.random.default_rng(m * 11 + hop)
+    win = 0.5 * (1 - np.cos(2 * np.pi * (np.arange(m) + 0.5) / m)) + 0.05
+    o = OracleSTFT(win, hop, 1000.0, fft_mode=mode, mfft=mfft, phase_shift=ps)
+    st = StandaloneSTFT(win, hop, 1000.0, fft_mode=mode, mfft=mfft, phase_shift=ps, precision=prec)
+    assert st.kernel_name() == "mixed_radix" and st.kernel_name(True) == "mixed_radix"
+    n = 150 * hop + m + 5
+    x = rng.uniform(-1, 1, (3, n)).astype(np.float32 if prec == "f32" else np.float64)
+    S = st.stft(x)
+    ref = np.stack([o.stft(r.astype(np.float64)) for r in x])
+    assert S.shape == ref.shape and rel_err(S, ref) <= tol
+    assert rel_err(st.stft(x[1], 2, 40, k_offset=3), o.stft(x[1].astype(np.float64), 2, 40, 3)) <= tol
+    assert rel_err(st.spectrogram(x[2]), o.spectrogram(x[2].astype(np.float64))) <= 2 * tol
+    y = st.istft(S)
+    assert rel_err(y, np.stack([o.istft(s.astype(np.complex128)) for s in S])) <= tol
+    assert np.max(np.abs(y[:, :n] - x)) <= 50 * tol
+    y2 = st.istft(S[0], hop + 1, n - 3)
+    assert np.array_equal(y2, y[0, hop + 1:n - 3])                  # same summation order -> same bits
+
+
+def test_large_prime_factors_stay_on_the_generic_kernels():
+    win = np.hanning(34)[1:-1] + 0.1
+    for mfft in (34, 38, 62):                                       # 17, 19, 31
+        st = StandaloneSTFT(win[:32], 8, 1.0, mfft=mfft, precision="f64")
+        assert st.kernel_name() == "dft_generic"
+        o = OracleSTFT(win[:32], 8, 1.0, mfft=mfft)
+        x = np.random.default_rng(mfft).standard_normal(500)
+        assert rel_err(st.stft(x), o.stft(x)) <= 1e-12
+
+
+def test_device_tensors_and_determinism_400_160():
+    import torch
+    win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(400) / 400))
+    st = StandaloneSTFT(win, 160, 16000.0, precision="f32")
+    o = OracleSTFT(win, 160, 16000.0)
+    x = torch.rand((64, 160000), device="cuda", dtype=torch.float32) * 2 - 1
+    S = st.stft(x)
+    assert torch.equal(S, st.stft(x))
+    assert rel_err(S[63].cpu().numpy(), o.stft(x[63].double().cpu().numpy())) <= 2e-5
+    y = st.istft(S)
+    assert torch.equal(y, st.istft(S))
+    assert float((y[:, :160000] - x).abs().max()) <= 1e-5

@@ -17,6 +17,9 @@ CASES = [
     ("f32 1024/256 onesided B=512x160000", hann(1024), 256, "onesided", None, "f32", 512, 160000, False),
     ("f32 2048/512 onesided B=256x480000", hann(2048), 512, "onesided", None, "f32", 256, 480000, False),
     ("f32 256/64 onesided B=1024x160000", hann(256), 64, "onesided", None, "f32", 1024, 160000, False),
+    ("f32 400/160 onesided B=1024x160000", hann(400), 160, "onesided", None, "f32", 1024, 160000, False),
+    ("f64 400/160 onesided B=256x160000", hann(400), 160, "onesided", None, "f64", 256, 160000, False),
+    ("f32 1000/250 onesided B=256x160000", hann(1000), 250, "onesided", None, "f32", 256, 160000, False),
 ]
 ALIGN = "--align" in sys.argv      # pad S rows to 128-byte lines (what veils_b200.stft does for device tensors)
 sel = [a for a in sys.argv[1:] if not a.startswith("--")]

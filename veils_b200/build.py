@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libveils_cuda.so")
 CLI = os.path.join(HERE, "veils_comparison_helper")          # csrc/cli/comparison_helper.cpp
 SOURCES = ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu", "pad.cu", "detrend.cu",
-           "wide_fwd.cu", "wide_inv.cu"]
+           "wide_fwd.cu", "wide_inv.cu", "smooth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas", "--use_fast_math=false"]
 

@@ -30,6 +30,7 @@ struct DeviceTables {
     float *tw_pk_inv = nullptr;
     void *ptab_pk = nullptr;
     void *itab_pk = nullptr;
+    void *tw_smooth = nullptr;    // mixed-radix twiddles (smooth_impl.cuh)
     float *wide_fwd = nullptr;    // wide family tables (wide_impl.cuh)
     float *wide_inv = nullptr;
     void *detr_w = nullptr;       // [2][F] complex: fft_func(win * 1), fft_func(win * i)  (detrending)
@@ -156,12 +157,17 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 if (e == cudaSuccess) e = cudaMemcpy(d->ptab_pk, pt.data(), pt.size(), cudaMemcpyHostToDevice);
             }
         }
+        if (e == cudaSuccess && (pl.smooth_fwd || pl.smooth_inv)) {
+            std::vector<double> tw((size_t)smooth_twiddle_count(pl.M));
+            smooth_twiddle_fill(pl.M, tw.data());
+            e = upload_prec(pl, tw, &d->tw_smooth);
+        }
         if (e == cudaSuccess && pl.wide) {
             std::vector<double> tw((size_t)wide_table_floats(pl.M));
             wide_table_fill_host(pl.M, pl.wide_tf, false, pl.win.data(), 0.5, tw.data());
             e = upload_as<float>(tw, (void **)&d->wide_fwd);
         }
-        if (e == cudaSuccess && !((pl.pow2_fwd || pl.pk_fwd) && (pl.pow2_inv || pl.pk_inv))) {
+        if (e == cudaSuccess && !((pl.pow2_fwd || pl.pk_fwd || pl.smooth_fwd) && (pl.pow2_inv || pl.pk_inv || pl.smooth_inv))) {
             std::vector<double> tw((size_t)pl.M * 2);
             for (int64_t m = 0; m < pl.M; ++m) twiddle(m, pl.M, &tw[2 * m], &tw[2 * m + 1]);
             e = cudaMalloc((void **)&d->tw_full, tw.size() * sizeof(double));
@@ -169,7 +175,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) {
-            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk); cudaFree(d->wide_fwd);
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk); cudaFree(d->wide_fwd); cudaFree(d->tw_smooth);
             delete d;
             return cuda_fail(e, "upload plan tables");
         }
@@ -233,6 +239,7 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.tw_pk_inv = pl.dev->tw_pk_inv;
     tb.ptab_pk = pl.dev->ptab_pk;
     tb.itab_pk = pl.dev->itab_pk;
+    tb.tw_smooth = (const T *)pl.dev->tw_smooth;
     tb.wide_fwd = pl.dev->wide_fwd;
     tb.wide_inv = pl.dev->wide_inv;
     return tb;
@@ -269,6 +276,13 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         pl.wide = !force_generic && pl.precision == F32 && getenv("VEILS_NO_WIDE") == nullptr &&
                   wide_supported(pl.M, pl.N, pl.H, pl.ps);
         pl.wide_tf = pl.wide ? wide_tf(pl.M) : 0;
+        // lengths the power-of-two families do not take: mixed radix (prime factors <= 13, <= 4 passes) before
+        // the O(M^2) kernels
+        const bool no_smooth = getenv("VEILS_NO_SMOOTH") != nullptr;
+        pl.smooth_fwd = !force_generic && !no_smooth && !pl.pow2_fwd && !pl.pk_fwd && !pl.wide &&
+                        smooth_supported(pl.M, pl.N, pl.H, pl.precision, false);
+        pl.smooth_inv = !force_generic && !no_smooth && !pl.pow2_inv && !pl.pk_inv && !pl.wide_inv &&
+                        smooth_supported(pl.M, pl.N, pl.H, pl.precision, true);
         // two-sided inverse: two rows per bin, no tensor-map landing yet -> the packed family is faster there
         // (measured c4: 49 % vs 27 % of the roofline); VEILS_WIDE_INV_ALL=1 forces the wide kernels
         pl.wide_inv = pl.wide && (pl.mode >= ONESIDED || !pl.pk_inv || getenv("VEILS_WIDE_INV_ALL") != nullptr);
@@ -294,6 +308,7 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->itab_pk);
         cudaFree(p->pl.dev->wide_fwd);
         cudaFree(p->pl.dev->wide_inv);
+        cudaFree(p->pl.dev->tw_smooth);
         delete p->pl.dev;
     }
     cudaSetDevice(p->pl.device);
@@ -477,10 +492,12 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
         ce = pl.wide ? wide_forward((const float *)x, out, prm, tb.wide_fwd, pl.wide_tf, st)
              : pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
              : pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
+             : pl.smooth_fwd ? smooth_forward<float>((const float *)x, out, prm, tb.win, tb.tw_smooth, st)
                            : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_fwd ? pow2_forward<double>((const double *)x, out, prm, tb, st)
+             : pl.smooth_fwd ? smooth_forward<double>((const double *)x, out, prm, tb.win, tb.tw_smooth, st)
                           : dft_generic_forward<double>((const double *)x, out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "stft launch");
@@ -708,10 +725,12 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
         ce = pl.wide_inv ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, pl.wide_tf, st)
              : pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
              : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
+             : pl.smooth_inv ? smooth_inverse<float>(S, (float *)x_out, prm, tb.dual_scaled, tb.tw_smooth, st)
                            : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_inv ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
+             : pl.smooth_inv ? smooth_inverse<double>(S, (double *)x_out, prm, tb.dual_scaled, tb.tw_smooth, st)
                           : dft_generic_inverse<double>(S, (double *)x_out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "istft launch");
@@ -955,7 +974,8 @@ uint64_t veils_kernel_launch_count(void) { return (uint64_t)g_launch_count.load(
 const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse) {
     if (inverse ? p->pl.wide_inv : p->pl.wide) return "pow2_wide";
     if (inverse ? p->pl.pk_inv : p->pl.pk_fwd) return "pow2_packed";
-    return (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) ? "pow2_tile" : "dft_generic";
+    if (inverse ? p->pl.pow2_inv : p->pl.pow2_fwd) return "pow2_tile";
+    return (inverse ? p->pl.smooth_inv : p->pl.smooth_fwd) ? "mixed_radix" : "dft_generic";
 }
 
 }  // extern "C"

@@ -54,6 +54,8 @@ struct Plan {
     bool pk_fwd = false;      // packed f32 family (preferred over pow2 when available)
     bool pk_inv = false;
     bool wide = false;        // wide f32 family (mfft 1024 / 2048 / 4096, default geometry): forward
+    bool smooth_fwd = false;  // mixed-radix family (non-power-of-two mfft with prime factors <= 13)
+    bool smooth_inv = false;
     int wide_tf = 0;          // slices per tile of the wide kernels, fixed at plan creation
     bool wide_inv = false;    // ... and inverse (one-sided layouts; two-sided ones stay with the packed family)
 };
