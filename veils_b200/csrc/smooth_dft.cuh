@@ -18,8 +18,13 @@ using p2::mk;
 
 // ---- constexpr sine / cosine of 2 pi m / n: reduction to [-pi/2, pi/2], 16-term Taylor series
 // (error < 1e-18), exact values on the axes
+#if defined(__CUDACC__)
+#define VCX __host__ __device__ constexpr
+#else
+#define VCX constexpr
+#endif
 constexpr double kPi = 3.14159265358979323846264338327950288;
-constexpr double sin_series(double x) {
+VCX double sin_series(double x) {
     const double x2 = x * x;
     double term = x, sum = x;
     for (int i = 1; i < 16; ++i) {
@@ -28,7 +33,7 @@ constexpr double sin_series(double x) {
     }
     return sum;
 }
-constexpr double cos_series(double x) {
+VCX double cos_series(double x) {
     const double x2 = x * x;
     double term = 1.0, sum = 1.0;
     for (int i = 1; i < 16; ++i) {
@@ -37,20 +42,35 @@ constexpr double cos_series(double x) {
     }
     return sum;
 }
-constexpr int mod_pos(int m, int n) { return ((m % n) + n) % n; }
-constexpr double cos2pi(int m, int n) {
+VCX int mod_pos(int m, int n) { return ((m % n) + n) % n; }
+VCX double cos2pi(int m, int n) {
     m = mod_pos(m, n);
     if ((4 * m) % n == 0) { const int q = 4 * m / n; return q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0); }
     if (2 * m > n) m = n - m;                               // cos is even around pi
     if (4 * m > n) return -cos_series(kPi - 2.0 * kPi * m / n);   // second quadrant
     return cos_series(2.0 * kPi * m / n);
 }
-constexpr double sin2pi(int m, int n) {
+VCX double sin2pi(int m, int n) {
     m = mod_pos(m, n);
     if ((4 * m) % n == 0) { const int q = 4 * m / n; return q == 1 ? 1.0 : (q == 3 ? -1.0 : 0.0); }
     if (2 * m > n) return -sin2pi(n - m, n);                // sin is odd around pi
     if (4 * m > n) return sin_series(kPi - 2.0 * kPi * m / n);
     return sin_series(2.0 * kPi * m / n);
+}
+
+// cos / sin of 2 pi m / R for m = 0 .. R-1 as a compile-time table: a `constexpr` local object of this
+// type is evaluated by the front end (host and device alike), and after unrolling every index is a
+// literal -- the butterflies multiply by immediates
+template <int R> struct Trig {
+    double c[R], s[R];
+};
+template <int R> VCX Trig<R> make_trig() {
+    Trig<R> t{};
+    for (int m = 0; m < R; ++m) {
+        t.c[m] = cos2pi(m, R);
+        t.s[m] = sin2pi(m, R);
+    }
+    return t;
 }
 
 // a * (c - i s) forward, a * (c + i s) inverse, c / s compile-time
@@ -70,6 +90,7 @@ template <bool INV, typename T> struct Dft<16, INV, T> { VHD static void run(cx<
 template <int R, bool INV, typename T> struct DftOdd {
     VHD static void run(cx<T> (&v)[R]) {
         constexpr int H = (R - 1) / 2;
+        constexpr Trig<R> tt = make_trig<R>();
         cx<T> s[H], d[H];
 #pragma unroll
         for (int n = 1; n <= H; ++n) {
@@ -85,7 +106,7 @@ template <int R, bool INV, typename T> struct DftOdd {
             T ar = v[0].x, ai = v[0].y, br = 0, bi = 0;
 #pragma unroll
             for (int n = 1; n <= H; ++n) {
-                const T c = (T)cos2pi(n * k, R), sn = (T)sin2pi(n * k, R);
+                const T c = (T)tt.c[(n * k) % R], sn = (T)tt.s[(n * k) % R];
                 ar += s[n - 1].x * c;
                 ai += s[n - 1].y * c;
                 br += d[n - 1].x * sn;
@@ -110,6 +131,7 @@ template <bool INV, typename T> struct Dft<13, INV, T> { VHD static void run(cx<
 // Cooley-Tukey A x B: n = B n1 + n2, k = k1 + A k2
 template <int A, int B, bool INV, typename T> struct DftComp {
     VHD static void run(cx<T> (&v)[A * B]) {
+        constexpr Trig<A * B> tt = make_trig<A * B>();
         cx<T> t[B][A];
 #pragma unroll
         for (int n2 = 0; n2 < B; ++n2) {
@@ -119,7 +141,7 @@ template <int A, int B, bool INV, typename T> struct DftComp {
             Dft<A, INV, T>::run(u);
 #pragma unroll
             for (int k1 = 0; k1 < A; ++k1)
-                t[n2][k1] = (n2 * k1 == 0) ? u[k1] : mulw<INV>(u[k1], cos2pi(n2 * k1, A * B), sin2pi(n2 * k1, A * B));
+                t[n2][k1] = (n2 * k1 == 0) ? u[k1] : mulw<INV>(u[k1], tt.c[(n2 * k1) % (A * B)], tt.s[(n2 * k1) % (A * B)]);
         }
 #pragma unroll
         for (int k1 = 0; k1 < A; ++k1) {
