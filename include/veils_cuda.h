@@ -207,8 +207,9 @@ int32_t veils_stream_sync(void *stream);
 int32_t veils_debug_launch_cost_us(veils_plan *p, const void *x, int64_t n, int64_t batch, int64_t x_pitch, void *S,
                                    int64_t ldp, void *stream, int32_t reps, double *us_per_call);
 uint64_t veils_kernel_launch_count(void);
-/* Name of the kernel family the plan dispatches to for forward / inverse
- * ("pow2_tile" | "dft_generic"); static storage. */
+/* Name of the kernel family the plan dispatches to for forward / inverse: "pow2_wide" (f32, mfft 1024 / 2048 /
+ * 4096, m_num = mfft = 4 hop) | "pow2_packed" (f32 powers of two) | "pow2_tile" (f32 / f64 powers of two) |
+ * "mixed_radix" (any mfft = product of <= 4 radices 2 .. 16) | "dft_generic" (everything else); static storage. */
 const char *veils_plan_kernel_name(const veils_plan *p, int32_t inverse);
 
 #ifdef __cplusplus
