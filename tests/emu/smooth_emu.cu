@@ -12,37 +12,29 @@ using namespace veils;
 using namespace veils::sm;
 namespace veils { std::atomic<unsigned long long> g_launch_count{0}; }
 
-template <typename T> static std::vector<cx<T>> tw_table(const Shape &s) {
-    std::vector<double> d((size_t)(2 * twiddle_entries(s)));
-    twiddle_fill(s, d.data());
-    std::vector<cx<T>> t(d.size() / 2);
-    for (size_t i = 0; i < t.size(); ++i) t[i] = mk<T>((T)d[2 * i], (T)d[2 * i + 1]);
-    return t;
-}
-
 template <typename T, int TF>
 static int emu_fwd(const T *x, int64_t n, int64_t batch, const double *win, int64_t M, int64_t N, int64_t H, int64_t F,
                    int64_t ps, int64_t mid, int64_t p0, int64_t P, int64_t k_offset, int mode, double fac2x, int spec,
                    void *out, int64_t ldp) {
     FwdArgs<T> a;
     if (!make_shape(M, N, H, F, ps, &a.s)) return 2;
-    std::vector<cx<T>> tw = tw_table<T>(a.s);
-    std::vector<T> w(win, win + N);
-    a.x = x; a.out = out; a.win = w.data(); a.tw = tw.data();
+    a.lay = tab_layout<T>(a.s, false);
+    std::vector<unsigned char> blob((size_t)a.lay.bytes);
+    tab_fill<T>(a.s, false, win, blob.data());
+    a.x = x; a.out = out; a.tab = blob.data();
     a.n = n; a.x_pitch = n; a.ldp = ldp; a.p0 = p0; a.P = P; a.k_offset = k_offset; a.ptiles = (P + TF - 1) / TF;
-    a.mid = (int)mid; a.mode = mode; a.spectrogram = spec; a.xpad = (H % 2 == 0) ? 1 : 0; a.fac2x = (T)fac2x;
+    a.mid = (int)mid; a.mode = mode; a.spectrogram = spec; a.xpad = xpad_of(H); a.fac2x = (T)fac2x;
     const int NT = 64;
     const int64_t span = (int64_t)(TF - 1) * H + N;
-    std::vector<cx<T>> work((size_t)M * TF);
-    std::vector<T> xin((size_t)(span + span / H + 8));
+    std::vector<cx<vec_t<T>>> work((size_t)a.s.LC * TF / Vec<T>::W);
+    std::vector<T> xin((size_t)(((span + H - 1) / H) * (H + a.xpad) + 4));
     FwdCtx<T> c;
-    c.a = &a; c.work = work.data(); c.xin = xin.data();
+    c.a = &a; c.tab = blob.data(); c.work = work.data(); c.xin = xin.data();
     for (int64_t blk = 0; blk < a.ptiles * batch; ++blk) {
         c.b = blk / a.ptiles; c.pt = blk % a.ptiles;
-        for (auto &v : work) v = mk<T>((T)NAN, (T)NAN);
+        for (auto &v : work) v = mk<vec_t<T>>(Vec<T>::bc((T)NAN), Vec<T>::bc((T)NAN));
         for (auto &v : xin) v = (T)NAN;
         for (int t = 0; t < NT; ++t) Fwd<T, TF>::stage(c, t, NT);
-        for (int t = 0; t < NT; ++t) Fwd<T, TF>::load(c, t, NT);
         for (int p = 0; p < a.s.np; ++p)
             for (int t = 0; t < NT; ++t) Fwd<T, TF>::pass(c, p, t, NT);
         for (int t = 0; t < NT; ++t) Fwd<T, TF>::store(c, t, NT);
@@ -58,10 +50,12 @@ static int emu_inv(const void *S, int64_t P, int64_t ldp, int64_t batch, const d
     if (!make_shape(M, N, H, F, ps, &a.s)) return 2;
     a.halo = (int)((N + H - 1) / H) - 1;
     if (a.halo >= TF) return 2;
-    std::vector<cx<T>> tw = tw_table<T>(a.s);
-    std::vector<T> d(N);
-    for (int64_t i = 0; i < N; ++i) d[i] = (T)(dual[i] / ((double)M * (mode >= 2 ? 1.0 : 2.0)));
-    a.S = S; a.xo = xo; a.dual = d.data(); a.tw = tw.data();
+    std::vector<double> d(N);
+    for (int64_t i = 0; i < N; ++i) d[i] = dual[i] / ((double)M * (mode >= 2 ? 1.0 : 2.0));
+    a.lay = tab_layout<T>(a.s, true);
+    std::vector<unsigned char> blob((size_t)a.lay.bytes);
+    tab_fill<T>(a.s, true, d.data(), blob.data());
+    a.S = S; a.xo = xo; a.tab = blob.data();
     a.P = P; a.ldp = ldp; a.out_pitch = out_pitch; a.p_min = p_min; a.k0 = k0; a.k1 = k1; a.q0 = q0; a.q1 = q1;
     a.mid = (int)mid; a.mode = mode; a.ostride = (int)(N | 1); a.rfac2x = (T)(1.0 / fac2x);
     const int own = TF - a.halo;
@@ -69,18 +63,17 @@ static int emu_inv(const void *S, int64_t P, int64_t ldp, int64_t batch, const d
     a.ntiles = (qh1 - qh0 + 1 + own - 1) / own;
     a.qa0 = qh0 - a.halo;
     const int NT = 64;
-    std::vector<cx<T>> work((size_t)M * TF);
-    std::vector<T> ola((size_t)TF * (a.ostride + 1));
+    std::vector<cx<vec_t<T>>> work((size_t)a.s.LC * TF / Vec<T>::W);
+    std::vector<T> ola((size_t)TF * a.ostride);
     InvCtx<T> c;
-    c.a = &a; c.work = work.data(); c.ola = ola.data();
+    c.a = &a; c.tab = blob.data(); c.work = work.data(); c.ola = ola.data();
     for (int64_t blk = 0; blk < a.ntiles * batch; ++blk) {
         c.b = blk / a.ntiles; c.qa = a.qa0 + (blk % a.ntiles) * own;
-        for (auto &v : work) v = mk<T>((T)NAN, (T)NAN);
+        for (auto &v : work) v = mk<vec_t<T>>(Vec<T>::bc((T)NAN), Vec<T>::bc((T)NAN));
         for (auto &v : ola) v = (T)NAN;
         for (int t = 0; t < NT; ++t) Inv<T, TF>::load(c, t, NT);
         for (int p = 0; p < a.s.np; ++p)
             for (int t = 0; t < NT; ++t) Inv<T, TF>::pass(c, p, t, NT);
-        for (int t = 0; t < NT; ++t) Inv<T, TF>::rows(c, t, NT);
         for (int t = 0; t < NT; ++t) Inv<T, TF>::gather(c, t, NT);
     }
     return 0;
@@ -97,11 +90,12 @@ int smooth_emu_factors(int64_t M, int *np, int *R) {
 // in-register DFT of length R (2 .. 16) on interleaved complex doubles
 int smooth_emu_dft(int R, int inverse, double *re_im) {
     cx<double> w[16 * 1];
-    Shape s;
-    if (R < 2 || R > 16 || !make_shape(R, R, 1, R, 0, &s)) return 0;
+    if (R < 2 || R > 16) return 0;
     for (int i = 0; i < R; ++i) w[i] = mk<double>(re_im[2 * i], re_im[2 * i + 1]);
-    if (inverse) pass_any<double, 1, true>(R, w, nullptr, 1, R, 0, 1);
-    else pass_any<double, 1, false>(R, w, nullptr, 1, R, 0, 1);
+    PassIO<double> io;
+    io.work = w; io.xin = nullptr; io.lt = nullptr; io.hp = 0; io.ola = nullptr; io.rt = nullptr; io.ostride = 0; io.half = 0;
+    if (inverse) pass_any<double, 1, true, 0>(R, io, nullptr, 1, 0u, 1, 0, 1);
+    else pass_any<double, 1, false, 0>(R, io, nullptr, 1, 0u, 1, 0, 1);
     for (int i = 0; i < R; ++i) { re_im[2 * i] = w[i].x; re_im[2 * i + 1] = w[i].y; }
     return 1;
 }

@@ -86,6 +86,8 @@ def run_inv(emu, o, prec, S, k0=None, k1=None):
 CASES = [  # m_num, hop, mfft, phase_shift
     (15, 8, 15, 0), (400, 160, 400, 0), (50, 10, 60, 3), (21, 4, 63, -5), (100, 25, 100, 0), (33, 7, 33, 0),
     (9, 3, 441, 2), (30, 6, 1000, 0), (12, 5, 26, 0),
+    # even mfft = half-length transform + split: single-pass halves, odd halves, odd rolls, mfft = 2 (no half)
+    (4, 2, 4, 0), (6, 2, 6, 1), (30, 10, 30, 0), (20, 5, 882, 7), (2, 1, 2, 0), (14, 3, 18, -3), (320, 160, 320, 0),
 ]
 
 

@@ -30,7 +30,8 @@ struct DeviceTables {
     float *tw_pk_inv = nullptr;
     void *ptab_pk = nullptr;
     void *itab_pk = nullptr;
-    void *tw_smooth = nullptr;    // mixed-radix twiddles (smooth_impl.cuh)
+    void *smooth_fwd = nullptr;   // mixed-radix plan blobs (smooth_impl.cuh)
+    void *smooth_inv = nullptr;
     float *wide_fwd = nullptr;    // wide family tables (wide_impl.cuh)
     float *wide_inv = nullptr;
     void *detr_w = nullptr;       // [2][F] complex: fft_func(win * 1), fft_func(win * i)  (detrending)
@@ -157,10 +158,11 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 if (e == cudaSuccess) e = cudaMemcpy(d->ptab_pk, pt.data(), pt.size(), cudaMemcpyHostToDevice);
             }
         }
-        if (e == cudaSuccess && (pl.smooth_fwd || pl.smooth_inv)) {
-            std::vector<double> tw((size_t)smooth_twiddle_count(pl.M));
-            smooth_twiddle_fill(pl.M, tw.data());
-            e = upload_prec(pl, tw, &d->tw_smooth);
+        if (e == cudaSuccess && pl.smooth_fwd) {
+            std::vector<unsigned char> blob((size_t)smooth_table_bytes(pl.M, pl.N, pl.H, pl.ps, pl.precision == F32 ? 0 : 1, false));
+            smooth_table_fill(pl.M, pl.N, pl.H, pl.ps, pl.precision == F32 ? 0 : 1, false, pl.win.data(), blob.data());
+            e = cudaMalloc(&d->smooth_fwd, blob.size());
+            if (e == cudaSuccess) e = cudaMemcpy(d->smooth_fwd, blob.data(), blob.size(), cudaMemcpyHostToDevice);
         }
         if (e == cudaSuccess && pl.wide) {
             std::vector<double> tw((size_t)wide_table_floats(pl.M));
@@ -175,7 +177,7 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
                 e = cudaMemcpy(d->tw_full, tw.data(), tw.size() * sizeof(double), cudaMemcpyHostToDevice);
         }
         if (e != cudaSuccess) {
-            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk); cudaFree(d->wide_fwd); cudaFree(d->tw_smooth);
+            cudaFree(d->win); cudaFree(d->win_half); cudaFree(d->tw_pow2); cudaFree(d->tw_full); cudaFree(d->tw_pk); cudaFree(d->tw_pk_inv); cudaFree(d->ptab_pk); cudaFree(d->wide_fwd); cudaFree(d->smooth_fwd);
             delete d;
             return cuda_fail(e, "upload plan tables");
         }
@@ -203,10 +205,20 @@ static int32_t ensure_device(Plan &pl, bool need_dual) {
             wide_table_fill_host(pl.M, pl.wide_tf, true, pl.dual.data(), sc, tw.data());
             e = upload_as<float>(tw, (void **)&wide_inv);
         }
+        void *smooth_inv = nullptr;
+        if (e == cudaSuccess && pl.smooth_inv) {
+            std::vector<double> ds(pl.dual);
+            for (double &v : ds) v *= sc;
+            std::vector<unsigned char> blob((size_t)smooth_table_bytes(pl.M, pl.N, pl.H, pl.ps, pl.precision == F32 ? 0 : 1, true));
+            smooth_table_fill(pl.M, pl.N, pl.H, pl.ps, pl.precision == F32 ? 0 : 1, true, ds.data(), blob.data());
+            e = cudaMalloc(&smooth_inv, blob.size());
+            if (e == cudaSuccess) e = cudaMemcpy(smooth_inv, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) {
-            cudaFree(dual); cudaFree(dual_scaled); cudaFree(itab); cudaFree(wide_inv);
+            cudaFree(dual); cudaFree(dual_scaled); cudaFree(itab); cudaFree(wide_inv); cudaFree(smooth_inv);
             return cuda_fail(e, "upload dual window");
         }
+        pl.dev->smooth_inv = smooth_inv;
         pl.dev->dual_scaled = dual_scaled;
         pl.dev->itab_pk = itab;
         pl.dev->wide_inv = wide_inv;
@@ -239,7 +251,8 @@ static Tables<T> tables_of(const Plan &pl) {
     tb.tw_pk_inv = pl.dev->tw_pk_inv;
     tb.ptab_pk = pl.dev->ptab_pk;
     tb.itab_pk = pl.dev->itab_pk;
-    tb.tw_smooth = (const T *)pl.dev->tw_smooth;
+    tb.smooth_fwd = pl.dev->smooth_fwd;
+    tb.smooth_inv = pl.dev->smooth_inv;
     tb.wide_fwd = pl.dev->wide_fwd;
     tb.wide_inv = pl.dev->wide_inv;
     return tb;
@@ -279,13 +292,20 @@ int32_t veils_plan_create(const veils_plan_desc *d, veils_plan **out) {
         // lengths the power-of-two families do not take: mixed radix (prime factors <= 13, <= 4 passes) before
         // the O(M^2) kernels
         const bool no_smooth = getenv("VEILS_NO_SMOOTH") != nullptr;
+        // VEILS_PREFER_SMOOTH: 1 = every precision, 2 = f64 only (measurement switch: the mixed-radix family also
+        // takes powers of two)
+        const char *pref = getenv("VEILS_PREFER_SMOOTH");
+        if (!force_generic && !no_smooth && pref && (pref[0] == '1' || (pref[0] == '2' && pl.precision != F32))) {
+            if (smooth_supported(pl.M, pl.N, pl.H, pl.precision, false)) { pl.pow2_fwd = pl.pk_fwd = pl.wide = false; pl.wide_tf = 0; }
+            if (smooth_supported(pl.M, pl.N, pl.H, pl.precision, true)) { pl.pow2_inv = pl.pk_inv = false; }
+        }
         pl.smooth_fwd = !force_generic && !no_smooth && !pl.pow2_fwd && !pl.pk_fwd && !pl.wide &&
                         smooth_supported(pl.M, pl.N, pl.H, pl.precision, false);
         pl.smooth_inv = !force_generic && !no_smooth && !pl.pow2_inv && !pl.pk_inv && !pl.wide_inv &&
                         smooth_supported(pl.M, pl.N, pl.H, pl.precision, true);
         // two-sided inverse: two rows per bin, no tensor-map landing yet -> the packed family is faster there
         // (measured c4: 49 % vs 27 % of the roofline); VEILS_WIDE_INV_ALL=1 forces the wide kernels
-        pl.wide_inv = pl.wide && (pl.mode >= ONESIDED || !pl.pk_inv || getenv("VEILS_WIDE_INV_ALL") != nullptr);
+        pl.wide_inv = pl.wide && !pl.smooth_inv && (pl.mode >= ONESIDED || !pl.pk_inv || getenv("VEILS_WIDE_INV_ALL") != nullptr);
     }
     *out = p;
     return VEILS_OK;
@@ -308,7 +328,8 @@ void veils_plan_destroy(veils_plan *p) {
         cudaFree(p->pl.dev->itab_pk);
         cudaFree(p->pl.dev->wide_fwd);
         cudaFree(p->pl.dev->wide_inv);
-        cudaFree(p->pl.dev->tw_smooth);
+        cudaFree(p->pl.dev->smooth_fwd);
+        cudaFree(p->pl.dev->smooth_inv);
         delete p->pl.dev;
     }
     cudaSetDevice(p->pl.device);
@@ -492,12 +513,12 @@ static int32_t forward_impl(veils_plan *p, const void *x, int64_t n, int64_t bat
         ce = pl.wide ? wide_forward((const float *)x, out, prm, tb.wide_fwd, pl.wide_tf, st)
              : pl.pk_fwd ? pk_forward((const float *)x, out, prm, tb, st)
              : pl.pow2_fwd ? pow2_forward<float>((const float *)x, out, prm, tb, st)
-             : pl.smooth_fwd ? smooth_forward<float>((const float *)x, out, prm, tb.win, tb.tw_smooth, st)
+             : pl.smooth_fwd ? smooth_forward<float>((const float *)x, out, prm, tb.smooth_fwd, st)
                            : dft_generic_forward<float>((const float *)x, out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_fwd ? pow2_forward<double>((const double *)x, out, prm, tb, st)
-             : pl.smooth_fwd ? smooth_forward<double>((const double *)x, out, prm, tb.win, tb.tw_smooth, st)
+             : pl.smooth_fwd ? smooth_forward<double>((const double *)x, out, prm, tb.smooth_fwd, st)
                           : dft_generic_forward<double>((const double *)x, out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "stft launch");
@@ -725,12 +746,12 @@ int32_t veils_istft_dev(veils_plan *p, const void *S, int64_t P, int64_t batch, 
         ce = pl.wide_inv ? wide_inverse(S, (float *)x_out, prm, tb.wide_inv, pl.wide_tf, st)
              : pl.pk_inv ? pk_inverse(S, (float *)x_out, prm, tb, st)
              : pl.pow2_inv ? pow2_inverse<float>(S, (float *)x_out, prm, tb, st)
-             : pl.smooth_inv ? smooth_inverse<float>(S, (float *)x_out, prm, tb.dual_scaled, tb.tw_smooth, st)
+             : pl.smooth_inv ? smooth_inverse<float>(S, (float *)x_out, prm, tb.smooth_inv, st)
                            : dft_generic_inverse<float>(S, (float *)x_out, prm, tb, st);
     } else {
         Tables<double> tb = tables_of<double>(pl);
         ce = pl.pow2_inv ? pow2_inverse<double>(S, (double *)x_out, prm, tb, st)
-             : pl.smooth_inv ? smooth_inverse<double>(S, (double *)x_out, prm, tb.dual_scaled, tb.tw_smooth, st)
+             : pl.smooth_inv ? smooth_inverse<double>(S, (double *)x_out, prm, tb.smooth_inv, st)
                           : dft_generic_inverse<double>(S, (double *)x_out, prm, tb, st);
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "istft launch");

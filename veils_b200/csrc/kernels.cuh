@@ -41,7 +41,8 @@ struct Tables {
     const float *tw_pk_inv = nullptr;   // packed-f32 inverse twiddles
     const void *ptab_pk = nullptr;      // packed-f32 tile table [M/2] x 16 bytes
     const void *itab_pk = nullptr;      // packed-f32 inverse table [M/2] x 16 bytes
-    const T *tw_smooth = nullptr;       // mixed-radix family: per-pass twiddles (layout: smooth_impl.cuh)
+    const void *smooth_fwd = nullptr;   // mixed-radix family: plan blobs (layout: smooth_impl.cuh)
+    const void *smooth_inv = nullptr;
     const float *wide_fwd = nullptr;    // wide family: forward table (layout: wide_impl.cuh)
     const float *wide_inv = nullptr;    // wide family: inverse table
 };
@@ -90,12 +91,14 @@ cudaError_t wide_inverse(const void *S, float *x_out, const InvParams &prm, cons
 
 // ---- mixed-radix family: any mfft = product of <= 4 radices 2 .. 16, f32 / f64 (smooth.cu) ------------
 bool smooth_supported(int64_t M, int64_t N, int64_t H, int precision, bool inverse);
-int64_t smooth_twiddle_count(int64_t M);                  // doubles (re, im pairs)
-void smooth_twiddle_fill(int64_t M, double *re_im);
+// plan blob of one direction (twiddles + load / split / row tables; layout: smooth_impl.cuh) in the plan's precision;
+// vec_n = the window (forward) or the dual window scaled by 1/M resp. 1/(2M) (inverse)
+int64_t smooth_table_bytes(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse);
+void smooth_table_fill(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse, const double *vec_n, void *out);
 template <typename T>
-cudaError_t smooth_forward(const T *x, void *out, const FwdParams &prm, const T *win, const T *tw, cudaStream_t st);
+cudaError_t smooth_forward(const T *x, void *out, const FwdParams &prm, const void *tab, cudaStream_t st);
 template <typename T>
-cudaError_t smooth_inverse(const void *S, T *x_out, const InvParams &prm, const T *dual_scaled, const T *tw, cudaStream_t st);
+cudaError_t smooth_inverse(const void *S, T *x_out, const InvParams &prm, const void *tab, cudaStream_t st);
 
 // ---- border extension for the twin's padding modes (pad.cu): mode 0 zeros, 1 edge, 2 even, 3 odd
 template <typename T>

@@ -10,94 +10,145 @@ using namespace sm;
 constexpr int SM_NT = 256;
 constexpr size_t SM_SMEM_LIMIT = 227 * 1024;
 
+// cooperative copy of the plan blob into shared memory (16-byte words; the blob is 16-byte padded)
+__device__ __forceinline__ void stage_tab(unsigned char *dst, const unsigned char *src, int bytes, int tid) {
+    const int4 *s = reinterpret_cast<const int4 *>(src);
+    int4 *d = reinterpret_cast<int4 *>(dst);
+    for (int i = tid; i < bytes / 16; i += SM_NT) d[i] = __ldg(s + i);
+}
+
+// Persistent forward kernel.  Shared memory: work[LC][TF] | staged samples | plan blob.
 template <typename T, int TF>
-__global__ void __launch_bounds__(SM_NT) smooth_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total) {
+__global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total,
+                                                           const int xin_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
     FwdCtx<T> c;
     c.a = &args;
-    c.work = reinterpret_cast<cx<T> *>(smem);
-    c.xin = reinterpret_cast<T *>(c.work + (size_t)args.s.M * TF);
-    const int tid = threadIdx.x;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        c.b = w / args.ptiles;
-        c.pt = w - c.b * args.ptiles;
+    c.work = reinterpret_cast<cx<vec_t<T>> *>(smem);
+    unsigned char *q = smem + sizeof(cx<T>) * (size_t)args.s.LC * TF;
+    T *xbuf[2] = {reinterpret_cast<T *>(q), reinterpret_cast<T *>(q + xin_bytes)};
+    c.tab = q + 2 * xin_bytes;
+    stage_tab(q + 2 * xin_bytes, args.tab, args.lay.bytes, tid);
+    // (signal, tile) of work item w, advanced by gridDim.x per iteration without a 64-bit division
+    c.b = blockIdx.x / args.ptiles;
+    c.pt = blockIdx.x - c.b * args.ptiles;
+    const int64_t db = gridDim.x / args.ptiles, dp = gridDim.x - db * args.ptiles;
+    if ((int64_t)blockIdx.x < total) {
+        c.xin = xbuf[0];
         Fwd<T, TF>::stage(c, tid, SM_NT);
-        __syncthreads();
-        Fwd<T, TF>::load(c, tid, SM_NT);
-        __syncthreads();
+        p2::cp_async_commit();
+    }
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x, it ^= 1) {
+        p2::cp_async_wait_all();
+        __syncthreads();                   // this tile's samples (and the tables) are in place
+        int64_t nb = c.b + db, npt = c.pt + dp;
+        if (npt >= args.ptiles) { npt -= args.ptiles; ++nb; }
+        if (w + gridDim.x < total) {       // stage the next tile into the other buffer while this one is transformed
+            FwdCtx<T> cn = c;
+            cn.b = nb; cn.pt = npt; cn.xin = xbuf[it ^ 1];
+            Fwd<T, TF>::stage(cn, tid, SM_NT);
+            p2::cp_async_commit();
+        }
+        c.xin = xbuf[it];
         for (int p = 0; p < args.s.np; ++p) {
             Fwd<T, TF>::pass(c, p, tid, SM_NT);
             __syncthreads();
         }
         Fwd<T, TF>::store(c, tid, SM_NT);
-        __syncthreads();
+        c.b = nb;
+        c.pt = npt;
     }
 }
 
+// Persistent inverse kernel.  Shared memory: work[LC][TF] | slice rows [TF][ostride] | plan blob.
 template <typename T, int TF>
-__global__ void __launch_bounds__(SM_NT) smooth_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total) {
+__global__ void __launch_bounds__(SM_NT, 2) smooth_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total,
+                                                           const int ola_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
     InvCtx<T> c;
     c.a = &args;
-    c.work = reinterpret_cast<cx<T> *>(smem);
-    c.ola = reinterpret_cast<T *>(c.work + (size_t)args.s.M * TF);
-    const int tid = threadIdx.x;
+    c.work = reinterpret_cast<cx<vec_t<T>> *>(smem);
+    unsigned char *q = smem + sizeof(cx<T>) * (size_t)args.s.LC * TF;
+    c.ola = reinterpret_cast<T *>(q);
+    c.tab = q + ola_bytes;
+    stage_tab(q + ola_bytes, args.tab, args.lay.bytes, tid);
     const int own = TF - args.halo;
+    c.b = blockIdx.x / args.ntiles;
+    int64_t ti = blockIdx.x - c.b * args.ntiles;
+    const int64_t db = gridDim.x / args.ntiles, dp = gridDim.x - db * args.ntiles;
+    __syncthreads();
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        c.b = w / args.ntiles;
-        c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
+        c.qa = args.qa0 + ti * own;
         Inv<T, TF>::load(c, tid, SM_NT);
         __syncthreads();
         for (int p = 0; p < args.s.np; ++p) {
             Inv<T, TF>::pass(c, p, tid, SM_NT);
             __syncthreads();
         }
-        Inv<T, TF>::rows(c, tid, SM_NT);
-        __syncthreads();
         Inv<T, TF>::gather(c, tid, SM_NT);
         __syncthreads();
+        c.b += db;
+        ti += dp;
+        if (ti >= args.ntiles) { ti -= args.ntiles; ++c.b; }
     }
 }
 
-template <typename T> size_t fwd_smem(int64_t M, int64_t N, int64_t H, int tf) {
-    const int64_t span = (int64_t)(tf - 1) * H + N;
-    return sizeof(cx<T>) * (size_t)M * tf + sizeof(T) * (size_t)(span + span / H + 8);
-}
-template <typename T> size_t inv_smem(int64_t M, int64_t N, int tf) {
-    return sizeof(cx<T>) * (size_t)M * tf + sizeof(T) * (size_t)tf * (size_t)((N | 1) + 1);
-}
 inline int halo_of(int64_t N, int64_t H) { return (int)((N + H - 1) / H) - 1; }
-// slices per tile: the widest of {32, 16, 8, 4} that leaves room for two CTAs per SM, else whatever fits
-template <typename T> int pick_tf(int64_t M, int64_t N, int64_t H, bool inverse) {
-    const int cand[4] = {sizeof(T) == 4 ? 32 : 16, sizeof(T) == 4 ? 16 : 8, sizeof(T) == 4 ? 8 : 4, 4};
-    int fits = 0;
-    for (int i = 0; i < 4; ++i) {
-        const int tf = cand[i];
-        if (inverse && halo_of(N, H) >= tf) continue;
-        const size_t b = inverse ? inv_smem<T>(M, N, tf) : fwd_smem<T>(M, N, H, tf);
-        if (b <= 110 * 1024) return tf;
-        if (!fits && b <= SM_SMEM_LIMIT) fits = tf;
-    }
-    return fits;
+template <typename T> size_t xin_bytes_of(const Shape &s, int tf) {
+    const int64_t span = (int64_t)(tf - 1) * s.H + s.N, rows = (span + s.H - 1) / s.H;
+    return (size_t)al16((int64_t)sizeof(T) * (rows * (s.H + xpad_of(s.H)) + 4));
+}
+template <typename T> size_t ola_bytes_of(const Shape &s, int tf) {
+    return (size_t)al16((int64_t)sizeof(T) * tf * ((s.N | 1) + 0));
+}
+// shared memory without / with the plan blob
+template <typename T> void smem_of(const Shape &s, int tf, bool inverse, size_t *core, size_t *with_tab) {
+    const size_t work = sizeof(cx<T>) * (size_t)s.LC * tf;
+    *core = work + (inverse ? ola_bytes_of<T>(s, tf) : 2 * xin_bytes_of<T>(s, tf));   // forward: double-buffered staging
+    *with_tab = *core + (size_t)tab_layout<T>(s, inverse).bytes;
+}
+// slices per tile: the wide tile when two CTAs of it fit an SM, else the narrow one, else whatever fits (plan blob included)
+template <typename T> int pick_tf(const Shape &s, bool inverse) {
+    const int cand[3] = {sizeof(T) == 4 ? 32 : 16, sizeof(T) == 4 ? 16 : 8, sizeof(T) == 4 ? 8 : 4};
+    const int force = VEILS_ENV_ONCE("VEILS_SMOOTH_TF", 0);
+    const size_t budgets[2] = {113 * 1024, SM_SMEM_LIMIT};
+    for (int bi = 0; bi < 2; ++bi)
+        for (int i = 0; i < 3; ++i) {
+            const int tf = cand[i];
+            if (force && tf != force) continue;
+            if (inverse && halo_of(s.N, s.H) >= tf) continue;
+            if (inverse && bi < 1 && 4 * halo_of(s.N, s.H) > tf) continue;     // more than a quarter of the tile recomputed
+            size_t core, full;
+            smem_of<T>(s, tf, inverse, &core, &full);
+            if (full <= budgets[bi]) return tf;
+        }
+    return 0;
 }
 
 template <typename T, int TF>
-cudaError_t launch_fwd(FwdArgs<T> &a, int64_t batch, size_t smem, cudaStream_t st) {
+cudaError_t launch_fwd(FwdArgs<T> &a, int64_t batch, cudaStream_t st) {
     auto kern = smooth_fwd_kernel<T, TF>;
     static KernelSlot slot;
+    size_t core, smem;
+    smem_of<T>(a.s, TF, false, &core, &smem);
     int per_sm = 0, dev = 0;
     cudaError_t e = prepare_kernel(slot, kern, SM_NT, smem, &per_sm, &dev);
     if (e != cudaSuccess) return e;
     a.ptiles = (a.P + TF - 1) / TF;
     const int64_t total = a.ptiles * batch, cap = (int64_t)per_sm * device_sms(dev);
-    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total);
+    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total, (int)xin_bytes_of<T>(a.s, TF));
     ++g_launch_count;
     return cudaGetLastError();
 }
 template <typename T, int TF>
-cudaError_t launch_inv(InvArgs<T> &a, int64_t batch, size_t smem, cudaStream_t st) {
+cudaError_t launch_inv(InvArgs<T> &a, int64_t batch, cudaStream_t st) {
     auto kern = smooth_inv_kernel<T, TF>;
     static KernelSlot slot;
+    size_t core, smem;
+    smem_of<T>(a.s, TF, true, &core, &smem);
     int per_sm = 0, dev = 0;
     cudaError_t e = prepare_kernel(slot, kern, SM_NT, smem, &per_sm, &dev);
     if (e != cudaSuccess) return e;
@@ -106,7 +157,7 @@ cudaError_t launch_inv(InvArgs<T> &a, int64_t batch, size_t smem, cudaStream_t s
     a.ntiles = (qh1 - qh0 + 1 + own - 1) / own;
     a.qa0 = qh0 - a.halo;
     const int64_t total = a.ntiles * batch, cap = (int64_t)per_sm * device_sms(dev);
-    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total);
+    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total, (int)ola_bytes_of<T>(a.s, TF));
     ++g_launch_count;
     return cudaGetLastError();
 }
@@ -116,60 +167,56 @@ bool smooth_supported(int64_t M, int64_t N, int64_t H, int precision, bool inver
     sm::Shape s;
     if (N > M || H < 1 || !sm::make_shape(M, N, H, M, 0, &s)) return false;
     if (inverse && H > N) return false;
-    return (precision == 0 ? pick_tf<float>(M, N, H, inverse) : pick_tf<double>(M, N, H, inverse)) > 0;
+    return (precision == 0 ? pick_tf<float>(s, inverse) : pick_tf<double>(s, inverse)) > 0;
 }
-int64_t smooth_twiddle_count(int64_t M) {
+int64_t smooth_table_bytes(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse) {
     sm::Shape s;
-    if (!sm::make_shape(M, M, 1, M, 0, &s)) return 0;
-    return 2 * sm::twiddle_entries(s);
+    if (!sm::make_shape(M, N, H, M, ps, &s)) return 0;
+    return precision == 0 ? sm::tab_layout<float>(s, inverse).bytes : sm::tab_layout<double>(s, inverse).bytes;
 }
-void smooth_twiddle_fill(int64_t M, double *re_im) {
+void smooth_table_fill(int64_t M, int64_t N, int64_t H, int64_t ps, int precision, bool inverse, const double *vec_n, void *out) {
     sm::Shape s;
-    if (sm::make_shape(M, M, 1, M, 0, &s)) sm::twiddle_fill(s, re_im);
+    if (!sm::make_shape(M, N, H, M, ps, &s)) return;
+    if (precision == 0) sm::tab_fill<float>(s, inverse, vec_n, (unsigned char *)out);
+    else sm::tab_fill<double>(s, inverse, vec_n, (unsigned char *)out);
 }
 
 template <typename T>
-cudaError_t smooth_forward(const T *x, void *out, const FwdParams &p, const T *win, const T *tw, cudaStream_t st) {
+cudaError_t smooth_forward(const T *x, void *out, const FwdParams &p, const void *tab, cudaStream_t st) {
     if (p.P <= 0 || p.batch <= 0) return cudaSuccess;
     sm::FwdArgs<T> a;
     if (!sm::make_shape(p.M, p.N, p.H, p.F, p.ps, &a.s)) return cudaErrorNotSupported;
-    a.x = x; a.out = out; a.win = win; a.tw = reinterpret_cast<const sm::cx<T> *>(tw);
+    a.x = x; a.out = out; a.tab = (const unsigned char *)tab; a.lay = sm::tab_layout<T>(a.s, false);
     a.n = p.n; a.x_pitch = p.x_pitch; a.ldp = p.ldp; a.p0 = p.p0; a.P = p.P; a.k_offset = p.k_offset; a.ptiles = 0;
-    a.mid = (int)p.mid; a.mode = p.mode; a.spectrogram = p.spectrogram; a.xpad = (p.H % 2 == 0) ? 1 : 0;
+    a.mid = (int)p.mid; a.mode = p.mode; a.spectrogram = p.spectrogram; a.xpad = sm::xpad_of(p.H);
     a.fac2x = p.mode == 3 ? (T)p.fac2x : (T)1;
-    const int tf = pick_tf<T>(p.M, p.N, p.H, false);
-    const size_t smem = fwd_smem<T>(p.M, p.N, p.H, tf);
-    switch (tf) {
-        case 32: return launch_fwd<T, 32>(a, p.batch, smem, st);
-        case 16: return launch_fwd<T, 16>(a, p.batch, smem, st);
-        case 8: return launch_fwd<T, 8>(a, p.batch, smem, st);
-        case 4: return launch_fwd<T, 4>(a, p.batch, smem, st);
-    }
+    constexpr int TFA = sizeof(T) == 4 ? 32 : 16, TFB = sizeof(T) == 4 ? 16 : 8, TFC = sizeof(T) == 4 ? 8 : 4;
+    const int tf = pick_tf<T>(a.s, false);
+    if (tf == TFA) return launch_fwd<T, TFA>(a, p.batch, st);
+    if (tf == TFB) return launch_fwd<T, TFB>(a, p.batch, st);
+    if (tf == TFC) return launch_fwd<T, TFC>(a, p.batch, st);
     return cudaErrorNotSupported;
 }
 template <typename T>
-cudaError_t smooth_inverse(const void *S, T *x_out, const InvParams &p, const T *dual_over_m, const T *tw, cudaStream_t st) {
+cudaError_t smooth_inverse(const void *S, T *x_out, const InvParams &p, const void *tab, cudaStream_t st) {
     if (p.batch <= 0 || p.k1 <= p.k0) return cudaSuccess;
     sm::InvArgs<T> a;
     if (!sm::make_shape(p.M, p.N, p.H, p.F, p.ps, &a.s)) return cudaErrorNotSupported;
-    a.S = S; a.xo = x_out; a.dual = dual_over_m; a.tw = reinterpret_cast<const sm::cx<T> *>(tw);
+    a.S = S; a.xo = x_out; a.tab = (const unsigned char *)tab; a.lay = sm::tab_layout<T>(a.s, true);
     a.P = p.P; a.ldp = p.ldp; a.out_pitch = p.out_pitch; a.p_min = p.p_min;
     a.k0 = p.k0; a.k1 = p.k1; a.q0 = p.q0; a.q1 = p.q1; a.qa0 = 0; a.ntiles = 0;
-    a.mid = (int)p.mid; a.mode = p.mode; a.halo = halo_of(p.N, p.H); a.ostride = (int)((p.N | 1) + 0);
+    a.mid = (int)p.mid; a.mode = p.mode; a.halo = halo_of(p.N, p.H); a.ostride = (int)(p.N | 1);
     a.rfac2x = p.mode == 3 ? (T)(1.0 / p.fac2x) : (T)1;
-    const int tf = pick_tf<T>(p.M, p.N, p.H, true);
-    const size_t smem = inv_smem<T>(p.M, p.N, tf);
-    switch (tf) {
-        case 32: return launch_inv<T, 32>(a, p.batch, smem, st);
-        case 16: return launch_inv<T, 16>(a, p.batch, smem, st);
-        case 8: return launch_inv<T, 8>(a, p.batch, smem, st);
-        case 4: return launch_inv<T, 4>(a, p.batch, smem, st);
-    }
+    constexpr int TFA = sizeof(T) == 4 ? 32 : 16, TFB = sizeof(T) == 4 ? 16 : 8, TFC = sizeof(T) == 4 ? 8 : 4;
+    const int tf = pick_tf<T>(a.s, true);
+    if (tf == TFA) return launch_inv<T, TFA>(a, p.batch, st);
+    if (tf == TFB) return launch_inv<T, TFB>(a, p.batch, st);
+    if (tf == TFC) return launch_inv<T, TFC>(a, p.batch, st);
     return cudaErrorNotSupported;
 }
-template cudaError_t smooth_forward<float>(const float *, void *, const FwdParams &, const float *, const float *, cudaStream_t);
-template cudaError_t smooth_forward<double>(const double *, void *, const FwdParams &, const double *, const double *, cudaStream_t);
-template cudaError_t smooth_inverse<float>(const void *, float *, const InvParams &, const float *, const float *, cudaStream_t);
-template cudaError_t smooth_inverse<double>(const void *, double *, const InvParams &, const double *, const double *, cudaStream_t);
+template cudaError_t smooth_forward<float>(const float *, void *, const FwdParams &, const void *, cudaStream_t);
+template cudaError_t smooth_forward<double>(const double *, void *, const FwdParams &, const void *, cudaStream_t);
+template cudaError_t smooth_inverse<float>(const void *, float *, const InvParams &, const void *, cudaStream_t);
+template cudaError_t smooth_inverse<double>(const void *, double *, const InvParams &, const void *, cudaStream_t);
 
 }  // namespace veils

@@ -73,10 +73,10 @@ template <int R> VCX Trig<R> make_trig() {
     return t;
 }
 
-// a * (c - i s) forward, a * (c + i s) inverse, c / s compile-time
+// a * (c - i s) forward, a * (c + i s) inverse, c / s compile-time; T = float, double or the packed pair f2
 template <bool INV, typename T> VHD cx<T> mulw(cx<T> a, double c, double s) {
-    const T cc = (T)c, ss = (T)(INV ? -s : s);
-    return mk<T>(a.x * cc + a.y * ss, a.y * cc - a.x * ss);
+    const T cc = p2::vconst<T>(c), ss = p2::vconst<T>(INV ? -s : s), ns = p2::vconst<T>(INV ? s : -s);
+    return mk<T>(p2::vfma(a.y, ss, a.x * cc), p2::vfma(a.x, ns, a.y * cc));
 }
 
 template <int R, bool INV, typename T> struct Dft;
@@ -103,14 +103,17 @@ template <int R, bool INV, typename T> struct DftOdd {
         for (int n = 0; n < H; ++n) o[0] = o[0] + s[n];
 #pragma unroll
         for (int k = 1; k <= H; ++k) {
-            T ar = v[0].x, ai = v[0].y, br = 0, bi = 0;
+            T ar = v[0].x, ai = v[0].y;
+            T br = d[0].x * p2::vconst<T>(tt.s[k % R]), bi = d[0].y * p2::vconst<T>(tt.s[k % R]);
+            ar = p2::vfma(s[0].x, p2::vconst<T>(tt.c[k % R]), ar);
+            ai = p2::vfma(s[0].y, p2::vconst<T>(tt.c[k % R]), ai);
 #pragma unroll
-            for (int n = 1; n <= H; ++n) {
-                const T c = (T)tt.c[(n * k) % R], sn = (T)tt.s[(n * k) % R];
-                ar += s[n - 1].x * c;
-                ai += s[n - 1].y * c;
-                br += d[n - 1].x * sn;
-                bi += d[n - 1].y * sn;
+            for (int n = 2; n <= H; ++n) {
+                const T c = p2::vconst<T>(tt.c[(n * k) % R]), sn = p2::vconst<T>(tt.s[(n * k) % R]);
+                ar = p2::vfma(s[n - 1].x, c, ar);
+                ai = p2::vfma(s[n - 1].y, c, ai);
+                br = p2::vfma(d[n - 1].x, sn, br);
+                bi = p2::vfma(d[n - 1].y, sn, bi);
             }
             // forward: X[k] = a - i b, X[R-k] = a + i b  (b = sum d sin);  inverse: the other way round
             const cx<T> lo = INV ? mk<T>(ar - bi, ai + br) : mk<T>(ar + bi, ai - br);
