@@ -754,6 +754,51 @@ def side_c5(e, args):
             "kernels": {"spectrogram": st.kernel_name(False)}}
 
 
+# ---- neighbouring shapes the round-1 review asked for next to the BASELINE configs: the c2 geometry in f64 (the
+#      reference's own precision), the non-power-of-two speech front end Hann 400 / hop 160 (mixed-radix family),
+#      and the 1024 / 256 and 2048 / 512 front ends (wide family): round trip on a sub-batch, roofline, oracle parity
+EXTRA = {
+    "f64_c2": dict(batch=256, n=160000, fs=16000.0, m=512, hop=128, mode="onesided", prec="f64", win="hann"),
+    "hann400": dict(batch=1024, n=160000, fs=16000.0, m=400, hop=160, mode="onesided", prec="f32", win="hann"),
+    "m1024": dict(batch=512, n=160000, fs=16000.0, m=1024, hop=256, mode="onesided", prec="f32", win="hann"),
+    "m2048": dict(batch=256, n=480000, fs=48000.0, m=2048, hop=512, mode="onesided", prec="f32", win="hann"),
+}
+
+
+def side_extra(e, name):
+    cfg = dict(EXTRA[name])
+    torch, L = e.torch, e.L
+    st = plan_of(e, cfg)
+    x = synth_device(cfg, torch, e.dev, 7000 + e.rank)
+    B, n = x.shape
+    P, F = st.p_num(n), st.f_pts
+    k0, k1 = st.istft_range(P)
+    ldp = -(-P // st.pitch_align) * st.pitch_align
+    S = torch.empty((B, F, ldp), dtype=torch.complex64 if cfg["prec"] == "f32" else torch.complex128, device=e.dev)
+    y = torch.empty((B, k1 - k0), dtype=x.dtype, device=e.dev)
+    stream = torch.cuda.current_stream(e.dev).cuda_stream
+
+    def fwd():
+        assert L.veils_stft_dev(st._h, x.data_ptr(), n, B, n, None, None, 0, S.data_ptr(), ldp, stream) == 0
+
+    def inv():
+        assert L.veils_istft_dev(st._h, S.data_ptr(), P, B, ldp, None, None, y.data_ptr(), k1 - k0, stream) == 0
+    ms_f = max_over_ranks(e, time_events(e, fwd, 5))
+    ms_i = max_over_ranks(e, time_events(e, inv, 5))
+    bf, bi = algorithmic_bytes(cfg, B, n, P, F, k1 - k0)
+    es, ey = parity_rows(e, cfg, st, x, S[:, :, :P], y, [0, B - 1])
+    tol = 1e-5 if cfg["prec"] == "f32" else 1e-12
+    return {"workload": f"{name}: {B} x {n}, {cfg['win']} {cfg['m']} / hop {cfg['hop']}, {cfg['mode']}, {cfg['prec']}, stft+istft",
+            "value": e.world * B * n / ((ms_f + ms_i) * 1e-3) / 1e6, "unit": "Msamples/s",
+            "roofline": {"bound": "hbm", "peak": e.peak, "unit": "GB/s", "stft": roof_entry(e, bf, ms_f),
+                         "istft": roof_entry(e, bi, ms_i),
+                         "roundtrip_frac": (bf + bi) / ((ms_f + ms_i) * 1e-3) / 1e9 / e.peak},
+            "parity": {"stft_rel_err_vs_oracle": es, "istft_rel_err_vs_oracle": ey, "tolerance": tol,
+                       "recon_max_abs_err": float((y[:, :n] - x).abs().max()),
+                       "checked": "first / interior / last 24 slices of the first and last row"},
+            "kernels": {"stft": st.kernel_name(False), "istft": st.kernel_name(True)}}
+
+
 # =========================================================================== main
 def main():
     ap = argparse.ArgumentParser()
@@ -767,7 +812,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sides", action="store_true", help="skip the c1 / c3 / c4 / c5 legs")
-    ap.add_argument("--sides", default="c1,c3,c4,c5")
+    ap.add_argument("--sides", default="c1,c3,c4,c5,f64_c2,hann400,m1024,m2048")
     ap.add_argument("--dense-pitch", action="store_true", help="S row pitch ldp = P (reference-dense)")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="sub-batches per e2e step")
     ap.add_argument("--e2e-streams", type=int, default=3)
@@ -997,6 +1042,8 @@ def main():
         for name in args.sides.split(","):
             fn = {"c1": lambda: side_c1(e), "c3": lambda: side_c3(e, args), "c4": lambda: side_c4(e, args),
                   "c5": lambda: side_c5(e, args)}.get(name.strip())
+            if fn is None and name.strip() in EXTRA:
+                fn = (lambda nm: lambda: side_extra(e, nm))(name.strip())
             if fn is None:
                 continue
             try:

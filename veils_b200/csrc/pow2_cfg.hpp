@@ -16,6 +16,9 @@ namespace p2 {
 #endif
 #define VEILS_P2_THREADS(logmc) ((logmc) >= 10 ? VEILS_P2_BIG_THREADS : 256)
 
+#ifndef VEILS_F64_L8_TF
+#define VEILS_F64_L8_TF 16
+#endif
 struct Cfg {
     int logmc;   // log2(mfft / 2)
     int tf;      // slices per tile
@@ -35,7 +38,7 @@ inline bool cfg_for(int64_t M, int precision, Cfg *c) {
     if (lm < 5 || lm > 13) return false;              // mfft in [32, 8192]
     c->logmc = lm - 1;
     static const int tf32[13] = {0, 0, 0, 0, 32, 32, 32, 32, 32, 32, 16, 8, 4};
-    static const int tf64[13] = {0, 0, 0, 0, 32, 32, 32, 32, 16, 16, 8, 4, 2};
+    static const int tf64[13] = {0, 0, 0, 0, 32, 32, 32, 32, VEILS_F64_L8_TF, 16, 8, 4, 2};
     c->tf = precision == 0 ? tf32[c->logmc] : tf64[c->logmc];
     int np, r1, r2, r3;
     fac_of(c->logmc, &np, &r1, &r2, &r3);
@@ -105,7 +108,8 @@ inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H 
 
 inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) {
     const int64_t span = (int64_t)(tf - 1) * H + N;
-    return span + (span / H + 1) * l.padw + 6;          // + zero pair used by padded table entries
+    return (span + (span / H + 1) * l.padw + 6 + 1) & ~int64_t(1);   // + zero pair used by padded table entries; even, so
+                                                                      // that the tables behind a single buffer stay 16-byte aligned
 }
 // exact shared-memory footprints of the instantiated kernels (see pow2_tile.cu)
 template <typename T, int LOGMC, int TF>
@@ -209,7 +213,7 @@ inline auto dispatch(int precision, int logmc, FN &fn) -> decltype(fn.template r
     } else {
         switch (logmc) {
             VEILS_P2_CASE(double, 4, 32) VEILS_P2_CASE(double, 5, 32) VEILS_P2_CASE(double, 6, 32)
-            VEILS_P2_CASE(double, 7, 32) VEILS_P2_CASE(double, 8, 16) VEILS_P2_CASE(double, 9, 16)
+            VEILS_P2_CASE(double, 7, 32) VEILS_P2_CASE(double, 8, VEILS_F64_L8_TF) VEILS_P2_CASE(double, 9, 16)
             VEILS_P2_CASE(double, 10, 8) VEILS_P2_CASE(double, 11, 4) VEILS_P2_CASE(double, 12, 2)
         }
     }

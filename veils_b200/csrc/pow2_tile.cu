@@ -200,8 +200,10 @@ struct FwdLaunch {
 
 struct InvLaunch {
     const void *S; void *xo; const InvParams *prm; const void *dual; const void *tw; cudaStream_t st;
-    template <typename T, int LOGMC, int TF, int NSUB>
+    template <typename T, int LOGMC, int TF, int NSUB0>
     cudaError_t run() {
+        // f64: pass 1 works one group per thread (Inv::pass1_u), so twice the threads find work
+        constexpr int NSUB = (sizeof(T) == 8 && 2 * TF * NSUB0 <= 256) ? 2 * NSUB0 : NSUB0;
         const InvParams &p = *prm;
         if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
         InvArgs<T> a = make_inv_args<T>(S, (T *)xo, p, (const T *)dual, (const T *)tw, TF);

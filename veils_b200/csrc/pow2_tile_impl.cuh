@@ -228,7 +228,12 @@ struct Geo {
     // small transforms: persistent CTAs keep the plan tables in shared memory and double-buffer
     // the staged signal tile (cp.async); large ones read the tables through the read-only path.
     static constexpr bool STAB = LOGMC <= 8;
-    static constexpr bool DBUF = LOGMC <= 8;
+    // f64 mfft 512: one staged-signal buffer keeps the CTA under half an SM's shared memory -- two resident CTAs
+    // are worth more than the prefetch (measured: forward 39.4 -> 55.0 % of the HBM roofline)
+#ifndef VEILS_F64_L8_DBUF
+#define VEILS_F64_L8_DBUF 0
+#endif
+    static constexpr bool DBUF = LOGMC <= 8 && !(sizeof(T) == 8 && LOGMC == 8 && !VEILS_F64_L8_DBUF);
     static constexpr int TWN = 2 * (MC + L1 + MC + 1);    // reals in the twiddle table
     VHD static cx<T> tlc(const T *q) {                     // complex table entry
         if (STAB) return *reinterpret_cast<const cx<T> *>(q);
@@ -617,7 +622,57 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             }
         }
     }
+    // One group per thread (f64): Z'[k] = E + i O needs X[k] and its mirror X[Mc - k]; instead of keeping the
+    // mirrored group in the same thread (2 x R1 complex doubles: 255 registers, 8 warps per SM) every thread
+    // loads the R1 mirror bins as well (they are the other threads' own bins: L1 / L2 hits) and merges only its
+    // own group -- half the registers, twice the resident warps, one code path for every group (k = 0 pairs with
+    // the Nyquist bin and k = Mc / 2 with itself through the same formula).
+    VHD static C merge_one(const T *twp, int k, C Xk, C Xp) {
+        const C Xm = conj(Xp);
+        const C E = Xk + Xm, Dm = Xk - Xm;
+        const C O = cmulconj(Dm, GEO::tlc(twp + 2 * k));     // conj(W_M^k) (Xk - conj X[Mc-k])
+        return mk<T>(E.x - O.y, E.y + O.x);                  // E + i O
+    }
+    template <bool ONES>
+    VHD static void pass1_u(const InvCtx<T> &c, int tid) {
+        const InvArgs<T> &p = c.a;
+        const int f = tid % TF, sub = tid / TF;
+        const int64_t q = c.qa + f;
+        const int64_t col = q - p.p_min;
+        const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+        const int64_t rb = p.ldp * (int64_t)sizeof(C);
+        const char *sb = reinterpret_cast<const char *>(p.S) + ((c.b * p.F) * p.ldp + (live ? col : 0)) * (int64_t)sizeof(C);
+        const T *twp0 = c.tw + GEO::TWP;
+        for (int j = sub; j < L1; j += NSUB) {
+            C v[R1];
+            if (live) {
+                C w[R1];
+#pragma unroll
+                for (int a = 0; a < R1; ++a) {
+                    v[a] = load_bin<ONES>(p, sb, rb, j + L1 * a);
+                    w[a] = load_bin<ONES>(p, sb, rb, MC - (j + L1 * a));
+                }
+#pragma unroll
+                for (int a = 0; a < R1; ++a) v[a] = merge_one(twp0, j + L1 * a, v[a], w[a]);
+            } else {
+#pragma unroll
+                for (int a = 0; a < R1; ++a) v[a] = mk<T>(0, 0);
+            }
+            Dft<R1, true, T>::run(v);
+            C *wj = c.work + j * TF + f;
+            const T *twj = c.tw + GEO::TW1 + 2 * j * R1;
+            wj[0] = v[0];
+#pragma unroll
+            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
+        }
+    }
+    static constexpr bool UNPAIRED = sizeof(T) == 8;
     VHD static void pass1(const InvCtx<T> &c, int tid) {
+        if (UNPAIRED) {
+            if (c.a.mode >= 2) pass1_u<true>(c, tid);
+            else pass1_u<false>(c, tid);
+            return;
+        }
         if (c.a.mode >= 2) pass1_t<true>(c, tid);
         else pass1_t<false>(c, tid);
     }
@@ -660,6 +715,25 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         const int f = tid % TF, sub = tid / TF;
         const int ps = p.ps, N = p.N;
         T *row = c.ola + (size_t)f * p.ostride;
+        if (N == M && (ps & 1) == 0) {
+            // no truncation, even roll: the pair (y[2m], y[2m+1]) lands on adjacent row samples j0, j0 + 1 (j0 even)
+            // and its dual-window factors are one aligned pair of the table
+#pragma unroll
+            for (int i = 0; i < GPT; ++i) {
+                const int g = sub + NSUB * i;
+                if (g < G) {
+                    int j0 = (2 * g + ps) & (M - 1);
+#pragma unroll
+                    for (int d = 0; d < RL; ++d) {
+                        const C w = GEO::tlc(c.dual + j0);
+                        row[j0] = r[i][d].x * w.x;
+                        row[j0 + 1] = r[i][d].y * w.y;
+                        j0 = (j0 + 2 * G) & (M - 1);
+                    }
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < GPT; ++i) {
             const int g = sub + NSUB * i;
@@ -677,9 +751,10 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
     }
 
     // ---- overlap-add as a gather over the samples this tile owns, increasing q
-    VHD static void gather(const InvCtx<T> &c, int tid) {
+    template <int HALO>
+    VHD static void gather_t(const InvCtx<T> &c, int tid) {
         const InvArgs<T> &p = c.a;
-        const int H = p.H, N = p.N, halo = p.halo;
+        const int H = p.H, N = p.N, halo = HALO >= 0 ? HALO : p.halo;
         const int64_t qo = c.qa + halo;                      // first owned "latest slice"
         int64_t ka = qo * H - p.mid, kb = (c.qa + TF) * (int64_t)H - p.mid;
         if (ka < p.k0) ka = p.k0;
@@ -693,15 +768,24 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             const int u = e + hH;
             if (u < ua || u >= ub) continue;
             const int r = (int)mulhi_u32((unsigned)e, p.magic_h);   // e / H
-            int jj = e - r * H + hH;                         // offset inside slice r
-            int idx = r * p.ostride + jj;
-            T acc = (T)0;
-            for (int h = 0; h <= halo; ++h) {                // increasing q (src/lib.rs:853)
-                if (jj < N) acc += c.ola[idx];
-                jj -= H;
-                idx += step;
+            const int jj = e - r * H + hH;                   // offset inside slice r (the oldest contributor)
+            const T *q = c.ola + r * p.ostride + jj;
+            // increasing q (src/lib.rs:853); only the oldest slice can fall beyond the window length (halo H < N)
+            T acc = jj < N ? q[0] : (T)0;
+            if (HALO >= 0) {
+#pragma unroll
+                for (int h = 1; h <= (HALO >= 0 ? HALO : 0); ++h) acc += q[h * step];
+            } else {
+                for (int h = 1; h <= halo; ++h) acc += q[h * step];
             }
             xo[u] = acc;
+        }
+    }
+    VHD static void gather(const InvCtx<T> &c, int tid) {
+        switch (c.a.halo) {
+            case 1: gather_t<1>(c, tid); break;
+            case 3: gather_t<3>(c, tid); break;
+            default: gather_t<-1>(c, tid); break;
         }
     }
 };
