@@ -38,7 +38,7 @@ struct EmuFwd {
         std::vector<T> tw = conv<T>(twd), win = conv<T>(pl->win, 0.5);
         FwdCtx<T> c;
         c.a = make_fwd_args<T>((const T *)x, out, prm, win.data(), tw.data(), TF);
-        std::vector<cx<T>> work((size_t)K::MC * TF);
+        std::vector<cx<T>> work((size_t)K::MCP * TF);
         std::vector<T> xin((size_t)fwd_xin_elems(prm.N, prm.H, TF, c.a.lay));
         c.work = work.data(); c.xin = xin.data(); c.tw = tw.data(); c.win = win.data();
         for (int64_t blk = 0; blk < c.a.ptiles * prm.batch; ++blk) {
@@ -63,7 +63,7 @@ struct EmuInv {
         std::vector<T> tw = conv<T>(twd), dual = conv<T>(pl->dual, sc);
         InvCtx<T> c;
         c.a = make_inv_args<T>(S, (T *)xo, prm, dual.data(), tw.data(), TF);
-        size_t elems = (size_t)K::MC * TF * 2;
+        size_t elems = (size_t)K::MCP * TF * 2;
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<T> buf(elems + 4);
         c.work = (cx<T> *)buf.data(); c.ola = buf.data(); c.tw = tw.data(); c.dual = dual.data();

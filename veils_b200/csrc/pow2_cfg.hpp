@@ -104,6 +104,17 @@ inline TileLayout tile_layout(int64_t H, bool vec) {
     else l.padw = (H % 2 == 0) ? 1 : 0;
     return l;
 }
+template <typename T> inline TileLayout fwd_layout(int64_t H, bool vec, int tf) {
+    TileLayout l = tile_layout(H, vec);
+    if (VEILS_P2_PADR && sizeof(T) == 8 && vec && tf < 8) {
+        // narrow f64 tiles: a quarter-warp reads 8 / tf consecutive 16-byte pairs of each of its tf slices, so the
+        // slice stride must be 128 / tf bytes past a multiple of 128 (ncu, c5: 8 instead of 4 wavefronts per LDS.128)
+        const int want = 128 / tf;
+        for (int pw = 0; pw < 16; pw += 2)
+            if (((H + pw) * 8) % 128 == want) { l.padw = pw; break; }
+    }
+    return l;
+}
 inline bool fwd_vec(int64_t ps, int64_t H, int64_t N) { return ps % 2 == 0 && H % 2 == 0 && N % 2 == 0 && H >= 4; }
 
 inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) {
@@ -115,14 +126,14 @@ inline int64_t fwd_xin_elems(int64_t N, int64_t H, int tf, const TileLayout &l) 
 template <typename T, int LOGMC, int TF>
 inline size_t fwd_smem_bytes_t(int64_t N, int64_t xin_elems) {
     using G = Geo<T, LOGMC, TF, 1>;
-    size_t b = sizeof(cx<T>) * (size_t)(G::MC + 1) * TF + sizeof(T) * (size_t)xin_elems * (G::DBUF ? 2 : 1);   // + Nyquist row
+    size_t b = sizeof(cx<T>) * (size_t)(G::MCP + 1) * TF + sizeof(T) * (size_t)xin_elems * (G::DBUF ? 2 : 1);   // + Nyquist row
     if (G::STAB) b += sizeof(T) * ((size_t)G::TWN + (size_t)N);
     return b;
 }
 template <typename T, int LOGMC, int TF>
 inline size_t inv_work_bytes_t(int64_t N) {
     using G = Geo<T, LOGMC, TF, 1>;
-    size_t work = sizeof(cx<T>) * (size_t)G::MC * TF;
+    size_t work = sizeof(cx<T>) * (size_t)G::MCP * TF;
     const size_t ola = sizeof(T) * (size_t)TF * (size_t)(N | 1);
     if (ola > work) work = ola;
     return (work + 15) & ~(size_t)15;
@@ -139,7 +150,7 @@ struct SmemQuery {
     template <typename T, int LOGMC, int TF, int NSUB>
     long long run() {
         if (inverse) return (long long)inv_smem_bytes_t<T, LOGMC, TF>(N);
-        const TileLayout l = tile_layout(H, fwd_vec(ps, H, N));
+        const TileLayout l = fwd_layout<T>(H, fwd_vec(ps, H, N), TF);
         return (long long)fwd_smem_bytes_t<T, LOGMC, TF>(N, fwd_xin_elems(N, H, TF, l));
     }
 };
@@ -156,7 +167,7 @@ inline FwdArgs<T> make_fwd_args(const T *x, void *out, const FwdParams &p, const
     a.ptiles = (p.P + tf - 1) / tf;
     a.N = (int)p.N; a.H = (int)p.H; a.mid = (int)p.mid; a.ps = (int)p.ps; a.F = (int)p.F;
     a.vec = fwd_vec(p.ps, p.H, p.N) ? 1 : 0;
-    a.lay = tile_layout(p.H, a.vec != 0);
+    a.lay = fwd_layout<T>(p.H, a.vec != 0, tf);
     a.magic_hp = a.vec ? (unsigned)((0x100000000ULL + (unsigned long long)(p.H / 2) - 1) / (unsigned long long)(p.H / 2)) : 0u;
     a.padded = p.N < p.M ? 1 : 0;
     a.mode = p.mode;

@@ -39,7 +39,7 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
     FwdCtx<T> c;
     c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
-    T *xin0 = reinterpret_cast<T *>(smem + sizeof(cx<T>) * (K::MC + 1) * TF);      // + staged Nyquist row
+    T *xin0 = reinterpret_cast<T *>(smem + sizeof(cx<T>) * (K::MCP + 1) * TF);      // + staged Nyquist row
     T *xin1 = K::DBUF ? xin0 + xin_elems : xin0;
     if (K::STAB) {
         T *stw = xin0 + (K::DBUF ? 2 : 1) * xin_elems;
@@ -102,9 +102,10 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
                     const int mul = args.spectrogram ? 1 : MUL;
                     const int p0 = (int)(cpt * TF) * mul;
                     constexpr unsigned RB = TF * (unsigned)sizeof(cx<T>);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB, p0, 0, g, (int)cb);
-                    tma::store_4d(&smap, wbase + K::GEO::goff(gp) * RB, p0, 0, gp, (int)cb);
-                    if (s2 == 0) tma::store_4d(&smap, wbase + K::MC * RB, p0, K::RL, 0, (int)cb);
+                    const bool sp = args.spectrogram != 0;
+                    tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB + (sp ? K::sskew(g) : 0), p0, 0, g, (int)cb);
+                    tma::store_4d(&smap, wbase + K::GEO::goff(gp) * RB + (sp ? K::sskew(gp) : 0), p0, 0, gp, (int)cb);
+                    if (s2 == 0) tma::store_4d(&smap, wbase + K::MCP * RB, p0, K::RL, 0, (int)cb);
                     tma::commit_group();
                 }
             };
@@ -173,7 +174,8 @@ struct FwdLaunch {
         memset(&smap, 0, sizeof(smap));
         // measured (profiles/r1c_ablation.txt): +3 % for f64; the f32 tile kernels (mfft >= 2048 here) are
         // 5 % faster with their plain stores, so only f64 takes the staged path
-        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !VEILS_ENV_ONCE("VEILS_PK_NO_TMA", 0);
+        // (padded narrow tiles: their rows are not 128-byte aligned, which a tensor-map source must be)
+        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !K::GEO::PADR && !VEILS_ENV_ONCE("VEILS_PK_NO_TMA", 0);
         if (stage) {
             // complex f64 elements are 16 bytes: described as pairs of 8-byte elements
             const int mul = (!p.spectrogram && sizeof(T) == 8) ? 2 : 1;
@@ -200,10 +202,21 @@ struct FwdLaunch {
 
 struct InvLaunch {
     const void *S; void *xo; const InvParams *prm; const void *dual; const void *tw; cudaStream_t st;
-    template <typename T, int LOGMC, int TF, int NSUB0>
+    template <typename T, int LOGMC, int TF0, int NSUB00>
     cudaError_t run() {
+#ifndef VEILS_F64_L8_INV_TF
+#define VEILS_F64_L8_INV_TF 32
+#endif
+#ifndef VEILS_F64_INV_MAXT
+#define VEILS_F64_INV_MAXT 512
+#endif
+        // the inverse may use a wider tile than the forward (fewer halo slices recomputed per owned slice)
+        constexpr bool WIDER = sizeof(T) == 8 && LOGMC == 8 && VEILS_F64_L8_INV_TF != TF0;
+        constexpr int TF = WIDER ? VEILS_F64_L8_INV_TF : TF0;
+        constexpr int L1H = (1 << LOGMC) / Fac<LOGMC>::R1 / 2;
+        constexpr int NSUB0 = WIDER ? (256 / TF < L1H ? 256 / TF : L1H) : NSUB00;
         // f64: pass 1 works one group per thread (Inv::pass1_u), so twice the threads find work
-        constexpr int NSUB = (sizeof(T) == 8 && 2 * TF * NSUB0 <= 256) ? 2 * NSUB0 : NSUB0;
+        constexpr int NSUB = (sizeof(T) == 8 && 2 * TF * NSUB0 <= VEILS_F64_INV_MAXT) ? 2 * NSUB0 : NSUB0;
         const InvParams &p = *prm;
         if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
         InvArgs<T> a = make_inv_args<T>(S, (T *)xo, p, (const T *)dual, (const T *)tw, TF);

@@ -223,8 +223,21 @@ struct Geo {
     static constexpr int G = MC / RL;                     // groups of the last pass
     // twiddle table (complex T, interleaved): [tw1: MC][tw2: L1][twp: MC + 1]
     static constexpr int TW1 = 0, TW2 = 2 * MC, TWP = 2 * (MC + L1);
+    // Narrow tiles (a row of TF slices is shorter than 128 bytes: the 8192 / 4096-point f64 and f32 plans): the
+    // warp rows of the last pass are whole pass-1 blocks apart, a power-of-two stride that lands every row on
+    // the same banks (ncu, c5: 16 instead of 4 wavefronts per LDS.128).  One extra row per pass-1 block skews
+    // them over the banks.
+    // Measured on c5 (profiles/r2o_ncu_full_c5_padded.txt): conflicts 57 % -> 6 % of the shared wavefronts, but the
+    // kernel time does not move (2.13 -> 2.18 ms: padded rows are no tensor-map source, so the stores leave through
+    // the LSU, and the tile of two slices is barrier- / latency-bound with 8 warps) -- kept behind a switch.
+#ifndef VEILS_P2_PADR
+#define VEILS_P2_PADR 0
+#endif
+    static constexpr int PADR = (VEILS_P2_PADR && NP == 3 && TF * (int)sizeof(cx<T>) < 128) ? 1 : 0;
+    static constexpr int L1P = L1 + PADR;                 // pitch (rows) of a pass-1 output block in the work buffer
+    static constexpr int MCP = MC + R1 * PADR;            // rows of the work buffer
     // work-memory offset (in complex elements) of last-pass group g: bins k = g + G d
-    VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1 + (g / R1) * L2; }
+    VHD static int goff(int g) { return (NP == 2) ? g * L1 : (g % R1) * L1P + (g / R1) * L2; }
     // small transforms: persistent CTAs keep the plan tables in shared memory and double-buffer
     // the staged signal tile (cp.async); large ones read the tables through the read-only path.
     static constexpr bool STAB = LOGMC <= 8;
@@ -354,7 +367,7 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
             const T *twj = c.tw + GEO::TW1 + 2 * j * R1;
             wj[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmul(v[cc], GEO::tlc(twj + 2 * cc));
+            for (int cc = 1; cc < R1; ++cc) wj[GEO::L1P * cc * TF] = cmul(v[cc], GEO::tlc(twj + 2 * cc));
         }
     }
     VHD static void pass1(const FwdCtx<T> &c, int tid) {
@@ -373,7 +386,7 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
         const int f = tid % TF, sub = tid / TF;
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
-            C *wb = c.work + (cb * L1 + j2) * TF + f;
+            C *wb = c.work + (cb * GEO::L1P + j2) * TF + f;
             const T *twj = c.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
@@ -390,10 +403,17 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
     // (row 0, this column); rb: row pitch in bytes.
     // byte offset of one-sided bin k in the STAGED tile (one-sided layouts, TMA store path): the RL
     // rows of last-pass group g = k mod G sit on the group's own work rows; bin Mc has an extra row
+    // narrow tiles, |X|^2 staging: the real cells fill only half of the group's rows, so every other run of
+    // groups starts one cell row later -- together with the padded block pitch the half-warp's rows fall on
+    // distinct banks (ncu, c5: 16 wavefronts per STS.64 before)
+    VHD static int sskew(int g) {
+        constexpr int CW = TF * (int)sizeof(T);
+        return GEO::PADR ? ((g / (64 / CW)) & 1) * CW : 0;
+    }
     template <bool SPEC>
     VHD static int64_t srow(int k) {
-        if (k >= MC) return (int64_t)MC * TF * (int64_t)sizeof(C);
-        return (int64_t)GEO::goff(k & (G - 1)) * TF * (int64_t)sizeof(C) +
+        if (k >= MC) return (int64_t)GEO::MCP * TF * (int64_t)sizeof(C);
+        return (int64_t)GEO::goff(k & (G - 1)) * TF * (int64_t)sizeof(C) + (SPEC ? sskew(k & (G - 1)) : 0) +
                (int64_t)(k / G) * TF * (int64_t)(SPEC ? sizeof(T) : sizeof(C));
     }
     template <bool ONES, bool SPEC, bool STAGE = false>
@@ -617,8 +637,8 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             wp[0] = vp[0];
 #pragma unroll
             for (int cc = 1; cc < R1; ++cc) {
-                wj[L1 * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
-                wp[L1 * cc * TF] = cmulconj(vp[cc], GEO::tlc(twq + 2 * cc));
+                wj[GEO::L1P * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
+                wp[GEO::L1P * cc * TF] = cmulconj(vp[cc], GEO::tlc(twq + 2 * cc));
             }
         }
     }
@@ -663,7 +683,7 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             const T *twj = c.tw + GEO::TW1 + 2 * j * R1;
             wj[0] = v[0];
 #pragma unroll
-            for (int cc = 1; cc < R1; ++cc) wj[L1 * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
+            for (int cc = 1; cc < R1; ++cc) wj[GEO::L1P * cc * TF] = cmulconj(v[cc], GEO::tlc(twj + 2 * cc));
         }
     }
     static constexpr bool UNPAIRED = sizeof(T) == 8;
@@ -683,7 +703,7 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         const int f = tid % TF, sub = tid / TF;
         for (int u = sub; u < R1 * L2; u += NSUB) {
             const int cb = u / L2, j2 = u % L2;
-            C *wb = c.work + (cb * L1 + j2) * TF + f;
+            C *wb = c.work + (cb * GEO::L1P + j2) * TF + f;
             const T *twj = c.tw + GEO::TW2 + 2 * j2 * R2;
             C v[R2];
 #pragma unroll
