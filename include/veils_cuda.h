@@ -119,6 +119,16 @@ int32_t veils_t(const veils_plan *p, int64_t n, const int64_t *p0, const int64_t
                 int64_t k_offset, double *out);
 /* f() (src/lib.rs:930-949; centered follows scipy): writes f_pts doubles */
 int32_t veils_f(const veils_plan *p, double *out);
+/* ---- scipy.signal.ShortTimeFFT axis helpers (host integer logic; the reference crate has none -- SURVEY 8 f4) */
+/* lower_border_end: first sample *k / slice *pp not touched by the left border (_short_time_fft.py lower_border_end) */
+int32_t veils_lower_border_end(const veils_plan *p, int64_t *k, int64_t *pp);
+/* upper_border_begin(n): first sample / slice touched by the right border of an n-sample signal */
+int32_t veils_upper_border_begin(const veils_plan *p, int64_t n, int64_t *k, int64_t *pp);
+/* extent(n, axes_seq, center_bins): out = (t0, t1, f0, f1), or (f0, f1, t0, t1) when ft_order != 0; two-sided layouts
+ * other than "centered" are an error, as in scipy */
+int32_t veils_extent(const veils_plan *p, int64_t n, int32_t ft_order, int32_t center_bins, double *out4);
+/* nearest_k_p(k, left): nearest sample index that is a slice position */
+int64_t veils_nearest_k_p(const veils_plan *p, int64_t k, int32_t left);
 /* StandaloneSTFT::debug_ifft_func (src/lib.rs:952-954): ifft_func (:414-505) of ONE slice, evaluated on the
  * host in f64 (debug helper, O(mfft^2)).  X: f_pts complex {re, im}; out: m_num complex {re, im}. */
 int32_t veils_debug_ifft_func(const veils_plan *p, const double *X, double *out);

@@ -44,6 +44,10 @@ PROTOTYPES = {
     "veils_istft_range": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, _I64P, _I64P]),
     "veils_t": (C.c_int32, [_P, C.c_int64, _I64P, _I64P, C.c_int64, _DP]),
     "veils_f": (C.c_int32, [_P, _DP]),
+    "veils_lower_border_end": (C.c_int32, [_P, _I64P, _I64P]),
+    "veils_upper_border_begin": (C.c_int32, [_P, C.c_int64, _I64P, _I64P]),
+    "veils_extent": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, _DP]),
+    "veils_nearest_k_p": (C.c_int64, [_P, C.c_int64, C.c_int32]),
     "veils_debug_ifft_func": (C.c_int32, [_P, _DP, _DP]),
     "veils_stft_dev": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _I64P, _I64P,
                                     C.c_int64, _P, C.c_int64, _P]),

@@ -439,6 +439,69 @@ int32_t veils_f(const veils_plan *p, double *out) {
     return VEILS_OK;
 }
 
+// ---- scipy.signal.ShortTimeFFT axis helpers (scipy _short_time_fft.py: lower_border_end, upper_border_begin,
+// extent, nearest_k_p); host integer logic on the plan's window
+static int64_t floordiv64(int64_t a, int64_t b) {
+    int64_t q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+int32_t veils_lower_border_end(const veils_plan *p, int64_t *k, int64_t *pp) {
+    if (!p || !k || !pp) return fail(VEILS_ERR_INVALID, "null argument");
+    const Plan &pl = p->pl;
+    int64_t m0 = 0;
+    while (m0 < pl.N && pl.win[(size_t)m0] == 0.0) ++m0;              // first non-zero window sample
+    int64_t q = 0;
+    for (int64_t kk = -pl.mid + m0; kk < pl.H + 1; kk += pl.H, ++q)
+        if (kk + pl.H >= 0) { *k = kk + pl.N; *pp = q + 1; return VEILS_OK; }
+    *k = 0;
+    *pp = pl.p_min > 0 ? pl.p_min : 0;
+    return VEILS_OK;
+}
+int32_t veils_upper_border_begin(const veils_plan *p, int64_t n, int64_t *k, int64_t *pp) {
+    if (!p || !k || !pp) return fail(VEILS_ERR_INVALID, "null argument");
+    const Plan &pl = p->pl;
+    const int64_t m2p = pl.N - pl.mid;
+    if (n < m2p) return fail(VEILS_ERR_INVALID, "Parameter n must be >= ceil(m_num/2) = " + std::to_string((long long)m2p) + "!");
+    const int64_t q2 = n / pl.H + 1;
+    int64_t q1 = floordiv64(n - pl.N, pl.H) - 1;
+    if (q1 < -1) q1 = -1;
+    for (int64_t q = q2; q > q1; --q) {
+        const int64_t kk = q * pl.H + (pl.N - pl.mid);
+        bool ok = kk <= n;
+        if (!ok) {                                                     // all(w2[n - kk:] == 0), numpy negative slicing
+            int64_t from = n - kk;                                     // < 0: counts from the end
+            if (from < -pl.N) from = -pl.N;
+            ok = true;
+            for (int64_t i = pl.N + from; i < pl.N; ++i)
+                if (pl.win[(size_t)i] != 0.0) { ok = false; break; }
+        }
+        if (ok) { *k = (q + 1) * pl.H - pl.mid; *pp = q + 1; return VEILS_OK; }
+    }
+    return fail(VEILS_ERR_INVALID, "upper_border_begin: no slice found");
+}
+int32_t veils_extent(const veils_plan *p, int64_t n, int32_t ft_order, int32_t center_bins, double *out4) {
+    if (!p || !out4) return fail(VEILS_ERR_INVALID, "null argument");
+    const Plan &pl = p->pl;
+    int64_t q0, q1;
+    if (pl.mode >= ONESIDED) { q0 = 0; q1 = pl.F; }
+    else if (pl.mode == CENTERED) { q0 = -(pl.M / 2); q1 = pl.M % 2 == 0 ? pl.M / 2 : pl.M / 2 + 1; }
+    else return fail(VEILS_ERR_INVALID, "Attribute fft_mode=twosided must be in ['centered', 'onesided', 'onesided2X']");
+    int64_t p1;
+    int32_t rc = veils_p_max(p, n, &p1);
+    if (rc != VEILS_OK) return rc;
+    const double o = center_bins ? 0.5 : 0.0, dt = (double)pl.H / pl.fs, df = pl.fs / (double)pl.M;
+    const double t0 = dt * ((double)pl.p_min - o), t1 = dt * ((double)p1 - o);
+    const double f0 = df * ((double)q0 - o), f1 = df * ((double)q1 - o);
+    if (ft_order) { out4[0] = f0; out4[1] = f1; out4[2] = t0; out4[3] = t1; }
+    else { out4[0] = t0; out4[1] = t1; out4[2] = f0; out4[3] = f1; }
+    return VEILS_OK;
+}
+int64_t veils_nearest_k_p(const veils_plan *p, int64_t k, int32_t left) {
+    const int64_t H = p->pl.H, q = floordiv64(k, H);
+    if (q * H == k) return k;
+    return left ? q * H : (q + 1) * H;
+}
+
 // StandaloneSTFT::debug_ifft_func (src/lib.rs:952-954 -> ifft_func :414-505) of ONE slice, on the host:
 // mode prologue, direct O(M^2) inverse DFT in f64 (a debug helper, not a compute path), 1/M, roll right by
 // p_s over mfft, first m_num samples.  X: f_pts complex {re, im}; out: m_num complex.  One-sided layouts

@@ -175,59 +175,32 @@ class StandaloneSTFT:
         _check(self._L.veils_f(self._h, _dptr(out)))
         return out
 
-    # ---- scipy.signal.ShortTimeFFT axis helpers (host integer logic only) -------
+    # ---- scipy.signal.ShortTimeFFT axis helpers: host integer logic behind the C ABI -------
     @property
     def lower_border_end(self):
-        """(k, p): first sample / slice not affected by the left border (scipy
-        _short_time_fft.py `lower_border_end`): slide the window right until its non-zero part
-        no longer sticks out to the left of sample 0."""
-        w2 = np.abs(self.win) ** 2
-        m0 = int(np.flatnonzero(w2)[0])
-        k0 = -self.m_num_mid + m0
-        for q_, k_ in enumerate(range(k0, self.hop + 1, self.hop)):
-            if k_ + self.hop >= 0:
-                return k_ + self.m_num, q_ + 1
-        return 0, max(self.p_min, 0)
+        """(k, p): first sample / slice not affected by the left border (scipy `lower_border_end`)."""
+        k, p = C.c_int64(), C.c_int64()
+        _check(self._L.veils_lower_border_end(self._h, C.byref(k), C.byref(p)))
+        return k.value, p.value
 
     def upper_border_begin(self, n):
         """(k, p): first sample / slice affected by the right border of an n-sample signal
         (scipy `upper_border_begin`)."""
-        m2p = self.m_num - self.m_num_mid
-        if n < m2p:
-            raise VeilsError(_lib.ERR_INVALID, f"Parameter n must be >= ceil(m_num/2) = {m2p}!")
-        w2 = np.abs(self.win) ** 2
-        q2 = n // self.hop + 1
-        q1 = max((n - self.m_num) // self.hop - 1, -1)
-        for q_ in range(q2, q1, -1):
-            k_ = q_ * self.hop + (self.m_num - self.m_num_mid)
-            if k_ <= n or np.all(w2[n - k_:] == 0):
-                return (q_ + 1) * self.hop - self.m_num_mid, q_ + 1
-        raise RuntimeError("unreachable")
+        k, p = C.c_int64(), C.c_int64()
+        _check(self._L.veils_upper_border_begin(self._h, int(n), C.byref(k), C.byref(p)))
+        return k.value, p.value
 
     def extent(self, n, axes_seq="tf", center_bins=False):
         """(t0, t1, f0, f1) of stft(x) for plotting (scipy `extent`)."""
         if axes_seq not in ("tf", "ft"):
             raise VeilsError(_lib.ERR_INVALID, f"Parameter axes_seq='{axes_seq}' not in ['tf', 'ft']!")
-        if self.onesided_fft:
-            q0, q1 = 0, self.f_pts
-        elif self.fft_mode == "centered":
-            q0 = -(self.mfft // 2)
-            q1 = self.mfft // 2 if self.mfft % 2 == 0 else self.mfft // 2 + 1
-        else:
-            raise VeilsError(_lib.ERR_INVALID, f"Attribute fft_mode={self.fft_mode} must be in "
-                                               "['centered', 'onesided', 'onesided2X']")
-        p0, p1 = self.p_min, self.p_max(n)
-        o = 0.5 if center_bins else 0.0
-        t0, t1 = self.delta_t * (p0 - o), self.delta_t * (p1 - o)
-        f0, f1 = self.delta_f * (q0 - o), self.delta_f * (q1 - o)
-        return (t0, t1, f0, f1) if axes_seq == "tf" else (f0, f1, t0, t1)
+        out = np.empty(4)
+        _check(self._L.veils_extent(self._h, int(n), int(axes_seq == "ft"), int(bool(center_bins)), _dptr(out)))
+        return tuple(float(v) for v in out)
 
     def nearest_k_p(self, k, left=True):
         """Nearest sample index that is a slice position t[p] (scipy `nearest_k_p`)."""
-        p_q, rem = divmod(k, self.hop)
-        if rem == 0:
-            return k
-        return p_q * self.hop if left else (p_q + 1) * self.hop
+        return int(self._L.veils_nearest_k_p(self._h, int(k), int(bool(left))))
 
     # ---- compute ---------------------------------------------------------------------------
     @staticmethod
