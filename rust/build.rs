@@ -17,7 +17,8 @@ fn main() {
     let mut cmd = Command::new(nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-o"]).arg(&lib);
-    for f in ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu", "pad.cu", "detrend.cu"] {
+    for f in ["api.cu", "plan.cpp", "dft_generic.cu", "pow2_tile.cu", "pow2_pk.cu", "pad.cu", "detrend.cu", "wide_fwd.cu",
+              "wide_inv.cu", "smooth.cu"] {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }

@@ -181,3 +181,12 @@ def test_product_path_never_touches_the_oracle():
     import sys
     code = "import sys, veils_b200; veils_b200.lib(); assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+
+
+def test_rust_build_script_lists_every_source():
+    """rust/build.rs compiles the same translation units as veils_b200/build.py."""
+    import re
+    from veils_b200 import build as vb
+    txt = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "rust", "build.rs")).read()
+    listed = set(re.findall(r'"([\w]+\.(?:cu|cpp))"', txt))
+    assert listed == set(vb.SOURCES)
