@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_const
     c.a = &args;
     c.work = reinterpret_cast<cx<vec_t<T>> *>(smem);
     unsigned char *q = smem + sizeof(cx<T>) * (size_t)args.s.LC * TF;
-    T *xbuf[2] = {reinterpret_cast<T *>(q), reinterpret_cast<T *>(q + xin_bytes)};
+    // the two staging buffers are addressed by arithmetic on the shared-memory base (a pointer picked from an array
+    // would be a generic pointer: LD instead of LDS in pass 1)
+    T *const xin0 = reinterpret_cast<T *>(q);
+    const int xin_elems = xin_bytes / (int)sizeof(T);
     c.tab = q + 2 * xin_bytes;
     stage_tab(q + 2 * xin_bytes, args.tab, args.lay.bytes, tid);
     // (signal, tile) of work item w, advanced by gridDim.x per iteration without a 64-bit division
@@ -35,7 +38,7 @@ __global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_const
     c.pt = blockIdx.x - c.b * args.ptiles;
     const int64_t db = gridDim.x / args.ptiles, dp = gridDim.x - db * args.ptiles;
     if ((int64_t)blockIdx.x < total) {
-        c.xin = xbuf[0];
+        c.xin = xin0;
         Fwd<T, TF>::stage(c, tid, SM_NT);
         p2::cp_async_commit();
     }
@@ -47,11 +50,11 @@ __global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_const
         if (npt >= args.ptiles) { npt -= args.ptiles; ++nb; }
         if (w + gridDim.x < total) {       // stage the next tile into the other buffer while this one is transformed
             FwdCtx<T> cn = c;
-            cn.b = nb; cn.pt = npt; cn.xin = xbuf[it ^ 1];
+            cn.b = nb; cn.pt = npt; cn.xin = xin0 + (it ^ 1) * xin_elems;
             Fwd<T, TF>::stage(cn, tid, SM_NT);
             p2::cp_async_commit();
         }
-        c.xin = xbuf[it];
+        c.xin = xin0 + it * xin_elems;
         for (int p = 0; p < args.s.np; ++p) {
             Fwd<T, TF>::pass(c, p, tid, SM_NT);
             __syncthreads();
