@@ -65,13 +65,24 @@ static int emu_inv(const void *S, int64_t P, int64_t ldp, int64_t batch, const d
     const int NT = 64;
     std::vector<cx<vec_t<T>>> work((size_t)a.s.LC * TF / Vec<T>::W);
     std::vector<T> ola((size_t)TF * a.ostride);
+    std::vector<cx<T>> nyq((size_t)TF);
     InvCtx<T> c;
-    c.a = &a; c.tab = blob.data(); c.work = work.data(); c.ola = ola.data();
+    c.a = &a; c.tab = blob.data(); c.work = work.data(); c.ola = ola.data(); c.nyq = nyq.data();
     for (int64_t blk = 0; blk < a.ntiles * batch; ++blk) {
         c.b = blk / a.ntiles; c.qa = a.qa0 + (blk % a.ntiles) * own;
         for (auto &v : work) v = mk<vec_t<T>>(Vec<T>::bc((T)NAN), Vec<T>::bc((T)NAN));
         for (auto &v : ola) v = (T)NAN;
-        for (int t = 0; t < NT; ++t) Inv<T, TF>::load(c, t, NT);
+        if (Inv<T, TF>::lands(a)) {
+            for (auto &v : nyq) v = mk<T>((T)NAN, (T)NAN);
+            for (int t = 0; t < NT; ++t) Inv<T, TF>::land(c, t, NT);
+            for (int it = 0; it < Inv<T, TF>::merge_iters(a, NT); ++it) {
+                std::vector<typename Inv<T, TF>::MReg> regs(NT);
+                for (int t = 0; t < NT; ++t) Inv<T, TF>::merge_load(c, t, it, NT, regs[t]);
+                for (int t = 0; t < NT; ++t) Inv<T, TF>::merge_store(c, t, it, NT, regs[t]);
+            }
+        } else {
+            for (int t = 0; t < NT; ++t) Inv<T, TF>::load(c, t, NT);
+        }
         for (int p = 0; p < a.s.np; ++p)
             for (int t = 0; t < NT; ++t) Inv<T, TF>::pass(c, p, t, NT);
         for (int t = 0; t < NT; ++t) Inv<T, TF>::gather(c, t, NT);

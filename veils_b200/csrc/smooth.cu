@@ -8,6 +8,9 @@ namespace {
 using namespace sm;
 
 constexpr int SM_NT = 256;
+#ifndef VEILS_SMOOTH_MINB
+#define VEILS_SMOOTH_MINB 2
+#endif
 constexpr size_t SM_SMEM_LIMIT = 227 * 1024;
 
 // cooperative copy of the plan blob into shared memory (16-byte words; the blob is 16-byte padded)
@@ -19,7 +22,7 @@ __device__ __forceinline__ void stage_tab(unsigned char *dst, const unsigned cha
 
 // Persistent forward kernel.  Shared memory: work[LC][TF] | staged samples | plan blob.
 template <typename T, int TF>
-__global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total,
+__global__ void __launch_bounds__(SM_NT, VEILS_SMOOTH_MINB) smooth_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total,
                                                            const int xin_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -65,9 +68,11 @@ __global__ void __launch_bounds__(SM_NT, 2) smooth_fwd_kernel(const __grid_const
     }
 }
 
-// Persistent inverse kernel.  Shared memory: work[LC][TF] | slice rows [TF][ostride] | plan blob.
+template <typename T, int TF> __host__ __device__ constexpr int nyq_bytes() { return (int)((TF * sizeof(cx<T>) + 15) & ~(size_t)15); }
+
+// Persistent inverse kernel.  Shared memory: work[LC][TF] | slice rows [TF][ostride] | Nyquist row | plan blob.
 template <typename T, int TF>
-__global__ void __launch_bounds__(SM_NT, 2) smooth_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total,
+__global__ void __launch_bounds__(SM_NT, VEILS_SMOOTH_MINB) smooth_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total,
                                                            const int ola_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -76,26 +81,47 @@ __global__ void __launch_bounds__(SM_NT, 2) smooth_inv_kernel(const __grid_const
     c.work = reinterpret_cast<cx<vec_t<T>> *>(smem);
     unsigned char *q = smem + sizeof(cx<T>) * (size_t)args.s.LC * TF;
     c.ola = reinterpret_cast<T *>(q);
-    c.tab = q + ola_bytes;
-    stage_tab(q + ola_bytes, args.tab, args.lay.bytes, tid);
+    c.nyq = reinterpret_cast<cx<T> *>(q + ola_bytes);
+    c.tab = q + ola_bytes + nyq_bytes<T, TF>();
+    stage_tab(q + ola_bytes + nyq_bytes<T, TF>(), args.tab, args.lay.bytes, tid);
     const int own = TF - args.halo;
     c.b = blockIdx.x / args.ntiles;
     int64_t ti = blockIdx.x - c.b * args.ntiles;
     const int64_t db = gridDim.x / args.ntiles, dp = gridDim.x - db * args.ntiles;
+    const bool lands = Inv<T, TF>::lands(args);
+    if (lands && (int64_t)blockIdx.x < total) {
+        c.qa = args.qa0 + ti * own;
+        Inv<T, TF>::land(c, tid, SM_NT);
+        p2::cp_async_commit();
+    }
     __syncthreads();
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
         c.qa = args.qa0 + ti * own;
-        Inv<T, TF>::load(c, tid, SM_NT);
+        if (lands) {
+            p2::cp_async_wait_all();
+            __syncthreads();               // the S tile has landed
+            Inv<T, TF>::merge(c, tid, SM_NT);
+        } else {
+            Inv<T, TF>::load(c, tid, SM_NT);
+        }
         __syncthreads();
         for (int p = 0; p < args.s.np; ++p) {
             Inv<T, TF>::pass(c, p, tid, SM_NT);
             __syncthreads();
         }
+        int64_t nb = c.b + db, nti = ti + dp;
+        if (nti >= args.ntiles) { nti -= args.ntiles; ++nb; }
+        if (lands && w + gridDim.x < total) {      // the work buffer is free: the next S tile lands during the overlap-add
+            InvCtx<T> cn = c;
+            cn.b = nb;
+            cn.qa = args.qa0 + nti * own;
+            Inv<T, TF>::land(cn, tid, SM_NT);
+            p2::cp_async_commit();
+        }
         Inv<T, TF>::gather(c, tid, SM_NT);
         __syncthreads();
-        c.b += db;
-        ti += dp;
-        if (ti >= args.ntiles) { ti -= args.ntiles; ++c.b; }
+        c.b = nb;
+        ti = nti;
     }
 }
 
@@ -110,7 +136,8 @@ template <typename T> size_t ola_bytes_of(const Shape &s, int tf) {
 // shared memory without / with the plan blob
 template <typename T> void smem_of(const Shape &s, int tf, bool inverse, size_t *core, size_t *with_tab) {
     const size_t work = sizeof(cx<T>) * (size_t)s.LC * tf;
-    *core = work + (inverse ? ola_bytes_of<T>(s, tf) : 2 * xin_bytes_of<T>(s, tf));   // forward: double-buffered staging
+    *core = work + (inverse ? ola_bytes_of<T>(s, tf) + (size_t)tf * sizeof(cx<T>) + 16   // + landed Nyquist row
+                            : 2 * xin_bytes_of<T>(s, tf));                                // forward: double-buffered staging
     *with_tab = *core + (size_t)tab_layout<T>(s, inverse).bytes;
 }
 // slices per tile: the wide tile when two CTAs of it fit an SM, else the narrow one, else whatever fits (plan blob included)

@@ -480,6 +480,7 @@ struct InvCtx {
     const unsigned char *tab;
     cx<vec_t<T>> *work;      // [LC][LN]
     T *ola;                  // [TF][ostride] windowed slices of the tile
+    cx<T> *nyq;              // [TF] landed Nyquist row (one-sided layouts, even mfft)
     int64_t b, qa;
 };
 
@@ -568,6 +569,101 @@ struct Inv {
             }
             wl[(size_t)k * LN] = za;
             if (k != 0 && 2 * k != LC) wl[(size_t)(LC - k) * LN] = zb;
+        }
+    }
+    // ---- one-sided layouts, even mfft: the S tile LANDS in the work buffer through cp.async while the previous
+    // tile's overlap-add runs (the direct loads left 25 % of the warp time waiting for S: ncu, long scoreboard
+    // at the first add of the merge), and the Hermitian merge runs in place from shared memory.  Raw layout: row
+    // k (bin) = TF complex slots (slice s at slot s) -- exactly the bytes of work row k; the Nyquist row has its own
+    // buffer.  Slices outside [q0, q1) or S arrive as zeros.
+    VHD static bool lands(const InvArgs<T> &p) { return p.s.half != 0 && p.mode >= 2; }
+    VHD static void land(const InvCtx<T> &c, int tid, int nt) {
+        const InvArgs<T> &p = *c.a;
+        const int LC = p.s.LC;
+        if (sizeof(cx<T>) == 8 && TF % 2 == 0 && ((c.qa - p.p_min) & 1) == 0 && (p.ldp & 1) == 0 &&
+            (reinterpret_cast<size_t>(p.S) & 15) == 0) {
+            // f32, even first column: two adjacent slices per 16-byte copy (both in range or both out of it; a
+            // straddling pair falls back to two 8-byte copies)
+            const int s2 = 2 * (tid % (TF / 2));
+            const int64_t q = c.qa + s2, col = q - p.p_min;
+            const bool l0 = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;
+            const bool l1 = q + 1 >= p.q0 && q + 1 < p.q1 && col + 1 >= 0 && col + 1 < p.P;
+            const cx<T> *src = reinterpret_cast<const cx<T> *>(p.S) + (c.b * p.s.F * p.ldp + ((l0 || l1) ? col : 0));
+            cx<T> *raw = reinterpret_cast<cx<T> *>(c.work) + s2;
+            for (int r = tid / (TF / 2); r <= LC; r += nt / (TF / 2)) {
+                cx<T> *dst = r < LC ? raw + (size_t)r * TF : c.nyq + s2;
+                const cx<T> *g = src + (int64_t)r * p.ldp;
+                if (l0 == l1) {
+                    p2::cp_async_zfill<16>(dst, g, l0);
+                } else {
+                    p2::cp_async_zfill<8>(dst, l0 ? g : g + 1, l0);
+                    p2::cp_async_zfill<8>(dst + 1, g + 1, l1);
+                }
+            }
+            return;
+        }
+        const int s = tid % TF;
+        const int64_t q = c.qa + s, col = q - p.p_min;
+        const bool live = q >= p.q0 && q < p.q1 && col >= 0 && col < p.P;        // :855-857
+        const cx<T> *src = reinterpret_cast<const cx<T> *>(p.S) + (c.b * p.s.F * p.ldp + (live ? col : 0));
+        cx<T> *raw = reinterpret_cast<cx<T> *>(c.work) + s;
+        for (int r = tid / TF; r <= LC; r += nt / TF)
+            p2::cp_async_zfill<(int)sizeof(cx<T>)>(r < LC ? raw + (size_t)r * TF : c.nyq + s, src + (int64_t)r * p.ldp, live);
+    }
+    struct MReg { cx<T> xk[Vec<T>::W], xl[Vec<T>::W]; };
+    VHD static int merge_iters(const InvArgs<T> &p, int nt) { const int nsub = nt / (TF / Vec<T>::W); return (p.s.LC / 2 + nsub) / nsub; }
+    // first half: the four raw bins of unit k = sub + it nsub (both slices of the lane, rows k and LC - k) into registers
+    VHD static void merge_load(const InvCtx<T> &c, int tid, int it, int nt, MReg &r) {
+        constexpr int W = Vec<T>::W, LN = TF / W;
+        const int LC = c.a->s.LC, lane = tid % LN, k = tid / LN + it * (nt / LN);
+        if (k > LC / 2) return;
+        const cx<T> *raw = reinterpret_cast<const cx<T> *>(c.work);
+#pragma unroll
+        for (int h = 0; h < W; ++h) {
+            r.xk[h] = raw[(size_t)k * TF + lane + h * LN];
+            r.xl[h] = k == 0 ? c.nyq[lane + h * LN] : raw[(size_t)(LC - k) * TF + lane + h * LN];
+        }
+    }
+    // second half (every lane of the unit has read both rows): Z'[k], Z'[LC - k] over the same rows
+    VHD static void merge_store(const InvCtx<T> &c, int tid, int it, int nt, const MReg &r) {
+        using VT = Vec<T>;
+        using V = typename VT::V;
+        constexpr int W = VT::W, LN = TF / W;
+        const InvArgs<T> &p = *c.a;
+        const int LC = p.s.LC, lane = tid % LN, k = tid / LN + it * (nt / LN);
+        if (k > LC / 2) return;
+        cx<V> Xk = mk<V>(VT::pk(r.xk[0].x, r.xk[W - 1].x), VT::pk(r.xk[0].y, r.xk[W - 1].y));
+        cx<V> Xl = mk<V>(VT::pk(r.xl[0].x, r.xl[W - 1].x), VT::pk(r.xl[0].y, r.xl[W - 1].y));
+        cx<V> za, zb;
+        if (k == 0) {
+            za = mk<V>(Xk.x + Xl.x, Xk.x - Xl.x);                                 // DC pairs with Nyquist (imaginary parts ignored)
+            zb = za;
+        } else {
+            const V rfac = VT::bc(p.rfac2x);                                      // 1 unless onesided2X
+            Xk.x = Xk.x * rfac; Xk.y = Xk.y * rfac; Xl.x = Xl.x * rfac; Xl.y = Xl.y * rfac;
+            const SEnt<T> t = reinterpret_cast<const SEnt<T> *>(c.tab + p.lay.a_off)[k];
+            const cx<V> Xm = mk<V>(Xl.x, VT::neg(Xl.y));
+            const cx<V> E = Xk + Xm, Dm = Xk - Xm;
+            const cx<V> O = mul_tw<true, T>(Dm, t.wr, t.wi);                      // conj(W_M^k) (Xk - conj Xl)
+            const cx<V> iO = mk<V>(VT::neg(O.y), O.x);
+            za = E + iO;
+            const cx<V> Y = E - iO;
+            zb = mk<V>(Y.x, VT::neg(Y.y));
+        }
+        cx<V> *wl = c.work + lane;
+        wl[(size_t)k * LN] = za;
+        if (k != 0 && 2 * k != LC) wl[(size_t)(LC - k) * LN] = zb;
+    }
+    // device flavour of the whole merge (the host emulation runs the two halves for all threads in turn)
+    VHD static void merge(const InvCtx<T> &c, int tid, int nt) {
+        const int iters = merge_iters(*c.a, nt);
+        for (int it = 0; it < iters; ++it) {
+            MReg r;
+            merge_load(c, tid, it, nt, r);
+#if defined(__CUDA_ARCH__)
+            __syncwarp();
+#endif
+            merge_store(c, tid, it, nt, r);
         }
     }
     // spectrum of slice q into the work buffer in natural order; only the real part of the inverse transform
@@ -661,7 +757,53 @@ struct Inv {
             if (col >= H) { col -= H; ++rl; }
         }
     }
+    // four consecutive samples per step (hop % 4 == 0: they share their contributing slices): a quarter of the index
+    // work per sample and one 16-byte store when the output is aligned (ncu: the scalar gather was 26 % of the
+    // inverse's instructions)
+    struct alignas(16) Quad { T v[4]; };
+    template <int HALO>
+    VHD static void gather4_t(const InvCtx<T> &c, int tid, int nt) {
+        const InvArgs<T> &p = *c.a;
+        const int H = p.s.H, N = p.s.N;
+        const int64_t base = c.qa * (int64_t)H - p.mid;                   // k = base + u
+        int64_t ka = base + (int64_t)HALO * H, kb = base + (int64_t)TF * H;
+        if (ka < p.k0) ka = p.k0;
+        if (kb > p.k1) kb = p.k1;
+        T *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
+        const int ua = (int)(ka - base), ub = (int)(kb - base);
+        const int cnt = (TF - HALO) * H, hH = HALO * H, step = p.ostride - H;
+        const bool al = sizeof(T) == 4 && ((reinterpret_cast<size_t>(xo + hH) & 15) == 0);   // e4 and hH are multiples of 4
+        for (int e = 4 * tid; e < cnt; e += 4 * nt) {
+            const int u = e + hH;
+            if (u + 3 < ua || u >= ub) continue;
+            const int rl = mdiv(e, p.s.magicH), col = e - rl * H;
+            const T *q = c.ola + (size_t)rl * p.ostride + col + hH;
+            Quad acc;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc.v[i] = (col + i + hH < N) ? q[i] : (T)0;
+#pragma unroll
+            for (int h = 1; h <= HALO; ++h) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc.v[i] += q[h * step + i];
+            }
+            if (al && u >= ua && u + 3 < ub) {
+                *reinterpret_cast<Quad *>(xo + u) = acc;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (u + i >= ua && u + i < ub) xo[u + i] = acc.v[i];
+            }
+        }
+    }
     VHD static void gather(const InvCtx<T> &c, int tid, int nt) {
+        if (sizeof(T) == 4 && c.a->s.H % 4 == 0 && c.a->halo >= 1 && c.a->halo <= 3) {   // (f64: measured slower)
+            switch (c.a->halo) {
+                case 1: gather4_t<1>(c, tid, nt); break;
+                case 2: gather4_t<2>(c, tid, nt); break;
+                default: gather4_t<3>(c, tid, nt); break;
+            }
+            return;
+        }
         switch (c.a->halo) {
             case 0: gather_t<0>(c, tid, nt); break;
             case 1: gather_t<1>(c, tid, nt); break;
