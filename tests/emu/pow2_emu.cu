@@ -46,7 +46,12 @@ struct EmuFwd {
             for (int t = 0; t < K::NT; ++t) K::fill(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
             for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
-            for (int t = 0; t < K::NT; ++t) K::pass_last(c, t);
+            if (K::UNPAIRED) {
+                for (int t = 0; t < K::NT; ++t) K::last_a(c, t);
+                for (int t = 0; t < K::NT; ++t) K::last_b(c, t);
+            } else {
+                for (int t = 0; t < K::NT; ++t) K::pass_last(c, t);
+            }
         }
         return 0;
     }

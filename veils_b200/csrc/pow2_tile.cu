@@ -89,7 +89,36 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
             K::pass_mid(c, tid);
             __syncthreads();
         }
-        if (STAGE) {
+        if (K::UNPAIRED) {
+            // one last-pass group per thread: Z goes back to the work buffer, the mirror values are read from there
+            K::last_a(c, tid);
+            __syncthreads();
+            if (STAGE) {
+                const int f = tid % TF;
+                const int64_t cb = c.b, cpt = c.pt;
+                const unsigned wbase = tma::smem_u32(c.work);
+                constexpr int MUL = sizeof(T) == 8 ? 2 : 1;  // complex f64 travels as two 8-byte elements
+                auto hook = [&](int g) {
+                    tma::fence_async_smem();
+                    __syncwarp();
+                    if (g >= 0 && f == 0) {
+                        const int mul = args.spectrogram ? 1 : MUL;
+                        const int p0 = (int)(cpt * TF) * mul;
+                        constexpr unsigned RB = TF * (unsigned)sizeof(cx<T>);
+                        tma::store_4d(&smap, wbase + K::GEO::goff(g) * RB, p0, 0, g, (int)cb);
+                        if (g == 0) tma::store_4d(&smap, wbase + K::MCP * RB, p0, K::RL, 0, (int)cb);
+                        tma::commit_group();
+                    }
+                };
+                cx<T> X[K::GPTU][K::RL], xn = mk<T>(0, 0);
+                K::last_x(c, tid, X, xn);
+                __syncthreads();           // every mirror value has been read: the rows may take the finished bins
+                if (args.spectrogram) K::template last_put<true, true, true>(c, tid, X, xn, hook);
+                else K::template last_put<true, false, true>(c, tid, X, xn, hook);
+            } else {
+                K::last_b(c, tid);
+            }
+        } else if (STAGE) {
             const int f = tid % TF;
             const int64_t cb = c.b, cpt = c.pt;
             const unsigned wbase = tma::smem_u32(c.work);
@@ -163,8 +192,11 @@ pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, co
 
 struct FwdLaunch {
     const void *x; void *out; const FwdParams *prm; const void *win; const void *tw; cudaStream_t st;
-    template <typename T, int LOGMC, int TF, int NSUB>
+    template <typename T, int LOGMC, int TF, int NSUB0>
     cudaError_t run() {
+        // VEILS_F64_FWD_UNPAIRED: the last pass works one group per thread (Fwd::last_a / last_x), so twice the threads find work
+        constexpr int GL = (1 << LOGMC) / Fwd<T, LOGMC, TF, NSUB0>::RL;
+        constexpr int NSUB = (VEILS_F64_FWD_UNPAIRED && sizeof(T) == 8 && 2 * TF * NSUB0 <= 512 && 2 * NSUB0 <= GL) ? 2 * NSUB0 : NSUB0;
         using K = Fwd<T, LOGMC, TF, NSUB>;
         const FwdParams &p = *prm;
         FwdArgs<T> a = make_fwd_args<T>((const T *)x, out, p, (const T *)win, (const T *)tw, TF);

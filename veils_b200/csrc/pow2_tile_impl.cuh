@@ -505,6 +505,98 @@ struct Fwd : Geo<T, LOGMC, TF_, NSUB_> {
             if (STAGE) hook(s);
         }
     }
+    // ---- last pass, one group per thread (f64): keeping both mirrored groups in one thread costs 2 x RL complex
+    // doubles (212 registers, 8 warps per SM).  Here every thread transforms ONE group and writes its Z back over
+    // the rows it read (last_a); after a CTA barrier it reads the RL mirror values Z[Mc - k] from the partner
+    // group's rows and splits only its own bins (last_x) -- half the registers, twice the threads; the price is one
+    // shared-memory round trip of Z and 5 more flops per bin.  last_put stores the bins (STAGE: over the thread's
+    // own rows, behind a second barrier, for the TMA boxes).
+    // Measured on B200: NOT a win -- c2 geometry in f64 54.4 % (paired: 55.1 %), c1 forward 74 us (60), c5 3.2 ms
+    // (2.1): the second pass over shared memory, two more barriers and the spills at 128 registers cost more than
+    // the doubled warps bring.  Kept behind a switch (the host emulation follows the same switch).
+#ifndef VEILS_F64_FWD_UNPAIRED
+#define VEILS_F64_FWD_UNPAIRED 0
+#endif
+    static constexpr bool UNPAIRED = VEILS_F64_FWD_UNPAIRED && sizeof(T) == 8;
+    static constexpr int GPTU = (G + NSUB - 1) / NSUB;       // groups per thread
+    VHD static void last_a(const FwdCtx<T> &c, int tid) {
+        const int f = tid % TF, sub = tid / TF;
+#pragma unroll 1
+        for (int g = sub; g < G; g += NSUB) {
+            C u[RL];
+            C *w = c.work + GEO::goff(g) * TF + f;
+#pragma unroll
+            for (int d = 0; d < RL; ++d) u[d] = w[d * TF];
+            Dft<RL, false, T>::run(u);
+#pragma unroll
+            for (int d = 0; d < RL; ++d) w[d * TF] = u[d];
+        }
+    }
+    // X[k], k = g + G d, of this thread's groups; xn = X[Mc] (held by the thread of group 0)
+    VHD static void last_x(const FwdCtx<T> &c, int tid, C (&X)[GPTU][RL], C &xn) {
+        const int f = tid % TF, sub = tid / TF;
+        const T *twp = c.tw + GEO::TWP;
+#pragma unroll
+        for (int i = 0; i < GPTU; ++i) {
+            const int g = sub + NSUB * i;
+            if (g >= G) continue;
+            const int gp = g == 0 ? 0 : G - g;
+            const C *w = c.work + GEO::goff(g) * TF + f, *wp = c.work + GEO::goff(gp) * TF + f;
+#pragma unroll
+            for (int d = 0; d < RL; ++d) {
+                const int dp = g == 0 ? (RL - d) % RL : RL - 1 - d;      // Mc - (g + G d) = gp + G dp
+                const C A = w[d * TF], Zp = wp[dp * TF];
+                const C B = conj(Zp);
+                const C E = A + B, Om = A - B;
+                const C tw = GEO::tlc(twp + 2 * (g + G * d));             // W_M^k
+                const C D = cmul(mk<T>(tw.y, -tw.x), Om);               // (-i W) (A - B)
+                X[i][d] = E + D;
+                if (g == 0 && d == 0) xn = conj(E - D);
+            }
+        }
+    }
+    template <bool ONES, bool SPEC, bool STAGE, typename HOOK>
+    VHD static void last_put(const FwdCtx<T> &c, int tid, const C (&X)[GPTU][RL], C xn, HOOK hook) {
+        const FwdArgs<T> &p = c.a;
+        const int f = tid % TF, sub = tid / TF;
+        const int64_t pl = c.pt * TF + f;
+        const bool live = STAGE || pl < p.P;
+        const int64_t esz = SPEC ? sizeof(T) : sizeof(C);
+        const int64_t rb = p.ldp * esz;
+        char *ob = STAGE ? reinterpret_cast<char *>(c.work) + f * esz
+                         : reinterpret_cast<char *>(p.out) + ((c.b * p.F) * p.ldp + pl) * esz;
+#pragma unroll
+        for (int i = 0; i < GPTU; ++i) {
+            const int g = sub + NSUB * i;
+            if (g >= G) {
+                if (STAGE) hook(-1);
+                continue;
+            }
+            if (live) {
+#pragma unroll
+                for (int d = 0; d < RL; ++d) store_bin<ONES, SPEC, STAGE>(p, ob, rb, g + G * d, X[i][d]);
+                if (g == 0) store_bin<ONES, SPEC, STAGE>(p, ob, rb, MC, xn);
+            }
+            if (STAGE) hook(g);
+        }
+    }
+    template <bool ONES, bool SPEC>
+    VHD static void last_b_t(const FwdCtx<T> &c, int tid) {
+        C X[GPTU][RL], xn = mk<T>(0, 0);
+        last_x(c, tid, X, xn);
+        last_put<ONES, SPEC, false>(c, tid, X, xn, NoHook());
+    }
+    // host emulation / plain-store device path: last_a for every thread, barrier, last_b for every thread
+    VHD static void last_b(const FwdCtx<T> &c, int tid) {
+        const int spectrogram = c.a.spectrogram;
+        if (c.a.mode >= 2) {
+            if (spectrogram) last_b_t<true, true>(c, tid);
+            else last_b_t<true, false>(c, tid);
+        } else {
+            if (spectrogram) last_b_t<false, true>(c, tid);
+            else last_b_t<false, false>(c, tid);
+        }
+    }
     VHD static void pass_last(const FwdCtx<T> &c, int tid) {
         const int spectrogram = c.a.spectrogram;
         if (c.a.mode >= 2) {
