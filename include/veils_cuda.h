@@ -172,7 +172,10 @@ int32_t veils_stft_dev_padded(veils_plan *p, const void *x, int64_t n, int64_t b
 /* stft_detrend of the twin (python/standalone_stft.py:38-50, 345-371; not in the Rust crate):
  * detr = NULL | "constant" (slice mean removed) | "linear" (least-squares line removed), applied
  * to every slice before windowing -- realised as the rank-2 correction S - a_p W1 - b_p W0 of the
- * plain stft.  coef_ws: device workspace of 16 bytes per slice and signal (batch * (p1-p0) * 16). */
+ * plain stft.  coef_ws: device workspace of 16 bytes per slice and signal (batch * (p1-p0) * 16).
+ * Accuracy: the correction is applied to S already rounded to the plan's precision, so in f32 its
+ * absolute error is ~1e-7 of the UN-detrended spectrum's magnitude; for signals with a large offset or
+ * ramp (where that dwarfs the detrended content) use an f64 plan, which meets the twin at 1e-12. */
 int32_t veils_stft_detrend_dev(veils_plan *p, const void *x, int64_t n, int64_t batch,
                                int64_t x_pitch, const int64_t *p0, const int64_t *p1,
                                int64_t k_offset, const char *padding, const char *detr, void *x_ext,
