@@ -60,3 +60,44 @@ def test_device_tensors_and_determinism_400_160():
     y = st.istft(S)
     assert torch.equal(y, st.istft(S))
     assert float((y[:, :160000] - x).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("f64", 1e-12), ("f32", 2e-5)])
+def test_randomized_mixed_radix_geometry(prec, tol):
+    """Randomized geometry for the mixed-radix family: smooth mfft (even and odd), window shorter than mfft, arbitrary
+    hop, roll, k_offset, slice and sample sub-ranges, very short signals, all four layouts."""
+    rng = np.random.default_rng(4242)
+    smooth = [6, 10, 12, 15, 18, 20, 21, 24, 30, 36, 45, 48, 60, 63, 70, 72, 90, 96, 100, 120, 126, 150, 160, 200, 240,
+              243, 250, 320, 360, 400, 441, 480, 486, 500, 600, 625, 640, 720, 800, 882, 960, 1000, 1200, 1215]
+    seen = 0
+    for it in range(36):
+        M = int(rng.choice(smooth))
+        N = int(M if rng.random() < 0.5 else rng.integers(max(2, M // 2), M + 1))
+        H = int(rng.choice([max(1, N // 4), max(1, N // 2), max(1, N // 3), int(rng.integers(1, N + 1))]))
+        mode = str(rng.choice(["onesided", "twosided", "centered", "onesided2X"]))
+        ps = int(rng.integers(-M + 1, M)) if rng.random() < 0.4 else 0
+        scale = rng.choice([None, None, "magnitude", "psd"])
+        win = rng.uniform(0.2, 1.0, N)
+        n = int(rng.integers(N, N + 60 * H + 50)) if rng.random() < 0.8 else int(N - N // 2 + rng.integers(0, 3))
+        x = rng.uniform(-1, 1, (2, n)).astype(np.float32 if prec == "f32" else np.float64)
+        o = OracleSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale)
+        s = StandaloneSTFT(win, H, 8000.0, fft_mode=mode, mfft=M, phase_shift=ps, scale_to=scale, precision=prec)
+        if s.kernel_name() != "mixed_radix":
+            continue
+        seen += 1
+        koff = int(rng.integers(-3, 4))
+        xr = x.astype(np.float64)
+        Sref = np.stack([o.stft(r, k_offset=koff) for r in xr])
+        assert rel_err(s.stft(x, k_offset=koff), Sref) <= tol, (M, N, H, mode, ps, n)
+        assert rel_err(s.spectrogram(x, k_offset=koff), np.abs(Sref) ** 2) <= 4 * tol, (M, N, H, mode, ps, n)
+        if o.invertible and s.kernel_name(True) == "mixed_radix":
+            S0 = np.stack([o.stft(r) for r in xr])
+            S0 = S0.astype(np.complex64 if prec == "f32" else np.complex128)
+            yref = np.stack([o.istft(q.astype(np.complex128)) for q in S0])
+            assert rel_err(s.istft(S0), yref) <= tol, (M, N, H, mode, ps, n)
+            if n > 2 * N:
+                k0 = int(rng.integers(0, n // 3))
+                k1 = int(rng.integers(k0 + N, n))
+                yr2 = np.stack([o.istft(q.astype(np.complex128), k0, k1) for q in S0])
+                assert rel_err(s.istft(S0, k0, k1), yr2) <= tol, (M, N, H, mode, ps, n, k0, k1)
+    assert seen >= 20
