@@ -57,7 +57,7 @@ static int emu_inv(const void *S, int64_t P, int64_t ldp, int64_t batch, const d
     tab_fill<T>(a.s, true, d.data(), blob.data());
     a.S = S; a.xo = xo; a.tab = blob.data();
     a.P = P; a.ldp = ldp; a.out_pitch = out_pitch; a.p_min = p_min; a.k0 = k0; a.k1 = k1; a.q0 = q0; a.q1 = q1;
-    a.mid = (int)mid; a.mode = mode; a.ostride = (int)(N | 1); a.rfac2x = (T)(1.0 / fac2x);
+    a.mid = (int)mid; a.mode = mode; a.ostride = ostride_of<T>(N, H); a.rfac2x = (T)(1.0 / fac2x);
     const int own = TF - a.halo;
     const int64_t qh0 = p2::fdiv64(k0 + mid, H), qh1 = p2::fdiv64(k1 - 1 + mid, H);
     a.ntiles = (qh1 - qh0 + 1 + own - 1) / own;

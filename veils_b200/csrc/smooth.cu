@@ -131,7 +131,7 @@ template <typename T> size_t xin_bytes_of(const Shape &s, int tf) {
     return (size_t)al16((int64_t)sizeof(T) * (rows * (s.H + xpad_of(s.H)) + 4));
 }
 template <typename T> size_t ola_bytes_of(const Shape &s, int tf) {
-    return (size_t)al16((int64_t)sizeof(T) * tf * ((s.N | 1) + 0));
+    return (size_t)al16((int64_t)sizeof(T) * tf * ostride_of<T>(s.N, s.H));
 }
 // shared memory without / with the plan blob
 template <typename T> void smem_of(const Shape &s, int tf, bool inverse, size_t *core, size_t *with_tab) {
@@ -235,7 +235,7 @@ cudaError_t smooth_inverse(const void *S, T *x_out, const InvParams &p, const vo
     a.S = S; a.xo = x_out; a.tab = (const unsigned char *)tab; a.lay = sm::tab_layout<T>(a.s, true);
     a.P = p.P; a.ldp = p.ldp; a.out_pitch = p.out_pitch; a.p_min = p.p_min;
     a.k0 = p.k0; a.k1 = p.k1; a.q0 = p.q0; a.q1 = p.q1; a.qa0 = 0; a.ntiles = 0;
-    a.mid = (int)p.mid; a.mode = p.mode; a.halo = halo_of(p.N, p.H); a.ostride = (int)(p.N | 1);
+    a.mid = (int)p.mid; a.mode = p.mode; a.halo = halo_of(p.N, p.H); a.ostride = sm::ostride_of<T>(p.N, p.H);
     a.rfac2x = p.mode == 3 ? (T)(1.0 / p.fac2x) : (T)1;
     constexpr int TFA = sizeof(T) == 4 ? 32 : 16, TFB = sizeof(T) == 4 ? 16 : 8, TFC = sizeof(T) == 4 ? 8 : 4;
     const int tf = pick_tf<T>(a.s, true);

@@ -111,6 +111,12 @@ template <typename T> inline TabLayout tab_layout(const Shape &s, bool inverse) 
     return l;
 }
 inline int xpad_of(int64_t H) { return (H % 2 == 0) ? 1 : 0; }      // odd slice stride: lanes on distinct banks
+// pitch of the inverse's slice rows: odd (lanes = slices on distinct banks); f32 with hop % 4 == 0: = 2 (mod 4), which
+// keeps the 16 lanes of a unit on distinct (even) banks AND the rows 8-byte aligned for the four-sample gather
+template <typename T> inline int ostride_of(int64_t N, int64_t H) {
+    if (sizeof(T) == 4 && H % 4 == 0) { int64_t s = N; while (s % 4 != 2) ++s; return (int)s; }
+    return (int)(N | 1);
+}
 // vec: forward = window [N]; inverse = dual window * 1/M (one-sided) or 1/(2M) (two-sided), [N]
 template <typename T> inline void tab_fill(const Shape &s, bool inverse, const double *vec, unsigned char *out) {
     const TabLayout l = tab_layout<T>(s, inverse);
@@ -807,13 +813,20 @@ struct Inv {
             if (u + 3 < ua || u >= ub) continue;
             const int rl = mdiv(e, p.s.magicH), col = e - rl * H;
             const T *q = c.ola + (size_t)rl * p.ostride + col + hH;
+            // rows are 8-byte aligned (ostride_of) and col, hH multiples of 4: two 8-byte reads per row
+            struct alignas(8) Pair { T a, b; };
             Quad acc;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc.v[i] = (col + i + hH < N) ? q[i] : (T)0;
+            {
+                const Pair p0 = *reinterpret_cast<const Pair *>(q), p1 = *reinterpret_cast<const Pair *>(q + 2);
+                acc.v[0] = (col + hH < N) ? p0.a : (T)0;
+                acc.v[1] = (col + 1 + hH < N) ? p0.b : (T)0;
+                acc.v[2] = (col + 2 + hH < N) ? p1.a : (T)0;
+                acc.v[3] = (col + 3 + hH < N) ? p1.b : (T)0;
+            }
 #pragma unroll
             for (int h = 1; h <= HALO; ++h) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc.v[i] += q[h * step + i];
+                const Pair p0 = *reinterpret_cast<const Pair *>(q + h * step), p1 = *reinterpret_cast<const Pair *>(q + h * step + 2);
+                acc.v[0] += p0.a; acc.v[1] += p0.b; acc.v[2] += p1.a; acc.v[3] += p1.b;
             }
             if (al && u >= ua && u + 3 < ub) {
                 *reinterpret_cast<Quad *>(xo + u) = acc;
