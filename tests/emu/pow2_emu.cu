@@ -72,23 +72,37 @@ struct EmuInv {
         if ((size_t)TF * c.a.ostride > elems) elems = (size_t)TF * c.a.ostride;
         std::vector<T> buf(elems + 4);
         c.work = (cx<T> *)buf.data(); c.ola = buf.data(); c.tw = tw.data(); c.dual = dual.data();
-        const int own = TF - c.a.halo;
         std::vector<cx<T>> regs((size_t)K::NT * K::GPT * K::RL);
-        for (int64_t blk = 0; blk < c.a.ntiles * prm.batch; ++blk) {
-            c.b = blk / c.a.ntiles; c.qa = c.a.qa0 + (blk % c.a.ntiles) * own;
-            for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
-            for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
-            for (int t = 0; t < K::NT; ++t) {
-                cx<T> r[K::GPT][K::RL];
-                K::last_load(c, t, r);
-                std::memcpy(&regs[(size_t)t * K::GPT * K::RL], r, sizeof(r));
+        tile_inv_chunks<T>(c.a, prm, TF, prm.batch, emu_grid_hint);
+        std::vector<T> carry0(inv_carry_elems(prm.N, prm.H) + 1, (T)NAN), carry1(inv_carry_elems(prm.N, prm.H) + 1, (T)NAN);
+        const int64_t lc = (int64_t)TF * c.a.chunk_tiles - c.a.halo;
+        for (int64_t ch = 0; ch < c.a.cps * prm.batch; ++ch) {
+            c.b = ch / c.a.cps;
+            const int64_t a0 = c.a.qh0 + (ch - c.b * c.a.cps) * lc;
+            c.kown = a0 * (int64_t)c.a.H - c.a.mid;
+            int flip = 0;
+            for (int tl = 0; tl < c.a.chunk_tiles; ++tl) {
+                c.qa = a0 - c.a.halo + (int64_t)tl * TF;
+                if (c.qa > c.a.qh1) break;
+                c.first = tl == 0;
+                c.last = tl + 1 >= c.a.chunk_tiles || c.qa + TF > c.a.qh1;
+                c.carry_in = flip ? carry1.data() : carry0.data();
+                c.carry_out = flip ? carry0.data() : carry1.data();
+                flip ^= 1;
+                for (int t = 0; t < K::NT; ++t) K::pass1(c, t);
+                for (int t = 0; t < K::NT; ++t) K::pass_mid(c, t);
+                for (int t = 0; t < K::NT; ++t) {
+                    cx<T> r[K::GPT][K::RL];
+                    K::last_load(c, t, r);
+                    std::memcpy(&regs[(size_t)t * K::GPT * K::RL], r, sizeof(r));
+                }
+                for (int t = 0; t < K::NT; ++t) {
+                    cx<T> r[K::GPT][K::RL];
+                    std::memcpy(r, &regs[(size_t)t * K::GPT * K::RL], sizeof(r));
+                    K::last_store(c, t, r);
+                }
+                for (int t = 0; t < K::NT; ++t) K::gather_s(c, t);
             }
-            for (int t = 0; t < K::NT; ++t) {
-                cx<T> r[K::GPT][K::RL];
-                std::memcpy(r, &regs[(size_t)t * K::GPT * K::RL], sizeof(r));
-                K::last_store(c, t, r);
-            }
-            for (int t = 0; t < K::NT; ++t) K::gather(c, t);
         }
         return 0;
     }

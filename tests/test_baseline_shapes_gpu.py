@@ -154,3 +154,24 @@ def test_sample_indices_beyond_2_31():
         assert rel_err(S.cpu().numpy(), ref) <= 1e-5, padding
     t = st.t(n, p0, p1)
     assert abs(t[-1] - (p1 - 1) * 128 / 16000.0) <= 1e-9 * t[-1]
+
+
+@pytest.mark.parametrize("m,hop", [(8192, 2048), (4096, 1024), (4096, 512)])
+def test_large_mfft_f64_inverse_streams(m, hop):
+    """f64 tiles of mfft 8192 / 4096 hold 2 / 4 slices -- fewer than the 3 (or 7) slices an output sample overlaps.
+    The streaming overlap-add carries the partial sums from tile to tile, so these plans invert on the pow2 kernels
+    (they used to fall back to the O(M^2) family) and match the oracle at 1e-12."""
+    rng = np.random.default_rng(m + hop)
+    win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(m) / m))
+    st = StandaloneSTFT(win, hop, 16000.0, precision="f64")
+    o = OracleSTFT(win, hop, 16000.0)
+    assert st.kernel_name(True) == "pow2_tile"
+    n = 5 * m + 37 if hop >= 1024 else 2 * m + 300
+    x = rng.uniform(-1, 1, (2, n))
+    S = np.stack([o.stft(r) for r in x])
+    y = st.istft(S)
+    yref = np.stack([o.istft(s) for s in S])
+    assert rel_err(y, yref) <= 1e-12
+    assert np.max(np.abs(y[:, :n] - x)) <= 1e-11
+    k0, k1 = m // 2 + 3, n - m // 3
+    assert np.array_equal(st.istft(S[0], k0, k1), y[0, k0:k1])          # same summation order -> same bits

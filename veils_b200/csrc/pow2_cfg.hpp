@@ -138,10 +138,11 @@ inline size_t inv_work_bytes_t(int64_t N) {
     if (ola > work) work = ola;
     return (work + 15) & ~(size_t)15;
 }
+inline size_t inv_carry_elems(int64_t N, int64_t H) { return (size_t)((N - H + 3) & ~int64_t(3)); }   // one carry buffer (N - H), 16-byte multiple
 template <typename T, int LOGMC, int TF>
-inline size_t inv_smem_bytes_t(int64_t N) {
+inline size_t inv_smem_bytes_t(int64_t N, int64_t H) {
     using G = Geo<T, LOGMC, TF, 1>;
-    size_t b = inv_work_bytes_t<T, LOGMC, TF>(N);
+    size_t b = inv_work_bytes_t<T, LOGMC, TF>(N) + 2 * sizeof(T) * inv_carry_elems(N, H);   // + the two carry buffers
     if (G::STAB) b += sizeof(T) * ((size_t)G::TWN + (size_t)N);
     return b;
 }
@@ -149,7 +150,7 @@ struct SmemQuery {
     int64_t N, H, ps; bool inverse;
     template <typename T, int LOGMC, int TF, int NSUB>
     long long run() {
-        if (inverse) return (long long)inv_smem_bytes_t<T, LOGMC, TF>(N);
+        if (inverse) return (long long)inv_smem_bytes_t<T, LOGMC, TF>(N, H);
         const TileLayout l = fwd_layout<T>(H, fwd_vec(ps, H, N), TF);
         return (long long)fwd_smem_bytes_t<T, LOGMC, TF>(N, fwd_xin_elems(N, H, TF, l));
     }
@@ -204,6 +205,23 @@ inline InvArgs<T> make_inv_args(const void *S, T *xo, const InvParams &p, const 
     return a;
 }
 
+// streaming overlap-add: chunk geometry of a launch (owned slices qh0 .. qh1 per signal; a chunk = chunk_tiles
+// consecutive tiles walked by one CTA, the first of which re-computes the `halo` slices before its first owned one)
+template <typename T>
+inline void tile_inv_chunks(InvArgs<T> &a, const InvParams &p, int tf, int64_t batch, int64_t grid_hint) {
+    a.qh0 = fdiv64(p.k0 + p.mid, p.H);
+    a.qh1 = fdiv64(p.k1 - 1 + p.mid, p.H);
+    const int64_t Q = a.qh1 - a.qh0 + 1;
+    int ct = (50 * a.halo + tf - 1) / tf;              // halo re-computation <= ~2 % of a chunk
+    const int ctmin = a.halo / tf + 1;                 // at least one owned slice per chunk (small problems: one tile
+                                                       // per chunk = independent tiles, the shortest critical path)
+    if (ct < ctmin) ct = ctmin;
+    if (ct > 256) ct = 256;
+    auto cps = [&](int c) { const int64_t lc = (int64_t)tf * c - a.halo; return (Q + lc - 1) / lc; };
+    while (ct > ctmin && batch * cps(ct) < 4 * grid_hint) --ct;   // enough chunks to balance the CTAs
+    a.chunk_tiles = ct;
+    a.cps = cps(ct);
+}
 // Calls fn.template run<T, LOGMC, TF, NSUB>() for the configuration of (M, precision).
 #define VEILS_P2_CASE(T, LM, TFV)                                             \
     case LM: {                                                                \
@@ -237,7 +255,7 @@ inline bool supported(int64_t M, int64_t N, int64_t H, int64_t ps, int precision
     if (N > M || H < 2 || H >= 65536) return false;
     if (inverse) {
         if (H > N) return false;
-        if (inv_halo(N, H) >= c.tf) return false;     // at least one owned slice per tile
+        // (streaming overlap-add: tiles may be narrower than the overlap)
     }
     SmemQuery q{N, H, ps, inverse};
     const long long need = dispatch(precision, c.logmc, q);

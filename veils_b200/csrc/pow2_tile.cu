@@ -150,7 +150,7 @@ pow2_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total, co
 // Persistent inverse kernel.  Shared memory: work[Mc][TF] (aliased by ola) | (STAB) twiddles, dual.
 template <typename T, int LOGMC, int TF, int NSUB>
 __global__ void __launch_bounds__(TF *NSUB, min_ctas<T, LOGMC, TF>())
-pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, const int work_bytes) {
+pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, const int work_bytes, const int carry_elems) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using K = Inv<T, LOGMC, TF, NSUB>;
     const int tid = threadIdx.x;
@@ -158,8 +158,10 @@ pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, co
     c.a = args;
     c.work = reinterpret_cast<cx<T> *>(smem);
     c.ola = reinterpret_cast<T *>(smem);
+    T *carry0 = reinterpret_cast<T *>(smem + work_bytes);
+    T *carry1 = carry0 + carry_elems;
     if (K::STAB) {
-        T *stw = reinterpret_cast<T *>(smem + work_bytes);
+        T *stw = carry1 + carry_elems;
         T *sdual = stw + K::TWN;
         copy_table(stw, args.tw, K::TWN, tid, K::NT);
         copy_table(sdual, args.dual, args.N, tid, K::NT);
@@ -170,23 +172,37 @@ pow2_inv_kernel(const __grid_constant__ InvArgs<T> args, const int64_t total, co
         c.dual = args.dual;
     }
     __syncthreads();
-    const int own = TF - args.halo;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-        c.b = w / args.ntiles;
-        c.qa = args.qa0 + (w - c.b * args.ntiles) * own;
-        K::pass1(c, tid);
-        __syncthreads();
-        if (K::NP == 3) {
-            K::pass_mid(c, tid);
+    // streaming overlap-add: a CTA walks the tiles of one chunk of one signal in order; only the first tile of a chunk
+    // re-computes the `halo` slices before its first owned one, every other tile owns all TF slices
+    const int64_t lc = (int64_t)TF * args.chunk_tiles - args.halo;       // owned slices per chunk
+    for (int64_t ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        c.b = ch / args.cps;
+        const int64_t a0 = args.qh0 + (ch - c.b * args.cps) * lc;         // first owned slice
+        c.kown = a0 * (int64_t)args.H - args.mid;
+        int flip = 0;
+#pragma unroll 1
+        for (int t = 0; t < args.chunk_tiles; ++t) {
+            c.qa = a0 - args.halo + (int64_t)t * TF;
+            if (c.qa > args.qh1) break;
+            c.first = t == 0;
+            c.last = t + 1 >= args.chunk_tiles || c.qa + TF > args.qh1;
+            c.carry_in = flip ? carry1 : carry0;
+            c.carry_out = flip ? carry0 : carry1;
+            flip ^= 1;
+            K::pass1(c, tid);
             __syncthreads();
+            if (K::NP == 3) {
+                K::pass_mid(c, tid);
+                __syncthreads();
+            }
+            cx<T> r[K::GPT][K::RL];
+            K::last_load(c, tid, r);
+            __syncthreads();               // all reads of `work` done before it becomes `ola`
+            K::last_store(c, tid, r);
+            __syncthreads();
+            K::gather_s(c, tid);
+            __syncthreads();               // `ola` consumed before the next tile overwrites `work`
         }
-        cx<T> r[K::GPT][K::RL];
-        K::last_load(c, tid, r);
-        __syncthreads();                   // all reads of `work` done before it becomes `ola`
-        K::last_store(c, tid, r);
-        __syncthreads();
-        K::gather(c, tid);
-        __syncthreads();                   // `ola` consumed before the next tile overwrites `work`
     }
 }
 
@@ -250,19 +266,19 @@ struct InvLaunch {
         // f64: pass 1 works one group per thread (Inv::pass1_u), so twice the threads find work
         constexpr int NSUB = (sizeof(T) == 8 && 2 * TF * NSUB0 <= VEILS_F64_INV_MAXT) ? 2 * NSUB0 : NSUB0;
         const InvParams &p = *prm;
-        if (TF - inv_halo(p.N, p.H) < 1) return cudaErrorInvalidConfiguration;
         InvArgs<T> a = make_inv_args<T>(S, (T *)xo, p, (const T *)dual, (const T *)tw, TF);
         const int work_bytes = (int)inv_work_bytes_t<T, LOGMC, TF>(p.N);
-        const size_t smem = inv_smem_bytes_t<T, LOGMC, TF>(p.N);
+        const size_t smem = inv_smem_bytes_t<T, LOGMC, TF>(p.N, p.H);
         auto kern = pow2_inv_kernel<T, LOGMC, TF, NSUB>;
         static KernelSlot slot;
         int per_sm = 0, dev = 0;
         cudaError_t e = prepare_kernel(slot, kern, TF * NSUB, smem, &per_sm, &dev);
         if (e != cudaSuccess) return e;
-        const int64_t total = a.ntiles * p.batch;
         const int64_t cap = (int64_t)per_sm * device_sms(dev);
+        tile_inv_chunks<T>(a, p, TF, p.batch, cap);
+        const int64_t total = a.cps * p.batch;
         const unsigned grid = (unsigned)(total < cap ? total : cap);
-        kern<<<grid, TF * NSUB, smem, st>>>(a, total, work_bytes);
+        kern<<<grid, TF * NSUB, smem, st>>>(a, total, work_bytes, (int)inv_carry_elems(p.N, p.H));
         ++g_launch_count;
         return cudaGetLastError();
     }

@@ -638,6 +638,11 @@ struct InvCtx {
     cx<T> *work;             // [MC][TF]  (shared)
     T *ola;                  // [TF][ostride] -- ALIASES work
     int64_t b, qa;           // signal, first slice computed by this tile
+    // streaming overlap-add (tile family, round 2): a CTA walks the tiles of one chunk of one signal in order
+    const T *carry_in;       // [N - H] partial sums (earlier tiles' slices) of the samples that follow the previous tile
+    T *carry_out;            // [N - H] ... of the samples that follow this tile
+    int first, last;         // first tile of its chunk: no carry in; last tile: no carry out
+    int64_t kown;            // first sample the chunk owns (its leading `halo` slices are re-computed for it)
 };
 
 template <typename T, int LOGMC, int TF_, int NSUB_>
@@ -898,6 +903,74 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
             case 1: gather_t<1>(c, tid); break;
             case 3: gather_t<3>(c, tid); break;
             default: gather_t<-1>(c, tid); break;
+        }
+    }
+
+    // ---- STREAMING overlap-add (src/lib.rs:853-911), increasing q: a CTA walks the tiles of one chunk of one signal
+    // in order; local sample u = k + mid - qa H.
+    //   u in [0, TF H)             : completed by this tile -> global memory; what earlier tiles' slices contributed
+    //                                arrives in carry_in (u < N - H).  Only the first tile of a chunk re-computes the
+    //                                `halo` slices before its first owned one (kown clips its output).
+    //   u in [TF H, TF H + N - H)  : partial sums over the slices so far -> carry_out (a carry that reaches beyond
+    //                                the next tile -- tiles narrower than the overlap -- is forwarded).
+    // The sums run over earlier tiles' slices first, then this tile's in increasing q: the reference's order whatever
+    // the tiling; everything is owned by this CTA: deterministic, no atomics.  Tiles need not be wider than the
+    // overlap, which is what lets the two- and four-slice f64 tiles of mfft 8192 / 4096 invert 75 % overlap at all.
+    // (a plain loop over the overlap, not unrolled, and nothing else: unrolled / templated forms and a second loop form
+    // for long overlaps each measured 8 % slower on the c2 geometry in f64 -- the kernel sits at its 128-register cap)
+    VHD static T ola_sum(const InvCtx<T> &c, int u, T acc) {
+        const InvArgs<T> &p = c.a;
+        const int H = p.H, N = p.N, halo = p.halo;
+        const int rq = (int)mulhi_u32((unsigned)u, p.magic_h);           // u / H: latest contributing slice (tile index)
+        int r = rq - halo;
+        int jj = u - r * H;
+        for (int h = 0; h <= halo; ++h, ++r, jj -= H)
+            if (r >= 0 && r < TF && jj < N) acc += c.ola[r * p.ostride + jj];
+        return acc;
+    }
+    template <int HALO>
+    VHD static void gather_s_t(const InvCtx<T> &c, int tid) {
+        const InvArgs<T> &p = c.a;
+        const int H = p.H, N = p.N, halo = HALO >= 0 ? HALO : p.halo;
+        const int TFH = TF * H, NH = N - H, hH = halo * H, step = p.ostride - H;
+        const int64_t base = c.qa * (int64_t)H - p.mid;                  // k = base + u
+        T *xo = p.xo + c.b * p.out_pitch - p.k0 + base;
+        int64_t ka = base, kb = base + TFH;
+        if (ka < c.kown) ka = c.kown;
+        if (ka < p.k0) ka = p.k0;
+        if (kb > p.k1) kb = p.k1;
+        if (ka > kb) ka = kb;
+        const int ua = (int)(ka - base), ub = (int)(kb - base);
+        // (1) the bulk u in [halo H, TF H): every contributing slice is local
+        for (int e = tid; e < TFH - hH; e += NT) {
+            const int u = e + hH;
+            if (u < ua || u >= ub) continue;
+            const int r = (int)mulhi_u32((unsigned)e, p.magic_h);         // e / H
+            const int jj = e - r * H + hH;                               // offset inside slice r (the oldest contributor)
+            const T *q = c.ola + r * p.ostride + jj;
+            T acc = jj < N ? q[0] : (T)0;                                // only the oldest can fall beyond the window length
+            if (HALO >= 0) {
+#pragma unroll
+                for (int h = 1; h <= (HALO >= 0 ? HALO : 0); ++h) acc += q[h * step];
+            } else {
+                for (int h = 1; h <= halo; ++h) acc += q[h * step];
+            }
+            xo[u] = acc;
+        }
+        // (2) the head u in [0, halo H): completed with the previous tiles' carry
+        const int hend = hH < TFH ? hH : TFH;
+        for (int u = tid; u < hend; u += NT)
+            if (u >= ua && u < ub) xo[u] = ola_sum(c, u, (!c.first && u < NH) ? c.carry_in[u] : (T)0);
+        // (3) the tail handed on
+        if (!c.last)
+        for (int v = tid; v < NH; v += NT)
+            c.carry_out[v] = ola_sum(c, TFH + v, (!c.first && TFH + v < NH) ? c.carry_in[TFH + v] : (T)0);
+    }
+    VHD static void gather_s(const InvCtx<T> &c, int tid) {
+        switch (c.a.halo) {
+            case 1: gather_s_t<1>(c, tid); break;
+            case 3: gather_s_t<3>(c, tid); break;
+            default: gather_s_t<-1>(c, tid); break;
         }
     }
 };
