@@ -744,6 +744,9 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
     // loads the R1 mirror bins as well (they are the other threads' own bins: L1 / L2 hits) and merges only its
     // own group -- half the registers, twice the resident warps, one code path for every group (k = 0 pairs with
     // the Nyquist bin and k = Mc / 2 with itself through the same formula).
+#ifndef VEILS_P1U_BATCH
+#define VEILS_P1U_BATCH 8
+#endif
     VHD static C merge_one(const T *twp, int k, C Xk, C Xp) {
         const C Xm = conj(Xp);
         const C E = Xk + Xm, Dm = Xk - Xm;
@@ -763,6 +766,21 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
         for (int j = sub; j < L1; j += NSUB) {
             C v[R1];
             if (live) {
+#if VEILS_P1U_BATCH
+                // batches of VEILS_P1U_BATCH own + mirror bins in flight, merged before the next loads are issued
+                constexpr int HB = R1 >= VEILS_P1U_BATCH ? VEILS_P1U_BATCH : R1;
+#pragma unroll
+                for (int a0 = 0; a0 < R1; a0 += HB) {
+                    C w[HB];
+#pragma unroll
+                    for (int a = 0; a < HB; ++a) {
+                        v[a0 + a] = load_bin<ONES>(p, sb, rb, j + L1 * (a0 + a));
+                        w[a] = load_bin<ONES>(p, sb, rb, MC - (j + L1 * (a0 + a)));
+                    }
+#pragma unroll
+                    for (int a = 0; a < HB; ++a) v[a0 + a] = merge_one(twp0, j + L1 * (a0 + a), v[a0 + a], w[a]);
+                }
+#else
                 C w[R1];
 #pragma unroll
                 for (int a = 0; a < R1; ++a) {
@@ -771,6 +789,7 @@ struct Inv : Geo<T, LOGMC, TF_, NSUB_> {
                 }
 #pragma unroll
                 for (int a = 0; a < R1; ++a) v[a] = merge_one(twp0, j + L1 * a, v[a], w[a]);
+#endif
             } else {
 #pragma unroll
                 for (int a = 0; a < R1; ++a) v[a] = mk<T>(0, 0);
