@@ -223,7 +223,9 @@ struct FwdLaunch {
         // measured (profiles/r1c_ablation.txt): +3 % for f64; the f32 tile kernels (mfft >= 2048 here) are
         // 5 % faster with their plain stores, so only f64 takes the staged path
         // (padded narrow tiles: their rows are not 128-byte aligned, which a tensor-map source must be)
-        bool stage = sizeof(T) == 8 && p.mode >= 2 && p.batch < (1LL << 31) && !K::GEO::PADR && !VEILS_ENV_ONCE("VEILS_PK_NO_TMA", 0);
+        // round 2: with two CTAs per SM (mfft <= 512: rows of 16 / 32 slices = 256 / 512-byte runs) the plain stores win
+        // (c2 geometry in f64: 55.0 -> 61.0 %); the narrow tiles of mfft >= 1024 keep the staged path (c1, c5: 4-7 % better)
+        bool stage = sizeof(T) == 8 && LOGMC >= 9 && p.mode >= 2 && p.batch < (1LL << 31) && !K::GEO::PADR && !VEILS_ENV_ONCE("VEILS_PK_NO_TMA", 0);
         if (stage) {
             // complex f64 elements are 16 bytes: described as pairs of 8-byte elements
             const int mul = (!p.spectrogram && sizeof(T) == 8) ? 2 : 1;
