@@ -156,7 +156,10 @@ inline void pk_inv_chunks(InvArgs<float> &a, const InvParams &p, int tf, int64_t
     a.qh0 = fdiv64(p.k0 + p.mid, p.H);
     a.qh1 = fdiv64(p.k1 - 1 + p.mid, p.H);
     const int64_t Q = a.qh1 - a.qh0 + 1;
-    int ct = (50 * a.halo + tf - 1) / tf;              // halo re-computation <= ~2 % of a chunk
+#ifndef VEILS_CHUNK_HALO_FACTOR
+#define VEILS_CHUNK_HALO_FACTOR 50
+#endif
+    int ct = (VEILS_CHUNK_HALO_FACTOR * a.halo + tf - 1) / tf;   // halo re-computation <= ~2 % of a chunk
     if (ct < 2) ct = 2;
     if (ct > 64) ct = 64;
     auto cps = [&](int c) { const int64_t lc = (int64_t)tf * c - a.halo; return (Q + lc - 1) / lc; };

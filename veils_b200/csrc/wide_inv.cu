@@ -35,7 +35,10 @@ struct InvLaunch {
         if (e != cudaSuccess) return e;
         // streaming overlap-add: chunks of `ct` tiles; the first tile of a chunk re-computes `halo` slices
         const int64_t Q = a.qh1 - a.qh0 + 1;
-        int ct = (50 * 4 + TF - 1) / TF;                   // halo re-computation <= ~2 % of a chunk
+#ifndef VEILS_CHUNK_HALO_FACTOR
+#define VEILS_CHUNK_HALO_FACTOR 50
+#endif
+        int ct = (VEILS_CHUNK_HALO_FACTOR * 4 + TF - 1) / TF;      // halo re-computation <= ~2 % of a chunk
         if (ct > 64) ct = 64;
         auto cps = [&](int c) { const int64_t lc = (int64_t)TF * c - 4; return (Q + lc - 1) / lc; };
         while (ct > 2 && prm->batch * cps(ct) < 4 * (int64_t)cap) --ct;   // enough chunks to balance the CTAs
