@@ -23,7 +23,7 @@ __device__ __forceinline__ void stage_tab(unsigned char *dst, const unsigned cha
 // Persistent forward kernel.  Shared memory: work[LC][TF] | staged samples | plan blob.
 template <typename T, int TF>
 __global__ void __launch_bounds__(SM_NT, VEILS_SMOOTH_MINB) smooth_fwd_kernel(const __grid_constant__ FwdArgs<T> args, const int64_t total,
-                                                           const int xin_bytes) {
+                                                           const int xin_bytes, const int dbuf) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     FwdCtx<T> c;
@@ -34,8 +34,11 @@ __global__ void __launch_bounds__(SM_NT, VEILS_SMOOTH_MINB) smooth_fwd_kernel(co
     // would be a generic pointer: LD instead of LDS in pass 1)
     T *const xin0 = reinterpret_cast<T *>(q);
     const int xin_elems = xin_bytes / (int)sizeof(T);
-    c.tab = q + 2 * xin_bytes;
-    stage_tab(q + 2 * xin_bytes, args.tab, args.lay.bytes, tid);
+    // dbuf: two staging buffers (the next tile is staged while this one is transformed); else one buffer, re-filled
+    // as soon as pass 1 has read it (the wider tile that then fits half an SM is worth more than the earlier prefetch)
+    const int nbuf = dbuf ? 2 : 1;
+    c.tab = q + nbuf * xin_bytes;
+    stage_tab(q + nbuf * xin_bytes, args.tab, args.lay.bytes, tid);
     // (signal, tile) of work item w, advanced by gridDim.x per iteration without a 64-bit division
     c.b = blockIdx.x / args.ptiles;
     c.pt = blockIdx.x - c.b * args.ptiles;
@@ -51,16 +54,21 @@ __global__ void __launch_bounds__(SM_NT, VEILS_SMOOTH_MINB) smooth_fwd_kernel(co
         __syncthreads();                   // this tile's samples (and the tables) are in place
         int64_t nb = c.b + db, npt = c.pt + dp;
         if (npt >= args.ptiles) { npt -= args.ptiles; ++nb; }
-        if (w + gridDim.x < total) {       // stage the next tile into the other buffer while this one is transformed
-            FwdCtx<T> cn = c;
-            cn.b = nb; cn.pt = npt; cn.xin = xin0 + (it ^ 1) * xin_elems;
+        const bool more = w + gridDim.x < total;
+        FwdCtx<T> cn = c;
+        cn.b = nb; cn.pt = npt; cn.xin = xin0 + (dbuf ? (it ^ 1) * xin_elems : 0);
+        if (more && dbuf) {                // stage the next tile into the other buffer while this one is transformed
             Fwd<T, TF>::stage(cn, tid, SM_NT);
             p2::cp_async_commit();
         }
-        c.xin = xin0 + it * xin_elems;
+        c.xin = xin0 + (dbuf ? it * xin_elems : 0);
         for (int p = 0; p < args.s.np; ++p) {
             Fwd<T, TF>::pass(c, p, tid, SM_NT);
             __syncthreads();
+            if (p == 0 && more && !dbuf) { // single buffer: free once pass 1 has read it
+                Fwd<T, TF>::stage(cn, tid, SM_NT);
+                p2::cp_async_commit();
+            }
         }
         Fwd<T, TF>::store(c, tid, SM_NT);
         c.b = nb;
@@ -134,14 +142,15 @@ template <typename T> size_t ola_bytes_of(const Shape &s, int tf) {
     return (size_t)al16((int64_t)sizeof(T) * tf * ostride_of<T>(s.N, s.H));
 }
 // shared memory without / with the plan blob
-template <typename T> void smem_of(const Shape &s, int tf, bool inverse, size_t *core, size_t *with_tab) {
+template <typename T> void smem_of(const Shape &s, int tf, bool inverse, size_t *core, size_t *with_tab, bool dbuf = true) {
     const size_t work = sizeof(cx<T>) * (size_t)s.LC * tf;
     *core = work + (inverse ? ola_bytes_of<T>(s, tf) + (size_t)tf * sizeof(cx<T>) + 16   // + landed Nyquist row
-                            : 2 * xin_bytes_of<T>(s, tf));                                // forward: double-buffered staging
+                            : (dbuf ? 2 : 1) * xin_bytes_of<T>(s, tf));                   // forward: (double-)buffered staging
     *with_tab = *core + (size_t)tab_layout<T>(s, inverse).bytes;
 }
-// slices per tile: the wide tile when two CTAs of it fit an SM, else the narrow one, else whatever fits (plan blob included)
-template <typename T> int pick_tf(const Shape &s, bool inverse) {
+// slices per tile: the wide tile when two CTAs of it fit an SM, else the narrow one, else whatever fits (plan blob included).
+// Forward: a tile width is tried with two staging buffers first, then with one (*dbuf).
+template <typename T> int pick_tf(const Shape &s, bool inverse, bool *dbuf = nullptr) {
     const int cand[3] = {sizeof(T) == 4 ? 32 : 16, sizeof(T) == 4 ? 16 : 8, sizeof(T) == 4 ? 8 : 4};
     const int force = VEILS_ENV_ONCE("VEILS_SMOOTH_TF", 0);
     const size_t budgets[2] = {113 * 1024, SM_SMEM_LIMIT};
@@ -151,25 +160,30 @@ template <typename T> int pick_tf(const Shape &s, bool inverse) {
             if (force && tf != force) continue;
             if (inverse && halo_of(s.N, s.H) >= tf) continue;
             if (inverse && bi < 1 && 4 * halo_of(s.N, s.H) > tf) continue;     // more than a quarter of the tile recomputed
-            size_t core, full;
-            smem_of<T>(s, tf, inverse, &core, &full);
-            if (full <= budgets[bi]) return tf;
+            for (int d = 1; d >= (inverse ? 1 : 0); --d) {
+                size_t core, full;
+                smem_of<T>(s, tf, inverse, &core, &full, d != 0);
+                if (full <= budgets[bi]) {
+                    if (dbuf) *dbuf = d != 0;
+                    return tf;
+                }
+            }
         }
     return 0;
 }
 
 template <typename T, int TF>
-cudaError_t launch_fwd(FwdArgs<T> &a, int64_t batch, cudaStream_t st) {
+cudaError_t launch_fwd(FwdArgs<T> &a, int64_t batch, bool dbuf, cudaStream_t st) {
     auto kern = smooth_fwd_kernel<T, TF>;
-    static KernelSlot slot;
+    static KernelSlot slot;                 // ONE slot per kernel function: the shared-memory attribute is per function
     size_t core, smem;
-    smem_of<T>(a.s, TF, false, &core, &smem);
+    smem_of<T>(a.s, TF, false, &core, &smem, dbuf);
     int per_sm = 0, dev = 0;
     cudaError_t e = prepare_kernel(slot, kern, SM_NT, smem, &per_sm, &dev);
     if (e != cudaSuccess) return e;
     a.ptiles = (a.P + TF - 1) / TF;
     const int64_t total = a.ptiles * batch, cap = (int64_t)per_sm * device_sms(dev);
-    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total, (int)xin_bytes_of<T>(a.s, TF));
+    kern<<<(unsigned)(total < cap ? total : cap), SM_NT, smem, st>>>(a, total, (int)xin_bytes_of<T>(a.s, TF), dbuf ? 1 : 0);
     ++g_launch_count;
     return cudaGetLastError();
 }
@@ -221,10 +235,11 @@ cudaError_t smooth_forward(const T *x, void *out, const FwdParams &p, const void
     a.mid = (int)p.mid; a.mode = p.mode; a.spectrogram = p.spectrogram; a.xpad = sm::xpad_of(p.H);
     a.fac2x = p.mode == 3 ? (T)p.fac2x : (T)1;
     constexpr int TFA = sizeof(T) == 4 ? 32 : 16, TFB = sizeof(T) == 4 ? 16 : 8, TFC = sizeof(T) == 4 ? 8 : 4;
-    const int tf = pick_tf<T>(a.s, false);
-    if (tf == TFA) return launch_fwd<T, TFA>(a, p.batch, st);
-    if (tf == TFB) return launch_fwd<T, TFB>(a, p.batch, st);
-    if (tf == TFC) return launch_fwd<T, TFC>(a, p.batch, st);
+    bool dbuf = true;
+    const int tf = pick_tf<T>(a.s, false, &dbuf);
+    if (tf == TFA) return launch_fwd<T, TFA>(a, p.batch, dbuf, st);
+    if (tf == TFB) return launch_fwd<T, TFB>(a, p.batch, dbuf, st);
+    if (tf == TFC) return launch_fwd<T, TFC>(a, p.batch, dbuf, st);
     return cudaErrorNotSupported;
 }
 template <typename T>
