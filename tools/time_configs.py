@@ -37,7 +37,8 @@ for name, win, hop, mode, scale, prec, B, n, spec in CASES:
     ldp = (P + q - 1) // q * q
     S = torch.empty((B, F, ldp), dtype=rdt if spec else cdt, device=dev)
     def t(fn, reps=5):
-        fn(); fn(); torch.cuda.synchronize()
+        assert fn() == 0, "launch failed: " + (L.veils_last_error() or b"").decode()
+        fn(); torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(reps): fn()

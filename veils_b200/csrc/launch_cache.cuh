@@ -47,7 +47,17 @@ inline cudaError_t prepare_kernel(KernelSlot &slot, KernT kern, int threads, siz
         const long long c = slot.v[dev].load(std::memory_order_acquire) - 1;
         if (c >= 0 && (c & ~0xffLL) == key_hi) { *per_sm = (int)(c & 0xff); return cudaSuccess; }
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // The attribute is per FUNCTION and a smaller value LOWERS it: plans with different shared-memory needs that share
+    // an instantiation (or two host threads) must not shrink it under each other -- always opt in to the device maximum.
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev < 0 ? 0 : dev);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    const int max_dyn = optin - (int)fa.sharedSizeBytes;               // the kernel's static shared memory counts too
+    if ((long long)smem > (long long)max_dyn) return cudaErrorInvalidConfiguration;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn);
     if (e != cudaSuccess) return e;
     int n = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
