@@ -101,3 +101,19 @@ def test_randomized_mixed_radix_geometry(prec, tol):
                 yr2 = np.stack([o.istft(q.astype(np.complex128), k0, k1) for q in S0])
                 assert rel_err(s.istft(S0, k0, k1), yr2) <= tol, (M, N, H, mode, ps, n, k0, k1)
     assert seen >= 20
+
+
+def test_plans_sharing_a_kernel_with_different_shared_memory():
+    """Two plans that run the SAME kernel instantiation with different shared-memory sizes, interleaved: the per-function
+    shared-memory attribute must never be lowered under a plan that needs more (regression: 'invalid argument')."""
+    rng = np.random.default_rng(99)
+    plans = []
+    for m, hop in ((600, 150), (400, 160), (320, 80)):
+        win = 0.5 * (1 - np.cos(2 * np.pi * np.arange(m) / m))
+        plans.append((StandaloneSTFT(win, hop, 16000.0, precision="f32"), OracleSTFT(win, hop, 16000.0)))
+    x = rng.uniform(-1, 1, (2, 20000)).astype(np.float32)
+    for _ in range(2):
+        for st, o in plans + plans[::-1]:
+            S = st.stft(x)
+            assert rel_err(S[1], o.stft(x[1].astype(np.float64))) <= 2e-5
+            assert np.max(np.abs(st.istft(S)[:, :20000] - x)) <= 1e-4
