@@ -19,6 +19,9 @@ namespace p2 {
 #ifndef VEILS_F64_L8_TF
 #define VEILS_F64_L8_TF 16
 #endif
+#ifndef VEILS_F64_L10_TF
+#define VEILS_F64_L10_TF 8
+#endif
 struct Cfg {
     int logmc;   // log2(mfft / 2)
     int tf;      // slices per tile
@@ -38,7 +41,7 @@ inline bool cfg_for(int64_t M, int precision, Cfg *c) {
     if (lm < 5 || lm > 13) return false;              // mfft in [32, 8192]
     c->logmc = lm - 1;
     static const int tf32[13] = {0, 0, 0, 0, 32, 32, 32, 32, 32, 32, 16, 8, 4};
-    static const int tf64[13] = {0, 0, 0, 0, 32, 32, 32, 32, VEILS_F64_L8_TF, 16, 8, 4, 2};
+    static const int tf64[13] = {0, 0, 0, 0, 32, 32, 32, 32, VEILS_F64_L8_TF, 16, VEILS_F64_L10_TF, 4, 2};
     c->tf = precision == 0 ? tf32[c->logmc] : tf64[c->logmc];
     int np, r1, r2, r3;
     fac_of(c->logmc, &np, &r1, &r2, &r3);
@@ -243,7 +246,7 @@ inline auto dispatch(int precision, int logmc, FN &fn) -> decltype(fn.template r
         switch (logmc) {
             VEILS_P2_CASE(double, 4, 32) VEILS_P2_CASE(double, 5, 32) VEILS_P2_CASE(double, 6, 32)
             VEILS_P2_CASE(double, 7, 32) VEILS_P2_CASE(double, 8, VEILS_F64_L8_TF) VEILS_P2_CASE(double, 9, 16)
-            VEILS_P2_CASE(double, 10, 8) VEILS_P2_CASE(double, 11, 4) VEILS_P2_CASE(double, 12, 2)
+            VEILS_P2_CASE(double, 10, VEILS_F64_L10_TF) VEILS_P2_CASE(double, 11, 4) VEILS_P2_CASE(double, 12, 2)
         }
     }
     return decltype(fn.template run<float, 4, 32, 2>())(-1);
